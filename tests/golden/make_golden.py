@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Runs only in the build container (needs /root/reference; the GPU box never runs it).
+It imports the reference's own modules (noise_model, mcsim, wd_sortof_fast_implementation,
+generate_fig4_kendallrankanalysis' nested helpers) with sys.modules stubs for the plotting /
+optimiser packages that are not installed, runs them on seeded numpy legacy-RNG streams and
+stores inputs + outputs as small .npz files.  Nothing here is product code.
+
+    python tests/golden/make_golden.py
+"""
+import ast
+import json
+import os
+import sys
+import tempfile
+import types
+from unittest.mock import MagicMock
+
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+sys.dont_write_bytecode = True
+
+for name in ["matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.ticker", "seaborn",
+             "IPython", "IPython.display", "skquant", "skquant.opt", "SQSnobFit"]:
+    sys.modules[name] = MagicMock()
+sys.path.insert(0, REF)
+
+import noise_model as ref_nm  # noqa: E402
+import wd_sortof_fast_implementation as ref_wd  # noqa: E402
+import mcsim as ref_mc  # noqa: E402
+from scipy.stats import kendalltau  # noqa: E402
+
+
+def load_json(path):
+    return json.load(open(path, "rb"))
+
+
+# ---------------------------------------------------------------------------------------------
+# 1. Known-answer fixtures stored by the reference itself
+# ---------------------------------------------------------------------------------------------
+def make_kat_bestfid():
+    """noisy_analysis/lbfgs_spin_*_in: best_fid[i] is the nominal fidelity of controller[i]."""
+    out = {}
+    meta = []
+    for fn in sorted(os.listdir(f"{REF}/noisy_analysis")):
+        if not fn.startswith("lbfgs_spin_"):
+            continue
+        _, _, n, io, _ = fn.split("_")
+        n = int(n); i, o = (int(v) for v in io.split("-"))
+        rec = load_json(f"{REF}/noisy_analysis/{fn}")["lbfgs"][str(n)]
+        ctrl = np.array(rec["controller"], dtype=np.float64)
+        best = np.array(rec["best_fid"], dtype=np.float64)
+        key = f"n{n}_{i}_{o}"
+        out[key + "_ctrl"] = ctrl
+        out[key + "_best_fid"] = best
+        meta.append((key, n, i, o))
+    out["meta"] = np.array(meta)
+    np.savez_compressed(f"{OUT}/kat_bestfid.npz", **out)
+    print("kat_bestfid:", [m[0] for m in meta])
+
+
+def make_kat_mc_zero(per_group=60):
+    """sigma_sim = 0 rows of the stored .mc caches against the .le controllers."""
+    exp = f"{REF}/experiments/pipeline_nmplus2"
+    nl = "[0.   0.01 0.02 0.03 0.04 0.05 0.06 0.07 0.08 0.09 0.1 ]"
+    out = {}
+    meta = []
+    for n, i, o in [(4, 0, 2), (4, 0, 3), (5, 0, 2), (5, 0, 4), (6, 0, 3)]:
+        le = load_json(f"{exp}/ppo_spin_{n}_{i}-{o}_c_1000.le")
+        for tn in ["0.0", "0.03"]:
+            mc = load_json(f"{exp}/ppo_spin_{n}_{i}-{o}_c_1000.le_tn{tn}_br_1_nlvl{nl}.mc")
+            for algo in mc:
+                keyname = str(n) if algo == "lbfgs" else tn
+                if keyname not in le.get(algo, {}):
+                    continue
+                conts = le[algo][keyname]["controller"][:per_group]
+                ctrl = np.array([c if c is not None else [np.nan] * (n + 1) for c in conts], dtype=np.float64)
+                fid0 = np.array(mc[algo], dtype=np.float64)[0, :len(conts), 0]
+                key = f"n{n}_{i}_{o}_{algo}_tn{tn}"
+                out[key + "_ctrl"] = ctrl
+                out[key + "_fid0"] = fid0
+                meta.append((key, n, i, o))
+    out["meta"] = np.array(meta)
+    np.savez_compressed(f"{OUT}/kat_mc_zero.npz", **out)
+    print("kat_mc_zero groups:", len(meta))
+
+
+def make_kat_mcm_pairs(ncol=200):
+    """N=7 .mc/.mcm pairs (B=1) pin the statistics stage exactly."""
+    exp = f"{REF}/experiments/pipeline_nmplus2"
+    nl = "[0.   0.01 0.02 0.03 0.04 0.05 0.06 0.07 0.08 0.09 0.1 ]"
+    base = f"{exp}/ppo_spin_7_0-6_c_1000.le_tn0.02_br_1_nlvl{nl}"
+    if not (os.path.exists(base + ".mc") and os.path.exists(base + ".mcm")):
+        print("kat_mcm_pairs: files missing, skipped")
+        return
+    mc = load_json(base + ".mc"); mcm = load_json(base + ".mcm")
+    out = {}
+    algo = "nmplus"
+    out["fids"] = np.array(mc[algo], dtype=np.float64)[:, :ncol, :]
+    names = list(mcm[algo].keys())
+    out["names"] = np.array(names)
+    out["metrics"] = np.array([np.array(mcm[algo][k], dtype=np.float64)[:, :ncol] for k in names])
+    np.savez_compressed(f"{OUT}/kat_mcm_pairs.npz", **out)
+    print("kat_mcm_pairs:", out["fids"].shape, names)
+
+
+# ---------------------------------------------------------------------------------------------
+# 2. Seeded runs of the unmodified reference (sigma > 0 has no stored goldens)
+# ---------------------------------------------------------------------------------------------
+def run_reference_mcsim(n, i, o, controllers, noises, bootreps, seed, numcontrollers, algo="lbfgs"):
+    """Drive the real MCDataSim.get_metrics_dict in a temp experiments/ tree and recover the
+    standard-normal stream it consumed (np.random.normal(scale=s) == s*standard_normal())."""
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(f"{td}/experiments/golden")
+        keyname = str(n)
+        conts = [None if (isinstance(c, float) and np.isnan(c)) else list(map(float, c)) for c in controllers]
+        json.dump({algo: {keyname: {"controller": conts}}},
+                  open(f"{td}/experiments/golden/ppo_spin_{n}_{i}-{o}_c_{numcontrollers}", "w"))
+        os.chdir(td)
+        try:
+            sim = ref_mc.MCDataSim(experiment_name="golden", Nspin=n, inspin=i, outspin=o, noises=noises,
+                                   bootreps=bootreps, numcontrollers=numcontrollers, topk=10)
+            np.random.seed(seed)
+            metrics = sim.get_metrics_dict(None, noises, algoname=algo)
+            mcname = sim.get_mcname(None, noises)
+            fids = np.array(load_json(mcname)[algo], dtype=np.float64)
+        finally:
+            os.chdir(cwd)
+    # reconstruct the stream: one discarded draw per sigma level (mcsim.py:425), then 3N per
+    # evaluation; NaN-padded controllers (index >= len) consume nothing (mcsim.py:369-374).
+    # JSON `null` controllers are *not* np.nan -> the reference would crash; we never feed those.
+    K = 3 * n
+    S = len(noises); C = numcontrollers; B = bootreps
+    rs = np.random.RandomState(seed)
+    normals = np.zeros((S, C, B, K))
+    for s in range(S):
+        rs.standard_normal()
+        for c in range(C):
+            if c < len(controllers):
+                normals[s, c] = rs.standard_normal((B, K))
+    ctrl = np.full((C, n + 1), np.nan)
+    ctrl[:len(controllers)] = np.array(controllers, dtype=np.float64)
+    names = list(metrics[algo].keys())
+    mt = np.array([np.array(metrics[algo][k], dtype=np.float64) for k in names])
+    return dict(ctrl=ctrl, sigmas=np.array(noises, dtype=np.float64), normals=normals, fids=fids,
+                metric_names=np.array(names), metrics=mt, nio=np.array([n, i, o]), seed=seed,
+                alpha=1 - 0.95)
+
+
+def extract_nested(src_path, names):
+    """Pull nested helper functions out of generate_fig4_kendallrankanalysis.py and exec them
+    unchanged (they are closures inside plot_kendalltaus and cannot be imported)."""
+    tree = ast.parse(open(src_path).read())
+    found = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            found[node.name] = node
+    ns = {"np": np, "kendalltau": kendalltau, "vn_test": ref_mc.vn_test,
+          "self": types.SimpleNamespace(get_ranks=ref_mc.MCDataSim.get_ranks)}
+    for nm in names:
+        mod = ast.Module(body=[found[nm]], type_ignores=[])
+        exec(compile(mod, src_path, "exec"), ns)
+    return ns
+
+
+def make_replay():
+    noises = np.linspace(0, 0.1, 11)
+    lb = lambda n, i, o: load_json(f"{REF}/noisy_analysis/lbfgs_spin_{n}_{i}-{o}_in")["lbfgs"][str(n)]["controller"]
+    cases = {
+        # config 1: N=4 0->2, the 100 LBFGS controllers, padded with 4 NaN rows
+        "replay_n4_0_2": dict(n=4, i=0, o=2, controllers=lb(4, 0, 2), bootreps=6, seed=101, numcontrollers=104),
+        "replay_n5_0_4": dict(n=5, i=0, o=4, controllers=lb(5, 0, 4)[:40], bootreps=10, seed=102, numcontrollers=40),
+        "replay_n6_0_3": dict(n=6, i=0, o=3, controllers=lb(6, 0, 3)[:40], bootreps=10, seed=103, numcontrollers=40),
+        # config 3: N=7 0->6, all 57 LBFGS controllers in the mount
+        "replay_n7_0_6": dict(n=7, i=0, o=6, controllers=lb(7, 0, 6), bootreps=12, seed=104, numcontrollers=57),
+    }
+    ns = extract_nested(f"{REF}/generate_fig4_kendallrankanalysis.py",
+                        ["get_ranks_clustered_little", "jkt_or_ordinaltau_pairwise"])
+    for name, kw in cases.items():
+        d = run_reference_mcsim(noises=noises, **kw)
+        # ranking / Kendall stage with the reference's own functions on the reference's RIM matrix
+        W = d["metrics"][list(d["metric_names"]).index(r'$W(.,\delta(x-1))$')]
+        ok = ~np.isnan(W[0])
+        Wc = W[:, ok]
+        d["ranks_row0"] = ref_mc.MCDataSim.get_ranks(Wc[0])
+        d["clustered_row3"] = ns["get_ranks_clustered_little"](Wc[3], r=0.05 * (Wc[3].max() - Wc[3].min()))
+        d["kendall"] = np.array(ns["jkt_or_ordinaltau_pairwise"](Wc, alpha=0.05))
+        np.savez_compressed(f"{OUT}/{name}.npz", **d)
+        print(name, d["fids"].shape, "kendall", d["kendall"].shape)
+
+
+def make_wd_kats():
+    """Embedded unit-test vectors of wd_sortof_fast_implementation.py:182-311, evaluated by the
+    reference's own functions."""
+    rs = np.random.RandomState(7)
+    vecs = {
+        "X": np.array(ref_wd.testwdimplementation.X),
+        "normal_hi": rs.normal(0.85, 0.02, size=10000),
+        "normal_clip": rs.normal(0.85, 0.8, size=10000).clip(min=0, max=1),
+        "normal_10": rs.normal(0.67, 0.02, size=10),
+        "uniform_10": rs.uniform(size=10),
+        "ones": np.array([1., 1, 1, 1, 1]),
+        "mixed": np.array([1., 0, 1, 1, 0]),
+        "zeros": np.array([0., 0, 0, 0, 0]),
+        "scalar": np.array([0.76]),
+    }
+    out = {}
+    for k, v in vecs.items():
+        out[k] = v
+        out[k + "_wd"] = ref_wd.wd_from_ideal(v.copy())
+        out[k + "_wd0"] = ref_wd.wd_from_ideal_zero(v.copy())
+        out[k + "_rim1"] = ref_wd.RIM_p(v.copy(), 1)
+        out[k + "_rim2"] = ref_wd.RIM_p(v.copy(), 2)
+        out[k + "_rim3"] = ref_wd.RIM_p(v.copy(), 3)
+    out["dkw_0.05_100"] = ref_wd.compute_dkw_error(1 - 0.95, 100)
+    out["names"] = np.array(list(vecs.keys()))
+    np.savez_compressed(f"{OUT}/kat_wd.npz", **out)
+    print("kat_wd:", list(vecs.keys()))
+
+
+def make_real2_and_zz():
+    """Optimiser-side variant: LBFGS.fidelity_ss with the real 2-draw noise (qnewton.py:366-423)
+    and the Heisenberg/Z diagonal (qnewton.py:148-150), run through the real qnewton.LBFGS."""
+    import qnewton as ref_q
+    out = {}
+    for tag, n, i, o, zz in [("n5", 5, 0, 4, False), ("n6zz", 6, 0, 3, True), ("n16zz", 16, 0, 15, True)]:
+        env = ref_q.LBFGS(n, i, o, noise=0.05, heisenberg_int=zz, opt_train_size=2)
+        rs = np.random.RandomState(55 + n)
+        C, B = 12, 8
+        ctrl = np.concatenate([rs.uniform(-10, 10, (C, n)), rs.uniform(1, 30, (C, 1))], axis=1)
+        np.random.seed(900 + n)
+        fids = np.zeros((C, B))
+        for c in range(C):
+            for b in range(B):
+                fids[c, b] = env.fidelity_ss(ctrl[c], ham_noisy=True)
+        normals = np.random.RandomState(900 + n).standard_normal((C, B, 2 * n))
+        out[tag + "_ctrl"] = ctrl; out[tag + "_fids"] = fids; out[tag + "_normals"] = normals
+        out[tag + "_meta"] = np.array([n, i, o, int(zz)]); out[tag + "_sigma"] = 0.05
+        out[tag + "_nominal"] = np.array([env.fidelity_ss(ctrl[c]) for c in range(C)])
+    np.savez_compressed(f"{OUT}/replay_real2_zz.npz", **out)
+    print("replay_real2_zz done")
+
+
+def make_large_n():
+    """N=16 / N=32 (scaled configs 4/5) and the RL environment KATs (N=10, 3, 6) through the
+    reference's structured_perturbation.evaluate_noisy_fidelity."""
+    out = {}
+    for n in (10, 16, 32):
+        rs = np.random.RandomState(20221 + n)
+        C, B = 10, 6
+        ctrl = np.concatenate([rs.uniform(-10, 10, (C, n)), rs.uniform(1, 30, (C, 1))], axis=1)
+        model = ref_nm.structured_perturbation(Nspin=n, inspin=0, outspin=n - 1)
+        np.random.seed(300 + n)
+        model.rng(scale=0.05)
+        fids = np.zeros((C, B))
+        for c in range(C):
+            for b in range(B):
+                fids[c, b] = model.evaluate_noisy_fidelity(ctrl[c], True)
+        rs2 = np.random.RandomState(300 + n); rs2.standard_normal()
+        out[f"n{n}_ctrl"] = ctrl; out[f"n{n}_fids"] = fids
+        out[f"n{n}_normals"] = rs2.standard_normal((C, B, 3 * n))
+        out[f"n{n}_nominal"] = np.array([model.evaluate_noisy_fidelity(ctrl[c], False) for c in range(C)])
+    out["sigma"] = 0.05
+    np.savez_compressed(f"{OUT}/replay_large_n.npz", **out)
+    print("replay_large_n done")
+
+
+if __name__ == "__main__":
+    make_kat_bestfid()
+    make_kat_mc_zero()
+    make_kat_mcm_pairs()
+    make_wd_kats()
+    make_replay()
+    make_real2_and_zz()
+    make_large_n()
