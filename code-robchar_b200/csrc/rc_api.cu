@@ -1,0 +1,116 @@
+// Host-buffer pipeline entry point (what MCDataSim.get_metrics_dict computes from scratch,
+// mcsim.py:463-510) and the FP64 roofline micro-benchmark.
+#include "rc_common.cuh"
+
+using namespace rc;
+
+namespace rc {
+
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t st;
+    explicit DevBuf(cudaStream_t s) : st(s) {}
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    template <class T> T* as() { return (T*)p; }
+};
+
+// 8 independent dependent-FMA chains per thread; 2 flops per DFMA.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[0] = s;  // keep the chains alive
+}
+
+}  // namespace rc
+
+extern "C" int rc_fp64_peak_tflops(double* tflops, void* stream) {
+    if (!tflops) return set_error(RC_ERR_NULL, "rc_fp64_peak_tflops: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf out(st);
+    RC_CUDA_TRY(out.alloc(8));
+    const int sm = device_sm_count();
+    const int blocks = sm * 8, threads = 256, iters = 1 << 15;
+    cudaEvent_t e0, e1;
+    RC_CUDA_TRY(cudaEventCreate(&e0));
+    RC_CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        RC_CUDA_TRY(cudaEventRecord(e0, st));
+        dfma_peak_kernel<<<blocks, threads, 0, st>>>(out.as<double>(), iters, 0.999999, 1e-7);
+        RC_CUDA_TRY(cudaEventRecord(e1, st));
+        RC_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        RC_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return RC_OK;
+}
+
+extern "C" int rc_mc_sweep_host(const double* ctrl_host, int64_t C, int nspin, int inspin, int outspin,
+                                const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
+                                int64_t c_offset, int64_t b_offset, const double* replay_host, double dkw_eps,
+                                int fused, double* fids_host, double* stats_host, void* stream) {
+    if (nspin < 2 || nspin > RC_MAX_NSPIN) return set_error(RC_ERR_BAD_ARG, "nspin=%d outside [2,%d]", nspin, RC_MAX_NSPIN);
+    if (C < 0 || S < 0 || B < 1) return set_error(RC_ERR_BAD_ARG, "rc_mc_sweep_host: bad sizes C=%lld S=%d B=%lld", (long long)C, S, (long long)B);
+    const long long nseg = (long long)S * C, total = nseg * B;
+    if (total == 0) return RC_OK;
+    if (!ctrl_host || !sigma_host) return set_error(RC_ERR_NULL, "rc_mc_sweep_host: null ctrl/sigma");
+    if (!stats_host && !fids_host) return set_error(RC_ERR_NULL, "rc_mc_sweep_host: no output requested");
+    if (fused && fids_host) return set_error(RC_ERR_BAD_ARG, "rc_mc_sweep_host: fused mode does not materialise fidelities");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = (model == RC_MODEL_COMPLEX3 ? 3 : 2) * nspin;
+    DevBuf ctrl(st), sigma(st), replay(st), fids(st), stats(st), ws(st), counters(st);
+    RC_CUDA_TRY(ctrl.alloc((size_t)C * (nspin + 1) * 8));
+    RC_CUDA_TRY(sigma.alloc((size_t)S * 8));
+    RC_CUDA_TRY(counters.alloc(16));
+    RC_CUDA_TRY(cudaMemsetAsync(counters.p, 0, 16, st));
+    RC_CUDA_TRY(cudaMemcpyAsync(ctrl.p, ctrl_host, (size_t)C * (nspin + 1) * 8, cudaMemcpyHostToDevice, st));
+    RC_CUDA_TRY(cudaMemcpyAsync(sigma.p, sigma_host, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+    if (replay_host) {
+        RC_CUDA_TRY(replay.alloc((size_t)total * K * 8));
+        RC_CUDA_TRY(cudaMemcpyAsync(replay.p, replay_host, (size_t)total * K * 8, cudaMemcpyHostToDevice, st));
+    }
+    unsigned long long* nonconv = counters.as<unsigned long long>();
+    unsigned long long* illegal = nonconv + 1;
+    if (stats_host) RC_CUDA_TRY(stats.alloc((size_t)RC_NUM_STATS * nseg * 8));
+    int rcode;
+    if (fused) {
+        size_t wb = rc_fidelity_stats_workspace_bytes(nseg, B);
+        RC_CUDA_TRY(ws.alloc(wb));
+        rcode = rc_fidelity_stats(ctrl.as<double>(), C, nspin, inspin, outspin, sigma.as<double>(), S, B, model, zz, seed,
+                                  c_offset, b_offset, replay_host ? replay.as<double>() : nullptr, dkw_eps,
+                                  stats.as<double>(), nonconv, ws.p, wb, st);
+        if (rcode) return rcode;
+    } else {
+        RC_CUDA_TRY(fids.alloc((size_t)total * 8));
+        rcode = rc_fidelity_mc(ctrl.as<double>(), C, nspin, inspin, outspin, sigma.as<double>(), S, B, model, zz, seed,
+                               c_offset, b_offset, replay_host ? replay.as<double>() : nullptr, fids.as<double>(), nonconv, st);
+        if (rcode) return rcode;
+        // the reference dumps the UNSORTED tensor to .mc before any metric sorts it (mcsim.py:457-459)
+        if (fids_host) RC_CUDA_TRY(cudaMemcpyAsync(fids_host, fids.p, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+        if (stats_host) {
+            size_t wb = rc_stats_workspace_bytes(nseg, B);
+            if (wb == 0) return set_error(RC_ERR_BAD_ARG, "rc_mc_sweep_host: B too large for the sort path");
+            RC_CUDA_TRY(ws.alloc(wb));
+            rcode = rc_stats(fids.as<double>(), nseg, B, dkw_eps, stats.as<double>(), nullptr, illegal, ws.p, wb, st);
+            if (rcode) return rcode;
+        }
+    }
+    if (stats_host)
+        RC_CUDA_TRY(cudaMemcpyAsync(stats_host, stats.p, (size_t)RC_NUM_STATS * nseg * 8, cudaMemcpyDeviceToHost, st));
+    unsigned long long hc[2] = {0, 0};
+    RC_CUDA_TRY(cudaMemcpyAsync(hc, counters.p, 16, cudaMemcpyDeviceToHost, st));
+    RC_CUDA_TRY(cudaStreamSynchronize(st));
+    if (hc[0]) return set_error(RC_ERR_NONCONV, "eigensolver did not converge for %llu evaluations (NaN written)", hc[0]);
+    if (hc[1]) return set_error(RC_ERR_ILLEGAL_FIDS, "illegal fids values - must be in [0,1] (%llu samples)", hc[1]);
+    return RC_OK;
+}

@@ -1,0 +1,277 @@
+// Dispatch of the evolution/fidelity kernels over chain length + the C-ABI entry points
+// rc_fidelity_mc / rc_philox_normals.
+#include <stdlib.h>
+#include <string.h>
+#include "rc_common.cuh"
+#include "rc_fidelity.cuh"
+
+namespace rc {
+
+static thread_local char g_err[512];
+char* last_error_buffer() { return g_err; }
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int device_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+    int sm = 148;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    if (dev >= 0 && dev < 64) cached[dev] = sm;
+    return sm;
+}
+
+#define RC_DECL(n) cudaError_t launch_fid_reg_##n(const FidArgs&, int, cudaStream_t);
+RC_DECL(2) RC_DECL(3) RC_DECL(4) RC_DECL(5) RC_DECL(6) RC_DECL(7) RC_DECL(8) RC_DECL(9) RC_DECL(10)
+RC_DECL(11) RC_DECL(12) RC_DECL(13) RC_DECL(14) RC_DECL(15) RC_DECL(16)
+#undef RC_DECL
+#define RC_DECL(n) cudaError_t launch_fused_reg_##n(const FusedArgs&, int, cudaStream_t);
+RC_DECL(2) RC_DECL(3) RC_DECL(4) RC_DECL(5) RC_DECL(6) RC_DECL(7) RC_DECL(8) RC_DECL(9) RC_DECL(10)
+RC_DECL(11) RC_DECL(12) RC_DECL(13) RC_DECL(14) RC_DECL(15) RC_DECL(16)
+#undef RC_DECL
+
+static fid_launch_fn reg_table[REG_MAX_N + 1] = {
+    nullptr, nullptr, launch_fid_reg_2, launch_fid_reg_3, launch_fid_reg_4, launch_fid_reg_5, launch_fid_reg_6,
+    launch_fid_reg_7, launch_fid_reg_8, launch_fid_reg_9, launch_fid_reg_10, launch_fid_reg_11, launch_fid_reg_12,
+    launch_fid_reg_13, launch_fid_reg_14, launch_fid_reg_15, launch_fid_reg_16};
+
+static fused_launch_fn fused_table[REG_MAX_N + 1] = {
+    nullptr, nullptr, launch_fused_reg_2, launch_fused_reg_3, launch_fused_reg_4, launch_fused_reg_5,
+    launch_fused_reg_6, launch_fused_reg_7, launch_fused_reg_8, launch_fused_reg_9, launch_fused_reg_10,
+    launch_fused_reg_11, launch_fused_reg_12, launch_fused_reg_13, launch_fused_reg_14, launch_fused_reg_15,
+    launch_fused_reg_16};
+
+template <int MODEL, bool REPLAY>
+static cudaError_t launch_smem(const FidArgs& a, int sm_count, cudaStream_t st) {
+    const int threads = 64;
+    size_t smem = (size_t)4 * a.N * threads * sizeof(double);
+    auto kern = fidelity_smem_kernel<MODEL, REPLAY>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    int occ = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    if (err != cudaSuccess) return err;
+    if (occ < 1) occ = 1;
+    long long total = (long long)a.S * a.C * a.B;
+    long long nblk = (total + threads - 1) / threads;
+    long long grid = (long long)sm_count * occ;
+    if (grid > nblk) grid = nblk;
+    if (grid < 1) return cudaSuccess;
+    kern<<<(unsigned)grid, threads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// RC_REG_MAX_N=<n> (environment) moves the register/shared-memory crossover for tuning.
+static int reg_crossover() {
+    static int v = -1;
+    if (v < 0) {
+        const char* s = getenv("RC_REG_MAX_N");
+        v = s ? atoi(s) : REG_MAX_N;
+        if (v > REG_MAX_N) v = REG_MAX_N;
+        if (v < 1) v = 1;
+    }
+    return v;
+}
+
+cudaError_t launch_fidelity(const FidArgs& a, cudaStream_t st) {
+    int sm = device_sm_count();
+    if (a.N <= reg_crossover()) return reg_table[a.N](a, sm, st);
+    const bool replay = a.replay != nullptr;
+    if (a.model == MODEL_COMPLEX3)
+        return replay ? launch_smem<MODEL_COMPLEX3, true>(a, sm, st) : launch_smem<MODEL_COMPLEX3, false>(a, sm, st);
+    return replay ? launch_smem<MODEL_REAL2, true>(a, sm, st) : launch_smem<MODEL_REAL2, false>(a, sm, st);
+}
+
+template <int MODEL, bool REPLAY>
+static cudaError_t launch_fused_smem(const FusedArgs& g, int sm_count, cudaStream_t st) {
+    const int threads = 64;
+    size_t smem = (size_t)4 * g.f.N * threads * sizeof(double);
+    auto kern = fidelity_stats_smem_kernel<MODEL, REPLAY>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    int occ = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    if (err != cudaSuccess) return err;
+    if (occ < 1) occ = 1;
+    long long nitems = (long long)g.f.S * g.f.C * g.nchunks;
+    long long grid = (long long)sm_count * occ;
+    if (grid > nitems) grid = nitems;
+    if (grid < 1) return cudaSuccess;
+    kern<<<(unsigned)grid, threads, smem, st>>>(g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fused(const FusedArgs& g, cudaStream_t st) {
+    int sm = device_sm_count();
+    if (g.f.N <= reg_crossover()) return fused_table[g.f.N](g, sm, st);
+    const bool replay = g.f.replay != nullptr;
+    if (g.f.model == MODEL_COMPLEX3)
+        return replay ? launch_fused_smem<MODEL_COMPLEX3, true>(g, sm, st) : launch_fused_smem<MODEL_COMPLEX3, false>(g, sm, st);
+    return replay ? launch_fused_smem<MODEL_REAL2, true>(g, sm, st) : launch_fused_smem<MODEL_REAL2, false>(g, sm, st);
+}
+
+// chunking of the draw axis for the fused path: multiples of the CTA size, <= 4096 draws per item
+static void fused_chunking(int nspin, long long B, long long* chunk, long long* nchunks) {
+    const long long threads = nspin <= reg_crossover() ? 128 : 64;
+    long long ch = 4096;
+    if (B < ch) ch = (B + threads - 1) / threads * threads;
+    if (ch < threads) ch = threads;
+    *chunk = ch;
+    *nchunks = (B + ch - 1) / ch;
+    if (*nchunks < 1) *nchunks = 1;
+}
+
+// One thread per segment merges its chunk partials in order and emits the 15 statistics.
+__global__ void fused_finalize_kernel(const double* __restrict__ partials, long long nseg, long long nchunks,
+                                      long long B, double eps, double* __restrict__ stats) {
+    for (long long seg = (long long)blockIdx.x * blockDim.x + threadIdx.x; seg < nseg;
+         seg += (long long)gridDim.x * blockDim.x) {
+        Moments m;
+        moments_load(m, partials + seg * nchunks * PART_DOUBLES);
+        for (long long ch = 1; ch < nchunks; ++ch) {
+            Moments o;
+            moments_load(o, partials + (seg * nchunks + ch) * PART_DOUBLES);
+            moments_merge(m, o);
+        }
+        const double mn[3] = {m.mn, clip01(m.mn - eps), clip01(m.mn + eps)};
+        for (int k = 0; k < 3; ++k) {
+            stats[(ST_W + k) * nseg + seg] = m.s1[k] / (double)B;       // mean(1 - f) == sorted W1 formula
+            stats[(ST_Q95 + k) * nseg + seg] = -1.0 * (m.c95[k] / (double)B);
+            stats[(ST_Q98 + k) * nseg + seg] = -1.0 * (m.c98[k] / (double)B);
+            stats[(ST_STD + k) * nseg + seg] = sqrt(m.m2[k] / (double)B);
+            stats[(ST_WC + k) * nseg + seg] = -mn[k];
+        }
+    }
+}
+
+int check_model_args(int64_t C, int nspin, int inspin, int outspin, int S, int64_t B, int model) {
+    if (nspin < 2 || nspin > MAX_N) return set_error(RC_ERR_BAD_ARG, "nspin=%d outside [2,%d]", nspin, MAX_N);
+    if (inspin < 0 || inspin >= nspin || outspin < 0 || outspin >= nspin)
+        return set_error(RC_ERR_BAD_ARG, "inspin=%d / outspin=%d outside [0,%d)", inspin, outspin, nspin);
+    if (C < 0 || S < 0 || B < 0) return set_error(RC_ERR_BAD_ARG, "negative size C=%lld S=%d B=%lld", (long long)C, S, (long long)B);
+    if (S > 65535) return set_error(RC_ERR_BAD_ARG, "S=%d exceeds 65535 sigma levels", S);
+    if (model != MODEL_COMPLEX3 && model != MODEL_REAL2) return set_error(RC_ERR_BAD_ARG, "unknown model %d", model);
+    return RC_OK;
+}
+
+__global__ void philox_normals_kernel(long long C, long long B, int S, int n, int model, uint32_t k0, uint32_t k1,
+                                      long long c_off, long long b_off, double* out) {
+    const int P = model == MODEL_COMPLEX3 ? 3 : 2;
+    const int K = P * n;
+    const long long total = (long long)S * C * B;
+    for (long long ev = (long long)blockIdx.x * blockDim.x + threadIdx.x; ev < total;
+         ev += (long long)gridDim.x * blockDim.x) {
+        EvalIndex ix = decode_eval(ev, C, B);
+        double* row = out + ev * K;
+        for (int j = 0; j < K; ++j) row[j] = 0.0;
+        const int nc = K - (P - 1);
+        for (int p = 0; p < (nc + 1) / 2; ++p) {
+            double z0, z1;
+            normal_pair(k0, k1, (uint32_t)ix.s, (uint64_t)(ix.c + c_off), (uint64_t)(ix.b + b_off), p, z0, z1);
+            int jc = 2 * p;
+            row[jc == 0 ? 0 : jc + (P - 1)] = z0;
+            if (jc + 1 < nc) row[jc + 1 + (P - 1)] = z1;
+        }
+    }
+}
+
+}  // namespace rc
+
+using namespace rc;
+
+extern "C" int rc_version(void) { return 100; }
+extern "C" const char* rc_last_error(void) { return last_error_buffer(); }
+
+extern "C" int rc_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    RC_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    RC_CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return RC_OK;
+}
+
+extern "C" int rc_fidelity_mc(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
+                              const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed,
+                              int64_t c_offset, int64_t b_offset, const double* replay_dev, double* fids_dev,
+                              unsigned long long* nonconv_dev, void* stream) {
+    int rcode = check_model_args(C, nspin, inspin, outspin, S, B, model);
+    if (rcode) return rcode;
+    if ((long long)S * C * B == 0) return RC_OK;
+    if (!ctrl_dev || !sigma_dev || !fids_dev) return set_error(RC_ERR_NULL, "rc_fidelity_mc: null ctrl/sigma/fids pointer");
+    FidArgs a;
+    a.ctrl = ctrl_dev; a.sigma = sigma_dev; a.replay = replay_dev; a.fids = fids_dev; a.nonconv = nonconv_dev;
+    a.C = C; a.B = B; a.S = S; a.N = nspin; a.in = inspin; a.out = outspin; a.model = model; a.zz = zz;
+    a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+    a.c_offset = c_offset; a.b_offset = b_offset;
+    RC_CUDA_TRY(launch_fidelity(a, (cudaStream_t)stream));
+    return RC_OK;
+}
+
+extern "C" int rc_philox_normals(int64_t C, int nspin, int S, int64_t B, int model, uint64_t seed, int64_t c_offset,
+                                 int64_t b_offset, double* normals_dev, void* stream) {
+    int rcode = check_model_args(C, nspin, 0, 0, S, B, model);
+    if (rcode) return rcode;
+    long long total = (long long)S * C * B;
+    if (total == 0) return RC_OK;
+    if (!normals_dev) return set_error(RC_ERR_NULL, "rc_philox_normals: null output");
+    long long blocks = (total + 127) / 128;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    philox_normals_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(C, B, S, nspin, model, (uint32_t)seed,
+                                                                              (uint32_t)(seed >> 32), c_offset, b_offset,
+                                                                              normals_dev);
+    RC_CUDA_TRY(cudaGetLastError());
+    return RC_OK;
+}
+
+extern "C" size_t rc_fidelity_stats_workspace_bytes(int64_t nseg, int64_t B) {
+    if (nseg <= 0 || B <= 0) return 256;
+    long long chunk, nchunks;
+    fused_chunking(2, B, &chunk, &nchunks);  // 128-thread chunking gives the upper bound for both paths
+    long long ch64 = 4096;
+    if (B < ch64) ch64 = (B + 63) / 64 * 64;
+    long long n64 = (B + ch64 - 1) / ch64;
+    long long nmax = nchunks > n64 ? nchunks : n64;
+    return (size_t)nseg * nmax * PART_DOUBLES * sizeof(double) + 256;
+}
+
+extern "C" int rc_fidelity_stats(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
+                                 const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed,
+                                 int64_t c_offset, int64_t b_offset, const double* replay_dev, double dkw_eps,
+                                 double* stats_dev, unsigned long long* nonconv_dev, void* workspace_dev,
+                                 size_t workspace_bytes, void* stream) {
+    int rcode = check_model_args(C, nspin, inspin, outspin, S, B, model);
+    if (rcode) return rcode;
+    const long long nseg = (long long)S * C;
+    if (nseg == 0) return RC_OK;
+    if (B < 1) return set_error(RC_ERR_BAD_ARG, "rc_fidelity_stats: B must be >= 1");
+    if (!ctrl_dev || !sigma_dev || !stats_dev) return set_error(RC_ERR_NULL, "rc_fidelity_stats: null ctrl/sigma/stats pointer");
+    FusedArgs g;
+    FidArgs& a = g.f;
+    a.ctrl = ctrl_dev; a.sigma = sigma_dev; a.replay = replay_dev; a.fids = nullptr; a.nonconv = nonconv_dev;
+    a.C = C; a.B = B; a.S = S; a.N = nspin; a.in = inspin; a.out = outspin; a.model = model; a.zz = zz;
+    a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+    a.c_offset = c_offset; a.b_offset = b_offset;
+    g.eps = dkw_eps;
+    fused_chunking(nspin, B, &g.chunk, &g.nchunks);
+    const size_t need = (size_t)nseg * g.nchunks * PART_DOUBLES * sizeof(double);
+    if (!workspace_dev || workspace_bytes < need)
+        return set_error(RC_ERR_WORKSPACE, "rc_fidelity_stats: workspace %zu < required %zu bytes", workspace_bytes, need);
+    g.partials = (double*)workspace_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    RC_CUDA_TRY(launch_fused(g, st));
+    long long blocks = (nseg + 127) / 128;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    fused_finalize_kernel<<<(unsigned)blocks, 128, 0, st>>>(g.partials, nseg, g.nchunks, B, dkw_eps, stats_dev);
+    RC_CUDA_TRY(cudaGetLastError());
+    return RC_OK;
+}

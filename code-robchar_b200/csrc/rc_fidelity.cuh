@@ -1,0 +1,359 @@
+// Evolution + fidelity kernels: one lane per (sigma level, controller, noise draw).
+//
+// Reference path replaced: MCDataSim.get_algo_fid_dist's triple loop (mcsim.py:422-460) around
+// structured_perturbation.evaluate_noisy_fidelity (noise_model.py:98-147), and the optimiser-side
+// variant LBFGS.structured_perturabation / fidelity_ss (qnewton.py:366-423).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rc_ql.cuh"
+#include "rc_philox.cuh"
+#include "rc_stats.cuh"
+
+namespace rc {
+
+constexpr int MODEL_COMPLEX3 = 0;  // noise_model.py:122-147: (z_ii, nn_i, nn2_i) per site
+constexpr int MODEL_REAL2 = 1;     // qnewton.py:366-379:     (z_ii, nn_i) per site
+constexpr int REG_MAX_N = 16;      // register-resident eigensolver up to here, shared memory above
+constexpr int MAX_N = 32;
+
+struct FidArgs {
+    const double* ctrl;     // [C][N+1] biases then time (device)
+    const double* sigma;    // [S] simulation noise levels (device)
+    const double* replay;   // [S][C][B][K] standard normals in reference draw order, or nullptr (Philox)
+    double* fids;           // [S][C][B]
+    unsigned long long* nonconv;  // device counter of QL non-convergences (may be nullptr)
+    long long C, B;
+    int S, N, in, out, model, zz;
+    uint32_t seed_lo, seed_hi;
+    long long c_offset, b_offset;  // global index of this shard's first controller / draw (Philox counters)
+};
+
+__host__ __device__ constexpr int draws_per_site(int model) { return model == MODEL_COMPLEX3 ? 3 : 2; }
+
+// Heisenberg / Z diagonal of qnewton.py:148-150 for the open chain: t_i = (N-1)/2 - deg_i.
+RC_HD double zz_diag(int i, int n) { return 0.5 * (n - 1) - ((i == 0 || i == n - 1) ? 1.0 : 2.0); }
+
+struct EvalIndex { long long s, c, b; };
+RC_HD EvalIndex decode_eval(long long e, long long C, long long B) {
+    EvalIndex r;
+    long long sc = e / B;
+    r.b = e - sc * B;
+    r.s = sc / C;
+    r.c = sc - r.s * C;
+    return r;
+}
+
+#if defined(__CUDACC__)
+// d/e of the gauge-transformed real symmetric tridiagonal Hamiltonian from one row of draws.
+// get(j) returns the j-th STANDARD normal of this evaluation in reference draw order.
+template <int N, int MODEL, class Get>
+__device__ __forceinline__ void build_tridiagonal(const double* __restrict__ x, double sigma, int zz, Get&& get,
+                                                  double (&d)[N], double (&e)[N]) {
+    constexpr int P = draws_per_site(MODEL);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double base = zz ? zz_diag(i, N) : 0.0;
+        // reference order: (HH_ii + z_ii) + x_i  with z_ii = sigma * normal  (noise_model.py:100-104)
+        d[i] = __dadd_rn(__dadd_rn(base, __dmul_rn(sigma, get(P * i))), x[i]);
+        if (i >= 1) {
+            double a = __dadd_rn(1.0, __dmul_rn(sigma, get(P * i + 1)));
+            if (MODEL == MODEL_COMPLEX3) {
+                double bb = __dmul_rn(sigma, get(P * i + 2));
+                e[i - 1] = sqrt(fma(a, a, bb * bb));  // |1 + nn + i nn2|
+            } else {
+                e[i - 1] = a;
+            }
+        }
+    }
+    e[N - 1] = 0.0;
+}
+
+template <int N, int MODEL>
+struct PhiloxDraws {
+    // Lazy pairwise generation.  Compact order = reference order minus the discarded site-0
+    // coupling draws; build_tridiagonal consumes draws in ascending order, so after unrolling
+    // every index below is a compile-time constant and only one pair is live at a time.
+    static constexpr int P = draws_per_site(MODEL);
+    uint32_t k0, k1, s;
+    uint64_t c, b;
+    double za, zb;
+    __device__ __forceinline__ double operator()(int j) {
+        const int jc = j == 0 ? 0 : j - (P - 1);
+        if ((jc & 1) == 0) {
+            normal_pair(k0, k1, s, c, b, (uint32_t)(jc >> 1), za, zb);
+            return za;
+        }
+        return zb;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Register-resident kernel, N <= REG_MAX_N.  Persistent grid-stride over tiles of blockDim evals.
+// Replay mode stages the tile's contiguous [evals][K] normals through shared memory with
+// coalesced loads (row pitch padded to an odd number of doubles: conflict-free 64-bit reads).
+// ---------------------------------------------------------------------------------------------
+// Coalesced staging of `nvalid` consecutive replay rows (K doubles each) into padded shared rows.
+template <int K>
+__device__ __forceinline__ void stage_replay_rows(const double* __restrict__ src, int nvalid, double* stage) {
+    constexpr int KP = K | 1;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nvalid * K; idx += blockDim.x) {
+        int row = idx / K, j = idx - row * K;
+        stage[row * KP + j] = __ldcs(src + idx);
+    }
+    __syncthreads();
+}
+
+// One evaluation, register resident.  `row` = this lane's staged replay row (REPLAY only).
+template <int N, int MODEL, bool REPLAY>
+__device__ __forceinline__ double eval_reg(const FidArgs& a, long long s, long long c, long long b,
+                                           const double* row) {
+    const double* x = a.ctrl + c * (N + 1);
+    double xr[N + 1];
+#pragma unroll
+    for (int i = 0; i <= N; ++i) xr[i] = __ldg(x + i);
+    const double sigma = __ldg(a.sigma + s);
+    double d[N], ee[N];
+    if (REPLAY) {
+        build_tridiagonal<N, MODEL>(xr, sigma, a.zz, [&](int j) { return row[j]; }, d, ee);
+    } else {
+        PhiloxDraws<N, MODEL> pd{a.seed_lo, a.seed_hi, (uint32_t)s, (uint64_t)(c + a.c_offset),
+                                 (uint64_t)(b + a.b_offset), 0.0, 0.0};
+        build_tridiagonal<N, MODEL>(xr, sigma, a.zz, pd, d, ee);
+    }
+    int fail = 0;
+    double f = fidelity_reg<N>(d, ee, a.in, a.out, fabs(xr[N]), &fail);
+    if (fail && a.nonconv) atomicAdd(a.nonconv, 1ull);
+    return f;
+}
+
+template <int N, int MODEL, bool REPLAY>
+__global__ void __launch_bounds__(128) fidelity_reg_kernel(FidArgs a) {
+    constexpr int K = draws_per_site(MODEL) * N;
+    constexpr int KP = K | 1;
+    extern __shared__ double stage[];
+    const long long total = (long long)a.S * a.C * a.B;
+    const long long ntiles = (total + blockDim.x - 1) / blockDim.x;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long e0 = tile * blockDim.x;
+        const long long e = e0 + threadIdx.x;
+        if (REPLAY) {
+            long long nvalid = total - e0 < (long long)blockDim.x ? total - e0 : (long long)blockDim.x;
+            stage_replay_rows<K>(a.replay + e0 * K, (int)nvalid, stage);
+        }
+        if (e >= total) continue;
+        EvalIndex ix = decode_eval(e, a.C, a.B);
+        a.fids[e] = eval_reg<N, MODEL, REPLAY>(a, ix.s, ix.c, ix.b, stage + threadIdx.x * KP);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused evolution + streaming statistics (no fidelity tensor).  Work item = (segment, chunk of
+// `chunk` draws); the CTA writes one Moments partial per item; a finalize kernel merges the
+// partials of each segment in chunk order (deterministic).
+// ---------------------------------------------------------------------------------------------
+struct FusedArgs {
+    FidArgs f;
+    double eps;          // DKW shift
+    long long chunk;     // draws per work item (multiple of blockDim)
+    long long nchunks;   // chunks per segment
+    double* partials;    // [S*C][nchunks][PART_DOUBLES]
+};
+
+__device__ __forceinline__ void moments_add(Moments& m, double f, double eps, double (&shift)[3], bool first) {
+    const double v[3] = {f, clip01(f - eps), clip01(f + eps)};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (first) shift[k] = v[k];
+        const double y = v[k] - shift[k];   // shifted sums: mean[] holds sum(y), m2[] holds sum(y^2) until finish
+        m.mean[k] += y;
+        m.m2[k] = fma(y, y, m.m2[k]);
+        m.s1[k] += 1.0 - v[k];
+        m.c95[k] += (v[k] >= 0.95) ? 1.0 : 0.0;
+        m.c98[k] += (v[k] >= 0.98) ? 1.0 : 0.0;
+    }
+    m.mn = (f != f || m.mn != m.mn) ? NAN : fmin(m.mn, f);
+    m.n += 1.0;
+}
+
+__device__ __forceinline__ void moments_finish_thread(Moments& m, const double (&shift)[3]) {
+    if (m.n == 0.0) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double sy = m.mean[k], syy = m.m2[k];
+        m.mean[k] = shift[k] + sy / m.n;
+        m.m2[k] = fmax(syy - sy * sy / m.n, 0.0);
+        if (sy != sy || syy != syy) { m.mean[k] = NAN; m.m2[k] = NAN; }
+    }
+}
+
+__device__ __forceinline__ Moments moments_shfl_down(const Moments& m, int o) {
+    Moments r;
+    r.n = __shfl_down_sync(0xffffffffu, m.n, o);
+    r.mn = __shfl_down_sync(0xffffffffu, m.mn, o);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        r.mean[k] = __shfl_down_sync(0xffffffffu, m.mean[k], o);
+        r.m2[k] = __shfl_down_sync(0xffffffffu, m.m2[k], o);
+        r.s1[k] = __shfl_down_sync(0xffffffffu, m.s1[k], o);
+        r.c95[k] = __shfl_down_sync(0xffffffffu, m.c95[k], o);
+        r.c98[k] = __shfl_down_sync(0xffffffffu, m.c98[k], o);
+    }
+    return r;
+}
+
+__device__ __forceinline__ void moments_store(const Moments& m, double* p) {
+    p[0] = m.n; p[16] = m.mn;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { p[1 + k] = m.mean[k]; p[4 + k] = m.m2[k]; p[7 + k] = m.s1[k]; p[10 + k] = m.c95[k]; p[13 + k] = m.c98[k]; }
+}
+__device__ __forceinline__ void moments_load(Moments& m, const double* p) {
+    m.n = p[0]; m.mn = p[16];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { m.mean[k] = p[1 + k]; m.m2[k] = p[4 + k]; m.s1[k] = p[7 + k]; m.c95[k] = p[10 + k]; m.c98[k] = p[13 + k]; }
+}
+
+// CTA-wide deterministic merge of per-thread Moments; result valid in thread 0.
+__device__ __forceinline__ void moments_block_merge(Moments& m, double* scratch /* [nwarp][PART_DOUBLES] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Moments other = moments_shfl_down(m, o);
+        if (lane + o < 32) moments_merge(m, other);
+    }
+    __syncthreads();
+    if (lane == 0) moments_store(m, scratch + warp * PART_DOUBLES);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < nwarp; ++w) {
+            Moments o2;
+            moments_load(o2, scratch + w * PART_DOUBLES);
+            moments_merge(m, o2);
+        }
+    }
+}
+
+template <int N, int MODEL, bool REPLAY>
+__global__ void __launch_bounds__(128) fidelity_stats_reg_kernel(FusedArgs g) {
+    constexpr int K = draws_per_site(MODEL) * N;
+    constexpr int KP = K | 1;
+    extern __shared__ double stage[];
+    __shared__ double scratch[4 * PART_DOUBLES];
+    const FidArgs& a = g.f;
+    const long long nseg = (long long)a.S * a.C;
+    const long long nitems = nseg * g.nchunks;
+    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const long long seg = item / g.nchunks, ch = item - seg * g.nchunks;
+        const long long s = seg / a.C, c = seg - s * a.C;
+        const long long b0 = ch * g.chunk;
+        const long long b1 = b0 + g.chunk < a.B ? b0 + g.chunk : a.B;
+        Moments m;
+        moments_init(m);
+        double shift[3] = {0.0, 0.0, 0.0};
+        for (long long bt = b0; bt < b1; bt += blockDim.x) {
+            const long long b = bt + threadIdx.x;
+            if (REPLAY) {
+                long long nvalid = b1 - bt < (long long)blockDim.x ? b1 - bt : (long long)blockDim.x;
+                stage_replay_rows<K>(a.replay + (seg * a.B + bt) * K, (int)nvalid, stage);
+            }
+            if (b < b1) {
+                double f = eval_reg<N, MODEL, REPLAY>(a, s, c, b, stage + threadIdx.x * KP);
+                moments_add(m, f, g.eps, shift, m.n == 0.0);
+            }
+        }
+        moments_finish_thread(m, shift);
+        moments_block_merge(m, scratch);
+        if (threadIdx.x == 0) moments_store(m, g.partials + item * PART_DOUBLES);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory kernel for REG_MAX_N < N <= MAX_N: each lane owns a column of four [N] arrays.
+// ---------------------------------------------------------------------------------------------
+template <int MODEL, bool REPLAY>
+__device__ __forceinline__ double eval_smem(const FidArgs& a, long long s, long long c, long long b,
+                                            const double* row /* global replay row */, double* sm) {
+    const int n = a.N, ld = blockDim.x;
+    double* d = sm + threadIdx.x;
+    double* e = d + (size_t)n * ld;
+    double* zi = e + (size_t)n * ld;
+    double* zo = zi + (size_t)n * ld;
+    constexpr int P = draws_per_site(MODEL);
+    const double* x = a.ctrl + c * (n + 1);
+    const double sigma = __ldg(a.sigma + s);
+    const uint64_t cg = (uint64_t)(c + a.c_offset), bg = (uint64_t)(b + a.b_offset);
+    double zc[2] = {0.0, 0.0};  // current Philox pair
+    int have = -1;
+    auto get = [&](int j) -> double {
+        if (REPLAY) return __ldg(row + j);
+        int jc = j == 0 ? 0 : j - (P - 1);  // compact index
+        int p = jc >> 1;
+        if (p != have) { normal_pair(a.seed_lo, a.seed_hi, (uint32_t)s, cg, bg, p, zc[0], zc[1]); have = p; }
+        return zc[jc & 1];
+    };
+    for (int i = 0; i < n; ++i) {
+        double base = a.zz ? zz_diag(i, n) : 0.0;
+        d[(size_t)i * ld] = __dadd_rn(__dadd_rn(base, __dmul_rn(sigma, get(P * i))), __ldg(x + i));
+        if (i >= 1) {
+            double aa = __dadd_rn(1.0, __dmul_rn(sigma, get(P * i + 1)));
+            if (MODEL == MODEL_COMPLEX3) {
+                double bb = __dmul_rn(sigma, get(P * i + 2));
+                e[(size_t)(i - 1) * ld] = sqrt(fma(aa, aa, bb * bb));
+            } else {
+                e[(size_t)(i - 1) * ld] = aa;
+            }
+        }
+        zi[(size_t)i * ld] = (i == a.in) ? 1.0 : 0.0;
+        zo[(size_t)i * ld] = (i == a.out) ? 1.0 : 0.0;
+    }
+    int fail = 0;
+    double f = fidelity_strided(d, e, zi, zo, ld, n, fabs(__ldg(x + n)), &fail);
+    if (fail && a.nonconv) atomicAdd(a.nonconv, 1ull);
+    return f;
+}
+
+template <int MODEL, bool REPLAY>
+__global__ void __launch_bounds__(64) fidelity_smem_kernel(FidArgs a) {
+    extern __shared__ double sm[];
+    const long long K = (long long)draws_per_site(MODEL) * a.N;
+    const long long total = (long long)a.S * a.C * a.B;
+    for (long long ev = (long long)blockIdx.x * blockDim.x + threadIdx.x; ev < total;
+         ev += (long long)gridDim.x * blockDim.x) {
+        EvalIndex ix = decode_eval(ev, a.C, a.B);
+        a.fids[ev] = eval_smem<MODEL, REPLAY>(a, ix.s, ix.c, ix.b, REPLAY ? a.replay + ev * K : nullptr, sm);
+    }
+}
+
+template <int MODEL, bool REPLAY>
+__global__ void __launch_bounds__(64) fidelity_stats_smem_kernel(FusedArgs g) {
+    extern __shared__ double sm[];
+    __shared__ double scratch[2 * PART_DOUBLES];
+    const FidArgs& a = g.f;
+    const long long K = (long long)draws_per_site(MODEL) * a.N;
+    const long long nseg = (long long)a.S * a.C;
+    const long long nitems = nseg * g.nchunks;
+    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const long long seg = item / g.nchunks, ch = item - seg * g.nchunks;
+        const long long s = seg / a.C, c = seg - s * a.C;
+        const long long b0 = ch * g.chunk;
+        const long long b1 = b0 + g.chunk < a.B ? b0 + g.chunk : a.B;
+        Moments m;
+        moments_init(m);
+        double shift[3] = {0.0, 0.0, 0.0};
+        for (long long b = b0 + threadIdx.x; b < b1; b += blockDim.x) {
+            double f = eval_smem<MODEL, REPLAY>(a, s, c, b, REPLAY ? a.replay + (seg * a.B + b) * K : nullptr, sm);
+            moments_add(m, f, g.eps, shift, m.n == 0.0);
+        }
+        moments_finish_thread(m, shift);
+        moments_block_merge(m, scratch);
+        if (threadIdx.x == 0) moments_store(m, g.partials + item * PART_DOUBLES);
+    }
+}
+#endif  // __CUDACC__
+
+// launchers implemented in rc_fidelity_n.cu (one translation unit per N) / rc_fidelity.cu
+typedef cudaError_t (*fid_launch_fn)(const FidArgs&, int sm_count, cudaStream_t);
+typedef cudaError_t (*fused_launch_fn)(const FusedArgs&, int sm_count, cudaStream_t);
+
+}  // namespace rc

@@ -1,0 +1,254 @@
+// Transfer amplitude <out| exp(-i H T) |in> of a real symmetric tridiagonal H, lane-private.
+//
+// Replaces the reference's dense complex `scipy.linalg.expm(-1j*T*H)` followed by the
+// [out,in] element (noise_model.py:105-109, qnewton.py:397-400).  The reference Hamiltonian is
+// complex Hermitian tridiagonal (noise_model.py:135-147); a diagonal phase gauge maps it to the
+// real symmetric tridiagonal (d_i, b_i = |1 + nn_i + i nn2_i|) and |U[out,in]|^2 is invariant.
+//
+// Algorithm: implicit-shift QL with Wilkinson shifts (Givens chase from the bottom of the
+// unreduced block), accumulating the plane rotations ONLY into the two rows `in` and `out` of
+// the eigenvector matrix.  Then amp = sum_k V[out,k] V[in,k] exp(-i lambda_k T).
+// Backward stable => |fid - expm| ~ 1e-14 (tests pin 1e-10).
+//
+// Register-resident variant (QlReg<N>): all loops over matrix positions are compile-time
+// unrolled so d/e/zi/zo live in registers; the eigenvalue index l is a compile-time constant
+// (template recursion) and only the per-eigenvalue sweep count is data dependent.  A warp
+// evaluates 32 noise draws of the SAME controller, so sweep counts are strongly correlated
+// across lanes and divergence stays low.
+#pragma once
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define RC_HD __host__ __device__ __forceinline__
+#define RC_D __device__ __forceinline__
+#else
+#define RC_HD inline
+#define RC_D inline
+#endif
+
+namespace rc {
+
+constexpr int QL_MAX_SWEEPS = 40;  // per eigenvalue (EISPACK uses 30)
+
+RC_HD double rc_rsqrt(double h) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(h);
+#else
+    return 1.0 / sqrt(h);
+#endif
+}
+
+#ifdef RC_QL_STATS
+struct QlStats { int sweeps_per_l[64]; int total_sweeps; int rotations; };
+#define RC_STAT(x) x
+#else
+#define RC_STAT(x)
+#endif
+
+RC_HD double wilkinson_g(double dl, double dl1, double el, double dm) {
+    double delta = 0.5 * (dl1 - dl);
+    double e2 = el * el;
+    double t = delta + copysign(sqrt(fma(delta, delta, e2)), delta);
+    return (dm - dl) + e2 / t;
+}
+
+// One implicit QL sweep on the unreduced block [L, m] (m found by the caller), L compile time.
+// e[i] couples sites i and i+1; e[N-1] is a scratch slot.
+template <int N, int L>
+struct QlSweep {
+    static RC_HD void run(double (&d)[N], double (&e)[N], double (&zi)[N], double (&zo)[N], int m, double dm) {
+        // Wilkinson shift from the leading 2x2 of the block, single-division form:
+        // mu = d[L] - e^2 / (delta + sign(delta) sqrt(delta^2 + e^2)),  g = d[m] - mu
+        double g = wilkinson_g(d[L], d[L + 1], e[L], dm);
+        double r;
+        double s = 1.0, c = 1.0, p = 0.0;
+#pragma unroll
+        for (int i = N - 2; i >= L; --i) {
+            if (i < m) {
+                double f = s * e[i];
+                double b = c * e[i];
+                double h = f * f + g * g;
+                double rinv = rc_rsqrt(h);
+                r = h * rinv;
+                if (!(h > 0.0)) { rinv = 0.0; r = 0.0; }  // underflow guard: identity-like step
+                e[i + 1] = r;
+                s = f * rinv;
+                c = (h > 0.0) ? g * rinv : 1.0;
+                g = d[i + 1] - p;
+                r = (d[i] - g) * s + 2.0 * c * b;
+                p = s * r;
+                d[i + 1] = g + p;
+                g = c * r - b;
+                double t = zi[i + 1];
+                zi[i + 1] = s * zi[i] + c * t;
+                zi[i] = c * zi[i] - s * t;
+                t = zo[i + 1];
+                zo[i + 1] = s * zo[i] + c * t;
+                zo[i] = c * zo[i] - s * t;
+            }
+        }
+        d[L] -= p;
+        e[L] = g;
+#pragma unroll
+        for (int i = L + 1; i < N; ++i)
+            if (i == m) e[i] = 0.0;
+    }
+};
+
+template <int N, int L>
+struct QlLevel {
+    static RC_HD int run(double (&d)[N], double (&e)[N], double (&zi)[N], double (&zo)[N], double tol
+#ifdef RC_QL_STATS
+                         , QlStats* st
+#endif
+    ) {
+        int fail = 0;
+        if constexpr (L < N - 1) {
+            int it = 0;
+            while (true) {
+                // first negligible off-diagonal at or after L (descending scan: smallest index wins)
+                int m = N - 1;
+                double dm = d[N - 1];
+#pragma unroll
+                for (int i = N - 2; i >= L; --i) {
+                    if (fabs(e[i]) <= tol) { m = i; dm = d[i]; }
+                }
+                if (m == L) break;
+                if (++it > QL_MAX_SWEEPS) { fail = 1; break; }
+                QlSweep<N, L>::run(d, e, zi, zo, m, dm);
+                RC_STAT(st->sweeps_per_l[L]++; st->total_sweeps++; st->rotations += m - L;)
+            }
+            fail |= QlLevel<N, L + 1>::run(d, e, zi, zo, tol
+#ifdef RC_QL_STATS
+                                           , st
+#endif
+            );
+        }
+        return fail;
+    }
+};
+
+// amp = sum_k zo[k] zi[k] exp(-i d[k] T)
+template <int N>
+RC_HD void phase_sum(const double (&d)[N], const double (&zi)[N], const double (&zo)[N], double T, double& re,
+                     double& im) {
+    re = 0.0; im = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        double sn, cs;
+        sincos(d[k] * T, &sn, &cs);
+        double w = zo[k] * zi[k];
+        re = fma(w, cs, re);
+        im = fma(-w, sn, im);
+    }
+}
+
+// Full register-resident evaluation.  d[0..N-1] diagonal, e[0..N-2] off-diagonal (e[N-1] ignored).
+// Returns fidelity; *fail set to 1 when QL did not converge (result NaN).
+template <int N>
+RC_HD double fidelity_reg(double (&d)[N], double (&e)[N], int in, int out, double T, int* fail
+#ifdef RC_QL_STATS
+                          , QlStats* st
+#endif
+) {
+    double zi[N], zo[N];
+    double anorm = 0.0, chk = 0.0;
+    e[N - 1] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        zi[k] = (k == in) ? 1.0 : 0.0;
+        zo[k] = (k == out) ? 1.0 : 0.0;
+        anorm = fmax(anorm, fabs(d[k]) + fabs(e[k]));
+        chk += d[k] + e[k];
+    }
+    chk += T;
+    if (!(fabs(chk) <= DBL_MAX)) {  // NaN / Inf controller or draw -> NaN fidelity (mcsim.py:369-374)
+        *fail = 0;
+        return NAN;
+    }
+    double tol = DBL_EPSILON * anorm;
+    int f = QlLevel<N, 0>::run(d, e, zi, zo, tol
+#ifdef RC_QL_STATS
+                               , st
+#endif
+    );
+    *fail = f;
+    if (f) return NAN;
+    double re, im;
+    phase_sum<N>(d, zi, zo, T, re, im);
+    return re * re + im * im;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Strided-memory variant for large N: arrays live in shared (or any) memory with element stride
+// `ld` between consecutive matrix positions (column = this lane), dynamic loop bounds.
+// Holds the "i+1" elements in registers while chasing upwards to halve the memory traffic.
+// ---------------------------------------------------------------------------------------------
+RC_HD double fidelity_strided(double* d, double* e, double* zi, double* zo, int ld, int n, double T, int* fail) {
+#define AT(a, i) a[(size_t)(i) * ld]
+    double anorm = 0.0, chk = T;
+    AT(e, n - 1) = 0.0;
+    for (int k = 0; k < n; ++k) {
+        anorm = fmax(anorm, fabs(AT(d, k)) + fabs(AT(e, k)));
+        chk += AT(d, k) + AT(e, k);
+    }
+    if (!(fabs(chk) <= DBL_MAX)) { *fail = 0; return NAN; }
+    const double tol = DBL_EPSILON * anorm;
+    int bad = 0;
+    for (int l = 0; l < n - 1; ++l) {
+        int it = 0;
+        while (true) {
+            int m = l;
+            while (m < n - 1 && !(fabs(AT(e, m)) <= tol)) ++m;
+            if (m == l) break;
+            if (++it > QL_MAX_SWEEPS) { bad = 1; break; }
+            double g = wilkinson_g(AT(d, l), AT(d, l + 1), AT(e, l), AT(d, m));
+            double r;
+            double s = 1.0, c = 1.0, p = 0.0;
+            double d_up = AT(d, m), zi_up = AT(zi, m), zo_up = AT(zo, m);  // values at i+1
+            for (int i = m - 1; i >= l; --i) {
+                double ei = AT(e, i), di = AT(d, i), zii = AT(zi, i), zoi = AT(zo, i);
+                double f = s * ei, b = c * ei;
+                double h = f * f + g * g;
+                double rinv = rc_rsqrt(h);
+                r = h * rinv;
+                bool okh = h > 0.0;
+                if (!okh) { rinv = 0.0; r = 0.0; }
+                AT(e, i + 1) = r;
+                s = f * rinv;
+                c = okh ? g * rinv : 1.0;
+                g = d_up - p;
+                r = (di - g) * s + 2.0 * c * b;
+                p = s * r;
+                AT(d, i + 1) = g + p;
+                g = c * r - b;
+                AT(zi, i + 1) = s * zii + c * zi_up;
+                zi_up = c * zii - s * zi_up;
+                AT(zo, i + 1) = s * zoi + c * zo_up;
+                zo_up = c * zoi - s * zo_up;
+                d_up = di;
+            }
+            AT(zi, l) = zi_up;
+            AT(zo, l) = zo_up;
+            AT(d, l) = d_up - p;
+            AT(e, l) = g;
+            AT(e, m) = 0.0;
+        }
+        if (bad) break;
+    }
+    *fail = bad;
+    if (bad) return NAN;
+    double re = 0.0, im = 0.0;
+    for (int k = 0; k < n; ++k) {
+        double sn, cs;
+        sincos(AT(d, k) * T, &sn, &cs);
+        double w = AT(zo, k) * AT(zi, k);
+        re = fma(w, cs, re);
+        im = fma(-w, sn, im);
+    }
+#undef AT
+    return re * re + im * im;
+}
+
+}  // namespace rc

@@ -1,0 +1,273 @@
+// Ranking stage on device: ordinal ranks, clustered ranks and the Kendall tau-b matrix.
+//
+// Reference path replaced: MCDataSim.get_ranks (mcsim.py:513-518),
+// get_ranks_clustered_little (generate_fig4_kendallrankanalysis.py:146-164) and
+// scipy.stats.kendalltau as called from jkt_or_ordinaltau_pairwise (…fig4…py:94-120).
+// Everything that decides a rank is integer / comparison work on order-preserving 64-bit keys,
+// so results are bit-exact given the same RIM values (ties broken by index = stable argsort).
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+#include "rc_common.cuh"
+
+namespace rc {
+
+constexpr int RANK_SMEM_MAX = 4096;
+
+__device__ __forceinline__ unsigned long long rank_key(double f) {
+    if (f != f) return ~0ull;        // NaN last (np.argsort)
+    if (f == 0.0) f = 0.0;           // -0.0 == +0.0
+    unsigned long long b = (unsigned long long)__double_as_longlong(f);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// ---- small rows: one CTA per row, bitonic sort of (key, index) in shared memory -----------------
+__global__ void __launch_bounds__(512) argsort_small_kernel(const double* __restrict__ values, long long R, int n,
+                                                            int P, int* __restrict__ perm) {
+    extern __shared__ unsigned long long sm[];
+    unsigned long long* keys = sm;
+    int* idx = (int*)(sm + P);
+    for (long long row = blockIdx.x; row < R; row += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            keys[i] = i < n ? rank_key(values[row * n + i]) : ~0ull;
+            idx[i] = i < n ? i : 0x7FFFFFFF;
+        }
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                    int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    int p = i | j;
+                    bool up = (i & k) == 0;
+                    unsigned long long a = keys[i], b = keys[p];
+                    int ia = idx[i], ib = idx[p];
+                    bool gt = (a > b) || (a == b && ia > ib);  // index tie-break => stable order
+                    if (gt == up) { keys[i] = b; keys[p] = a; idx[i] = ib; idx[p] = ia; }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) perm[row * n + i] = idx[i];
+    }
+}
+
+// ---- large rows: key/index build + cub segmented radix sort (LSD radix sort is stable) ----------
+__global__ void build_keys_kernel(const double* __restrict__ values, long long total, int n, unsigned long long* keys,
+                                  int* idx) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        keys[i] = rank_key(values[i]);
+        idx[i] = (int)(i % n);
+    }
+}
+
+struct RowOffset {
+    int n;
+    __host__ __device__ int operator()(int i) const { return i * n; }
+};
+
+__global__ void scatter_ranks_kernel(const int* __restrict__ perm, long long R, long long n, long long* __restrict__ ranks) {
+    const long long total = R * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long row = i / n, pos = i - row * n;
+        ranks[row * n + perm[i]] = pos;  // ranks[argranks] = arange(n)  (mcsim.py:516-517)
+    }
+}
+
+// One thread per row walks the sorted order (the cluster anchor x0 is a sequential dependency).
+__global__ void clustered_walk_kernel(const double* __restrict__ values, const int* __restrict__ perm, long long R,
+                                      long long n, double alpha, double r_fixed, double* __restrict__ out) {
+    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < R; row += (long long)gridDim.x * blockDim.x) {
+        const double* v = values + row * n;
+        const int* p = perm + row * n;
+        long long last = n - 1;
+        while (last > 0 && v[p[last]] != v[p[last]]) --last;  // NaNs are sorted last
+        const double mn = v[p[0]], mx = v[p[last]];
+        const double r = alpha < 0.0 ? r_fixed : alpha * (mx - mn);  // …fig4…py:97
+        double x0 = mn, rank = 0.0;
+        for (long long i = 0; i < n; ++i) {
+            const double x = v[p[i]];
+            if (x - x0 > r) { rank += 1.0; x0 = x; }
+            out[row * n + p[i]] = rank;
+        }
+    }
+}
+
+// ---- Kendall tau-b ---------------------------------------------------------------------------
+// grid.y = pair (j, i); grid.x tiles the first index a; each thread owns one a and scans b > a
+// through shared-memory tiles.  Integer counts: 0 dis, 1 xtie, 2 ytie, 3 joint ties.
+constexpr int KT_THREADS = 128;
+__global__ void __launch_bounds__(KT_THREADS) kendall_count_kernel(const double* __restrict__ x, long long Rx,
+                                                                   const long long* __restrict__ y, long long Ry, long long n,
+                                                                   unsigned long long* __restrict__ counts) {
+    __shared__ double sx[KT_THREADS];
+    __shared__ long long sy[KT_THREADS];
+    const long long pair = blockIdx.y;
+    const long long j = pair / Ry, i = pair - j * Ry;
+    const double* xr = x + j * n;
+    const long long* yr = y + i * n;
+    const long long a = (long long)blockIdx.x * KT_THREADS + threadIdx.x;
+    const double xa = a < n ? xr[a] : 0.0;
+    const long long ya = a < n ? yr[a] : 0;
+    unsigned long long dis = 0, xt = 0, yt = 0, nt = 0;
+    for (long long b0 = (long long)blockIdx.x * KT_THREADS; b0 < n; b0 += KT_THREADS) {
+        __syncthreads();
+        const long long bl = b0 + threadIdx.x;
+        sx[threadIdx.x] = bl < n ? xr[bl] : 0.0;
+        sy[threadIdx.x] = bl < n ? yr[bl] : 0;
+        __syncthreads();
+        const int lim = n - b0 < KT_THREADS ? (int)(n - b0) : KT_THREADS;
+        if (a < n) {
+            for (int t = 0; t < lim; ++t) {
+                const long long b = b0 + t;
+                if (b <= a) continue;
+                const double dx = xa - sx[t];
+                const long long dy = ya - sy[t];
+                const bool xe = dx == 0.0, ye = dy == 0;
+                xt += xe; yt += ye; nt += xe && ye;
+                dis += (!xe && !ye && ((dx < 0.0) != (dy < 0)));
+            }
+        }
+    }
+    // warp reduce then one atomic per warp (integer adds commute: deterministic result)
+    for (int o = 16; o > 0; o >>= 1) {
+        dis += __shfl_down_sync(0xffffffffu, dis, o);
+        xt += __shfl_down_sync(0xffffffffu, xt, o);
+        yt += __shfl_down_sync(0xffffffffu, yt, o);
+        nt += __shfl_down_sync(0xffffffffu, nt, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long* c = counts + pair * 4;
+        if (dis) atomicAdd(c + 0, dis);
+        if (xt) atomicAdd(c + 1, xt);
+        if (yt) atomicAdd(c + 2, yt);
+        if (nt) atomicAdd(c + 3, nt);
+    }
+}
+
+__global__ void kendall_finalize_kernel(const unsigned long long* __restrict__ counts, long long npairs, long long n,
+                                        double* __restrict__ tau) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += (long long)gridDim.x * blockDim.x) {
+        const long long tot = n * (n - 1) / 2;
+        const long long dis = (long long)counts[p * 4 + 0], xtie = (long long)counts[p * 4 + 1];
+        const long long ytie = (long long)counts[p * 4 + 2], ntie = (long long)counts[p * 4 + 3];
+        double t;
+        if (n < 2 || xtie == tot || ytie == tot) {
+            t = NAN;
+        } else {
+            const long long cmd = tot - xtie - ytie + ntie - 2 * dis;
+            t = (double)cmd / sqrt((double)(tot - xtie)) / sqrt((double)(tot - ytie));  // scipy _kendalltau, variant 'b'
+            t = fmin(1.0, fmax(-1.0, t));
+        }
+        tau[p] = t;
+    }
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static size_t rank_cub_temp(long long R, long long n) {
+    size_t bytes = 0;
+    auto off = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), RowOffset{(int)n});
+    cub::DeviceSegmentedRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                             (const int*)nullptr, (int*)nullptr, (int)(R * n), (int)R, off, off + 1);
+    return align256(bytes);
+}
+
+// perm (int32 [R][n]) at the start of the workspace
+static int argsort_rows(const double* values, long long R, long long n, void* ws, size_t ws_bytes, cudaStream_t st) {
+    int* perm = (int*)ws;
+    const int sm = device_sm_count();
+    if (n <= RANK_SMEM_MAX) {
+        int P = 2;
+        while (P < n) P <<= 1;
+        int threads = P / 2 < 32 ? 32 : (P / 2 > 512 ? 512 : P / 2);
+        size_t smem = (size_t)P * (sizeof(unsigned long long) + sizeof(int));
+        if (smem > 40 * 1024)
+            RC_CUDA_TRY(cudaFuncSetAttribute(argsort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        long long grid = R < (long long)sm * 8 ? R : (long long)sm * 8;
+        argsort_small_kernel<<<(unsigned)grid, threads, smem, st>>>(values, R, (int)n, P, perm);
+        RC_CUDA_TRY(cudaGetLastError());
+        return RC_OK;
+    }
+    if (R * n >= (1ll << 31)) return set_error(RC_ERR_BAD_ARG, "rank: R*n=%lld exceeds 2^31", R * n);
+    char* p = (char*)ws + align256((size_t)R * n * sizeof(int));
+    unsigned long long* k_in = (unsigned long long*)p; p += align256((size_t)R * n * 8);
+    unsigned long long* k_out = (unsigned long long*)p; p += align256((size_t)R * n * 8);
+    int* i_in = (int*)p; p += align256((size_t)R * n * 4);
+    size_t tb = rank_cub_temp(R, n);
+    if ((size_t)(p - (char*)ws) + tb > ws_bytes) return set_error(RC_ERR_WORKSPACE, "rank: workspace too small");
+    build_keys_kernel<<<sm * 8, 256, 0, st>>>(values, R * n, (int)n, k_in, i_in);
+    RC_CUDA_TRY(cudaGetLastError());
+    auto off = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), RowOffset{(int)n});
+    RC_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortPairs(p, tb, k_in, k_out, i_in, perm, (int)(R * n), (int)R, off, off + 1,
+                                                         0, 64, st));
+    return RC_OK;
+}
+
+}  // namespace rc
+
+using namespace rc;
+
+extern "C" size_t rc_ranks_workspace_bytes(int64_t R, int64_t n) {
+    if (R <= 0 || n <= 0) return 256;
+    size_t b = align256((size_t)R * n * sizeof(int));
+    if (n > RANK_SMEM_MAX) {
+        if (R * n >= (1ll << 31)) return 0;
+        b += 2 * align256((size_t)R * n * 8) + align256((size_t)R * n * 4) + rank_cub_temp(R, n);
+    }
+    return b + 256;
+}
+
+extern "C" int rc_ranks(const double* values_dev, int64_t R, int64_t n, int64_t* ranks_dev, void* workspace_dev,
+                        size_t workspace_bytes, void* stream) {
+    if (R < 0 || n < 0) return set_error(RC_ERR_BAD_ARG, "rc_ranks: negative size");
+    if (R == 0 || n == 0) return RC_OK;
+    if (!values_dev || !ranks_dev || !workspace_dev) return set_error(RC_ERR_NULL, "rc_ranks: null pointer");
+    if (workspace_bytes < rc_ranks_workspace_bytes(R, n))
+        return set_error(RC_ERR_WORKSPACE, "rc_ranks: workspace %zu < %zu", workspace_bytes, rc_ranks_workspace_bytes(R, n));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rcode = argsort_rows(values_dev, R, n, workspace_dev, workspace_bytes, st);
+    if (rcode) return rcode;
+    long long total = R * n;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    scatter_ranks_kernel<<<(unsigned)blocks, 256, 0, st>>>((const int*)workspace_dev, R, n, (long long*)ranks_dev);
+    RC_CUDA_TRY(cudaGetLastError());
+    return RC_OK;
+}
+
+extern "C" int rc_clustered_ranks(const double* values_dev, int64_t R, int64_t n, double alpha, double r_fixed,
+                                  double* cranks_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (R < 0 || n < 0) return set_error(RC_ERR_BAD_ARG, "rc_clustered_ranks: negative size");
+    if (R == 0 || n == 0) return RC_OK;
+    if (!values_dev || !cranks_dev || !workspace_dev) return set_error(RC_ERR_NULL, "rc_clustered_ranks: null pointer");
+    if (workspace_bytes < rc_ranks_workspace_bytes(R, n))
+        return set_error(RC_ERR_WORKSPACE, "rc_clustered_ranks: workspace %zu < %zu", workspace_bytes, rc_ranks_workspace_bytes(R, n));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rcode = argsort_rows(values_dev, R, n, workspace_dev, workspace_bytes, st);
+    if (rcode) return rcode;
+    long long blocks = (R + 31) / 32;
+    clustered_walk_kernel<<<(unsigned)blocks, 32, 0, st>>>(values_dev, (const int*)workspace_dev, R, n, alpha, r_fixed, cranks_dev);
+    RC_CUDA_TRY(cudaGetLastError());
+    return RC_OK;
+}
+
+extern "C" int rc_kendall_tau_b(const double* x_dev, int64_t Rx, const int64_t* y_dev, int64_t Ry, int64_t n,
+                                double* tau_dev, long long* counts_dev, void* stream) {
+    if (Rx < 0 || Ry < 0 || n < 0) return set_error(RC_ERR_BAD_ARG, "rc_kendall_tau_b: negative size");
+    if (Rx == 0 || Ry == 0) return RC_OK;
+    if (!x_dev || !y_dev || !tau_dev || !counts_dev) return set_error(RC_ERR_NULL, "rc_kendall_tau_b: null pointer");
+    if (Rx * Ry > 65535) return set_error(RC_ERR_BAD_ARG, "rc_kendall_tau_b: more than 65535 row pairs");
+    cudaStream_t st = (cudaStream_t)stream;
+    RC_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, (size_t)Rx * Ry * 4 * sizeof(long long), st));
+    if (n >= 2) {
+        dim3 grid((unsigned)((n + KT_THREADS - 1) / KT_THREADS), (unsigned)(Rx * Ry));
+        kendall_count_kernel<<<grid, KT_THREADS, 0, st>>>(x_dev, Rx, (const long long*)y_dev, Ry, n,
+                                                         (unsigned long long*)counts_dev);
+        RC_CUDA_TRY(cudaGetLastError());
+    }
+    long long np = Rx * Ry;
+    kendall_finalize_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>((const unsigned long long*)counts_dev, np, n, tau_dev);
+    RC_CUDA_TRY(cudaGetLastError());
+    return RC_OK;
+}

@@ -1,0 +1,230 @@
+// Statistics stage: per-(sigma, controller) segment sort + fused RIM / 1-Wasserstein, Q-threshold,
+// std and worst-case reductions for the centre and the two DKW-shifted variants.
+//
+// Reference path replaced: wd_from_ideal (wd_sortof_fast_implementation.py:82-116), the metric
+// registry Q / std_fids / wc_fids (mcsim.py:144-183) and the DKW loop of
+// MCDataSim.get_metrics_dict (mcsim.py:482-498).
+//
+//   B <= SMEM_SORT_MAX : one CTA per segment, bitonic sort of order-preserving 64-bit keys in
+//                        shared memory, statistics straight from shared memory (one HBM read).
+//   larger B           : cub::DeviceSegmentedRadixSort in chunks, then a streaming statistics
+//                        kernel over the sorted chunk (second pass served by L2).
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+#include "rc_common.cuh"
+#include "rc_stats.cuh"
+
+namespace rc {
+
+constexpr int SMEM_SORT_MAX = 4096;  // 32 KB of keys per CTA
+
+__device__ __forceinline__ unsigned long long f2key(double f) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(f);
+    if (f != f) b = 0x7FF8000000000000ull;  // canonical +NaN sorts last (numpy order)
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key2f(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// Deterministic block-wide sum of NV doubles per thread (fixed shuffle tree + fixed warp order).
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch /* [32*NV] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) scratch[warp * NV + k] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = 0.0;
+        for (int w = 0; w < nwarp; ++w) t += scratch[w * NV + k];
+        v[k] = t;
+    }
+}
+
+// Statistics of one ascending-sorted segment, read through `at(i)`.  All threads of the CTA call.
+template <class At>
+__device__ __forceinline__ void sorted_segment_stats(At at, long long B, double eps, long long seg, long long nseg,
+                                                     double* __restrict__ stats, unsigned long long* illegal,
+                                                     double* scratch) {
+    // pass 1: W sums, plain sums, threshold counts, legality
+    double acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+    unsigned long long bad = 0;
+    for (long long i = threadIdx.x; i < B; i += blockDim.x) {
+        const double f = at(i);
+        const double fn = (i + 1 < B) ? at(i + 1) : 1.0;
+        const double cdf = (double)(i + 1) / (double)B;  // np.arange(1, n+1) / n
+        const double v[3] = {f, clip01(f - eps), clip01(f + eps)};
+        const double vn[3] = {fn, (i + 1 < B) ? clip01(fn - eps) : 1.0, (i + 1 < B) ? clip01(fn + eps) : 1.0};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            acc[k] += (vn[k] - v[k]) * cdf;  // intervals * cdf (wd_sortof_fast_implementation.py:108-114)
+            acc[3 + k] += v[k];
+            acc[6 + k] += (v[k] >= 0.95) ? 1.0 : 0.0;
+            acc[9 + k] += (v[k] >= 0.98) ? 1.0 : 0.0;
+        }
+        if (fabs(f - 1e-8) > 1.0) ++bad;  // check_fidtype (wd_sortof_fast_implementation.py:23)
+    }
+    block_sum<12>(acc, scratch);
+    if (bad && illegal) atomicAdd(illegal, bad);
+    // pass 2: population variance about the mean (np.std)
+    double m2[3] = {0.0, 0.0, 0.0};
+    const double mean[3] = {acc[3] / (double)B, acc[4] / (double)B, acc[5] / (double)B};
+    for (long long i = threadIdx.x; i < B; i += blockDim.x) {
+        const double f = at(i);
+        const double v[3] = {f, clip01(f - eps), clip01(f + eps)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double dlt = v[k] - mean[k];
+            m2[k] += dlt * dlt;
+        }
+    }
+    block_sum<3>(m2, scratch);
+    if (threadIdx.x == 0) {
+        const double f0 = at(0);
+        const double mn[3] = {f0, clip01(f0 - eps), clip01(f0 + eps)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            stats[(0 + k) * nseg + seg] = acc[k];
+            stats[(3 + k) * nseg + seg] = -1.0 * (acc[6 + k] / (double)B);  // -Q(thr)  (mcsim.py:144-146,170-176)
+            stats[(6 + k) * nseg + seg] = -1.0 * (acc[9 + k] / (double)B);
+            stats[(9 + k) * nseg + seg] = sqrt(m2[k] / (double)B);
+            stats[(12 + k) * nseg + seg] = -mn[k];                         // -min  (mcsim.py:148)
+        }
+    }
+}
+
+// One CTA per segment: bitonic sort in shared memory, then statistics.
+__global__ void __launch_bounds__(512) sort_stats_small_kernel(const double* __restrict__ fids, long long nseg, int B,
+                                                               int P /* pow2 >= B */, double eps,
+                                                               double* __restrict__ stats, double* sorted_out,
+                                                               unsigned long long* illegal) {
+    extern __shared__ unsigned long long keys[];
+    __shared__ double scratch[16 * 12];
+    for (long long seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+        const double* src = fids + seg * (long long)B;
+        __syncthreads();
+        for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < B ? f2key(src[i]) : ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                    int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
+                    int p = i | j;
+                    bool up = (i & k) == 0;
+                    unsigned long long a = keys[i], b = keys[p];
+                    if ((a > b) == up) { keys[i] = b; keys[p] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        if (sorted_out) {
+            double* dst = sorted_out + seg * (long long)B;
+            for (int i = threadIdx.x; i < B; i += blockDim.x) dst[i] = key2f(keys[i]);
+        }
+        sorted_segment_stats([&](long long i) { return key2f(keys[i]); }, B, eps, seg, nseg, stats, illegal, scratch);
+    }
+}
+
+// Streaming statistics over already-sorted segments in global memory (large B).
+__global__ void __launch_bounds__(512) stats_sorted_kernel(const double* __restrict__ sorted, long long seg0,
+                                                           long long nseg_chunk, long long nseg, long long B, double eps,
+                                                           double* __restrict__ stats, unsigned long long* illegal) {
+    __shared__ double scratch[16 * 12];
+    for (long long s = blockIdx.x; s < nseg_chunk; s += gridDim.x) {
+        const double* src = sorted + s * B;
+        sorted_segment_stats([&](long long i) { return __ldg(src + i); }, B, eps, seg0 + s, nseg, stats, illegal, scratch);
+    }
+}
+
+struct SegOffset {
+    int B;
+    __host__ __device__ int operator()(int i) const { return i * B; }
+};
+
+static long long large_chunk_segments(long long nseg, long long B) {
+    const long long max_items = 1ll << 28;  // 2 GiB of doubles per chunk, well inside int offsets
+    long long c = max_items / B;
+    if (c < 1) c = 1;
+    if (c > nseg) c = nseg;
+    return c;
+}
+
+static size_t cub_temp_bytes(long long chunk_segs, long long B) {
+    size_t bytes = 0;
+    auto off = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), SegOffset{(int)B});
+    cub::DeviceSegmentedRadixSort::SortKeys(nullptr, bytes, (const double*)nullptr, (double*)nullptr,
+                                            (int)(chunk_segs * B), (int)chunk_segs, off, off + 1);
+    return (bytes + 255) & ~(size_t)255;
+}
+
+}  // namespace rc
+
+using namespace rc;
+
+extern "C" size_t rc_stats_workspace_bytes(int64_t nseg, int64_t B) {
+    if (nseg <= 0 || B <= SMEM_SORT_MAX) return 256;
+    if (B >= (1ll << 30)) return 0;
+    long long cs = large_chunk_segments(nseg, B);
+    return (size_t)cs * B * sizeof(double) + cub_temp_bytes(cs, B) + 256;
+}
+
+extern "C" int rc_stats(const double* fids_dev, int64_t nseg, int64_t B, double dkw_eps, double* stats_dev,
+                        double* sorted_dev, unsigned long long* illegal_dev, void* workspace_dev,
+                        size_t workspace_bytes, void* stream) {
+    if (nseg < 0 || B < 1) return set_error(RC_ERR_BAD_ARG, "rc_stats: nseg=%lld B=%lld", (long long)nseg, (long long)B);
+    if (nseg == 0) return RC_OK;
+    if (!fids_dev || !stats_dev) return set_error(RC_ERR_NULL, "rc_stats: null fids/stats pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sm = device_sm_count();
+    if (B <= SMEM_SORT_MAX) {
+        int P = 1;
+        while (P < B) P <<= 1;
+        if (P < 2) P = 2;
+        int threads = P / 2;
+        if (threads < 32) threads = 32;
+        if (threads > 512) threads = 512;
+        size_t smem = (size_t)P * sizeof(unsigned long long);
+        int occ = 0;
+        RC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sort_stats_small_kernel, threads, smem));
+        if (occ < 1) occ = 1;
+        long long grid = (long long)sm * occ;
+        if (grid > nseg) grid = nseg;
+        sort_stats_small_kernel<<<(unsigned)grid, threads, smem, st>>>(fids_dev, nseg, (int)B, P, dkw_eps, stats_dev,
+                                                                        sorted_dev, illegal_dev);
+        RC_CUDA_TRY(cudaGetLastError());
+        return RC_OK;
+    }
+    if (B >= (1ll << 30)) return set_error(RC_ERR_BAD_ARG, "rc_stats: B=%lld too large (limit 2^30)", (long long)B);
+    const size_t need = rc_stats_workspace_bytes(nseg, B);
+    if (!workspace_dev || workspace_bytes < need)
+        return set_error(RC_ERR_WORKSPACE, "rc_stats: workspace %zu < required %zu bytes", workspace_bytes, need);
+    const long long cs = large_chunk_segments(nseg, B);
+    double* chunk = (double*)workspace_dev;
+    size_t tmp_bytes = cub_temp_bytes(cs, B);
+    void* tmp = (char*)workspace_dev + (((size_t)cs * B * sizeof(double) + 255) & ~(size_t)255);
+    for (long long s0 = 0; s0 < nseg; s0 += cs) {
+        long long ns = nseg - s0 < cs ? nseg - s0 : cs;
+        auto off = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), SegOffset{(int)B});
+        size_t tb = tmp_bytes;
+        RC_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(tmp, tb, fids_dev + s0 * B, chunk, (int)(ns * B), (int)ns,
+                                                            off, off + 1, 0, 64, st));
+        long long grid = ns < (long long)sm * 4 ? ns : (long long)sm * 4;
+        stats_sorted_kernel<<<(unsigned)grid, 512, 0, st>>>(chunk, s0, ns, nseg, B, dkw_eps, stats_dev, illegal_dev);
+        RC_CUDA_TRY(cudaGetLastError());
+        if (sorted_dev)
+            RC_CUDA_TRY(cudaMemcpyAsync(sorted_dev + s0 * B, chunk, (size_t)ns * B * sizeof(double),
+                                        cudaMemcpyDeviceToDevice, st));
+    }
+    return RC_OK;
+}

@@ -1,0 +1,245 @@
+"""Device-level operations: torch tensors in HBM handed to the C-ABI by raw pointer.
+
+PyTorch is used only for device memory, streams and (in dist.py) torch.distributed.  Every
+function here requires a CUDA device and the built native library; nothing is computed on the
+CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MODEL_COMPLEX3, MODEL_REAL2, NUM_STATS, check, lib
+
+# keys of the reference's metric registry, in .mcm order (mcsim.py:178-183, 496-498)
+METRIC_W = r'$W(.,\delta(x-1))$'
+METRIC_NAMES = [METRIC_W, "Q th. 0.95", "Q th. 0.98", "std", "worst case fid"]
+STAT_KEYS = [m + s for m in METRIC_NAMES for s in ("", " upper", " lower")]
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.RobcharLibraryError("robchar_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f64(t, dev):
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t, dtype=np.float64))
+    return t.to(device=dev, dtype=torch.float64).contiguous()
+
+
+def draws_per_eval(nspin: int, model: int = MODEL_COMPLEX3) -> int:
+    return (3 if model == MODEL_COMPLEX3 else 2) * nspin
+
+
+def compute_dkw_error(alpha, nobs):
+    """wd_sortof_fast_implementation.py:38-39 (host scalar)."""
+    return np.sqrt(np.log(2 / alpha) / (2 * nobs))
+
+
+class Counters:
+    """Device counters [nonconv, illegal] checked lazily (one D2H) by raise_if_set()."""
+
+    def __init__(self, dev):
+        self.t = torch.zeros(2, dtype=torch.int64, device=dev)
+
+    @property
+    def nonconv_ptr(self):
+        return C.c_void_p(self.t.data_ptr())
+
+    @property
+    def illegal_ptr(self):
+        return C.c_void_p(self.t.data_ptr() + 8)
+
+    def raise_if_set(self):
+        nc, il = (int(v) for v in self.t.tolist())
+        if nc:
+            raise _lib.EigensolverNonConvergence(f"eigensolver did not converge for {nc} evaluations")
+        if il:
+            raise AssertionError("illegal fids values - must be in [0,1]")
+
+
+def fidelity_mc(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, *, model: int = MODEL_COMPLEX3,
+                zz: bool = False, seed: int = 0, c_offset: int = 0, b_offset: int = 0, replay=None, out=None,
+                counters: Counters | None = None, check_convergence: bool = True) -> torch.Tensor:
+    """Fidelity tensor [S][C][B] (mcsim.py:422-456).  replay: standard normals [S][C][B][K] or None (Philox)."""
+    dev = require_cuda()
+    ctrl = _f64(ctrl, dev)
+    sigmas = _f64(sigmas, dev).reshape(-1)
+    if ctrl.dim() != 2 or ctrl.shape[1] != nspin + 1:
+        raise ValueError(f"ctrl must be [C][{nspin + 1}], got {tuple(ctrl.shape)}")
+    Cn, S = ctrl.shape[0], sigmas.shape[0]
+    if replay is not None:
+        replay = _f64(replay, dev)
+        K = draws_per_eval(nspin, model)
+        if replay.numel() != S * Cn * B * K:
+            raise ValueError(f"replay must hold S*C*B*{K} standard normals")
+    if out is None:
+        out = torch.empty((S, Cn, B), dtype=torch.float64, device=dev)
+    own = counters is None
+    if own:
+        counters = Counters(dev)
+    check(lib().rc_fidelity_mc(_ptr(ctrl), Cn, nspin, inspin, outspin, _ptr(sigmas), S, B, model, int(bool(zz)),
+                               C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, _ptr(replay), _ptr(out),
+                               counters.nonconv_ptr, _stream()))
+    if own and check_convergence:
+        counters.raise_if_set()
+    return out
+
+
+def philox_normals(C_: int, nspin: int, S: int, B: int, *, model: int = MODEL_COMPLEX3, seed: int = 0,
+                   c_offset: int = 0, b_offset: int = 0) -> torch.Tensor:
+    dev = require_cuda()
+    K = draws_per_eval(nspin, model)
+    out = torch.empty((S, C_, B, K), dtype=torch.float64, device=dev)
+    check(lib().rc_philox_normals(C_, nspin, S, B, model, C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, _ptr(out),
+                                  _stream()))
+    return out
+
+
+def stats(fids: torch.Tensor, dkw_eps: float = 0.0, *, sort_inplace: bool = False, check_legal: bool = True) -> torch.Tensor:
+    """[15, *lead] statistics of fids[*lead, B] (mcsim.py:482-498).  sort_inplace mimics wd_from_ideal's
+    in-place sort of its argument (wd_sortof_fast_implementation.py:105)."""
+    dev = require_cuda()
+    fids = _f64(fids, dev) if not (isinstance(fids, torch.Tensor) and fids.is_cuda and fids.dtype == torch.float64
+                                   and fids.is_contiguous()) else fids
+    lead, B = tuple(fids.shape[:-1]), fids.shape[-1]
+    nseg = int(np.prod(lead)) if lead else 1
+    out = torch.empty((NUM_STATS,) + lead, dtype=torch.float64, device=dev)
+    wb = lib().rc_stats_workspace_bytes(nseg, B)
+    if wb == 0:
+        raise ValueError("segment length too large for the sort path; use fidelity_stats (streaming)")
+    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+    cnt = Counters(dev)
+    check(lib().rc_stats(_ptr(fids), nseg, B, float(dkw_eps), _ptr(out), _ptr(fids) if sort_inplace else C.c_void_p(0),
+                         cnt.illegal_ptr, _ptr(ws), wb, _stream()))
+    if check_legal:
+        cnt.raise_if_set()
+    return out
+
+
+def fidelity_stats(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, *, dkw_eps: float = 0.0,
+                   model: int = MODEL_COMPLEX3, zz: bool = False, seed: int = 0, c_offset: int = 0, b_offset: int = 0,
+                   replay=None, check_convergence: bool = True) -> torch.Tensor:
+    """Fused evolution + streaming statistics, [15][S][C]; never materialises the fidelity tensor."""
+    dev = require_cuda()
+    ctrl = _f64(ctrl, dev)
+    sigmas = _f64(sigmas, dev).reshape(-1)
+    Cn, S = ctrl.shape[0], sigmas.shape[0]
+    if replay is not None:
+        replay = _f64(replay, dev)
+    out = torch.empty((NUM_STATS, S, Cn), dtype=torch.float64, device=dev)
+    wb = lib().rc_fidelity_stats_workspace_bytes(S * Cn, B)
+    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+    cnt = Counters(dev)
+    check(lib().rc_fidelity_stats(_ptr(ctrl), Cn, nspin, inspin, outspin, _ptr(sigmas), S, B, model, int(bool(zz)),
+                                  C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, _ptr(replay), float(dkw_eps),
+                                  _ptr(out), cnt.nonconv_ptr, _ptr(ws), wb, _stream()))
+    if check_convergence:
+        cnt.raise_if_set()
+    return out
+
+
+def ranks(values) -> torch.Tensor:
+    """Ordinal ranks per row, ascending, NaN last, ties by index (mcsim.py:513-518)."""
+    dev = require_cuda()
+    v = _f64(values, dev)
+    one_d = v.dim() == 1
+    v2 = v.reshape(1, -1) if one_d else v.reshape(-1, v.shape[-1])
+    R, n = v2.shape
+    out = torch.empty((R, n), dtype=torch.int64, device=dev)
+    wb = lib().rc_ranks_workspace_bytes(R, n)
+    if wb == 0:
+        raise ValueError("ranking problem too large")
+    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+    check(lib().rc_ranks(_ptr(v2), R, n, _ptr(out), _ptr(ws), wb, _stream()))
+    return out.reshape(v.shape)
+
+
+def clustered_ranks(values, alpha: float | None = 0.05, r: float | None = None) -> torch.Tensor:
+    """get_ranks_clustered_little (generate_fig4_kendallrankanalysis.py:146-164); radius r, or
+    alpha*(max-min) per row when r is None (…fig4…py:97)."""
+    dev = require_cuda()
+    v = _f64(values, dev)
+    v2 = v.reshape(1, -1) if v.dim() == 1 else v.reshape(-1, v.shape[-1])
+    R, n = v2.shape
+    out = torch.empty((R, n), dtype=torch.float64, device=dev)
+    wb = lib().rc_ranks_workspace_bytes(R, n)
+    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+    a, rf = (-1.0, float(r)) if r is not None else (float(alpha), 0.0)
+    check(lib().rc_clustered_ranks(_ptr(v2), R, n, a, rf, _ptr(out), _ptr(ws), wb, _stream()))
+    return out.reshape(v.shape)
+
+
+def kendall_tau_b(x, y) -> torch.Tensor:
+    """tau[j][i] between x rows (double ranks) and y rows (int64 ranks); scipy.stats.kendalltau variant b."""
+    dev = require_cuda()
+    x = _f64(x, dev)
+    y = (y if isinstance(y, torch.Tensor) else torch.as_tensor(np.asarray(y))).to(device=dev, dtype=torch.int64).contiguous()
+    x2 = x.reshape(1, -1) if x.dim() == 1 else x
+    y2 = y.reshape(1, -1) if y.dim() == 1 else y
+    Rx, n = x2.shape
+    Ry = y2.shape[0]
+    if y2.shape[1] != n:
+        raise ValueError("x and y rows must have the same length")
+    tau = torch.empty((Rx, Ry), dtype=torch.float64, device=dev)
+    counts = torch.empty((Rx, Ry, 4), dtype=torch.int64, device=dev)
+    check(lib().rc_kendall_tau_b(_ptr(x2), Rx, _ptr(y2), Ry, n, _ptr(tau), _ptr(counts), _stream()))
+    return tau
+
+
+def kendall_matrix(wd_data_c, alpha: float = 0.05) -> torch.Tensor:
+    """jkt_or_ordinaltau_pairwise (generate_fig4_kendallrankanalysis.py:94-120): clustered ranks of row j
+    against ordinal ranks (+1) of row i."""
+    dev = require_cuda()
+    w = _f64(wd_data_c, dev)
+    cr = clustered_ranks(w, alpha=alpha)
+    rk = ranks(w) + 1
+    return kendall_tau_b(cr, rk)
+
+
+def mc_sweep_host(ctrl: np.ndarray, sigmas: np.ndarray, B: int, nspin: int, inspin: int, outspin: int, *,
+                  dkw_eps: float = 0.0, model: int = MODEL_COMPLEX3, zz: bool = False, seed: int = 0, c_offset: int = 0,
+                  b_offset: int = 0, replay: np.ndarray | None = None, fused: bool = False, want_fids: bool = False,
+                  stats_out: np.ndarray | None = None, fids_out: np.ndarray | None = None):
+    """Whole sweep through the C-ABI with HOST (numpy) buffers: H2D, evolution, statistics, D2H."""
+    require_cuda()
+    ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+    sigmas = np.ascontiguousarray(sigmas, dtype=np.float64).reshape(-1)
+    Cn, S = ctrl.shape[0], sigmas.shape[0]
+    if stats_out is None:
+        stats_out = np.empty((NUM_STATS, S, Cn))
+    if want_fids and fids_out is None:
+        fids_out = np.empty((S, Cn, B))
+    if replay is not None:
+        replay = np.ascontiguousarray(replay, dtype=np.float64)
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+    check(lib().rc_mc_sweep_host(vp(ctrl), Cn, nspin, inspin, outspin, vp(sigmas), S, B, model, int(bool(zz)),
+                                 C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, vp(replay), float(dkw_eps),
+                                 int(bool(fused)), vp(fids_out), vp(stats_out), _stream()))
+    return stats_out, fids_out
+
+
+def fp64_peak_tflops() -> float:
+    require_cuda()
+    v = C.c_double(0.0)
+    check(lib().rc_fp64_peak_tflops(C.byref(v), _stream()))
+    return v.value
+
+
+def device_info():
+    sm, maj, mnr = C.c_int(0), C.c_int(0), C.c_int(0)
+    check(lib().rc_device_info(C.byref(sm), C.byref(maj), C.byref(mnr)))
+    return sm.value, maj.value, mnr.value

@@ -1,0 +1,34 @@
+"""The RIM / Wasserstein robustness call named by the north star.
+
+Upstream ``rim_analysis.py`` is a toy plotting script that executes at import
+(rim_analysis.py:59,94-96); the real robustness functions live in
+``wd_sortof_fast_implementation.py:82-174``.  This module exposes those, plus the order-p helper
+of the toy script (rim_analysis.py:62-81) and the sweep-level entry point.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import engine
+from .wd_sortof_fast_implementation import (RIM_p, compute_dkw_error, dkw_ecdf_bounds, wd_from_ideal,  # noqa: F401
+                                            wd_from_ideal_batch, wd_from_ideal_zero)
+
+
+def p_order_rim(fids, orders=(1, 2, 3, 4)):
+    """rim_analysis.py:62-81: RIM_p over a list of orders."""
+    return [RIM_p(np.asarray(fids), p) for p in orders]
+
+
+def rim_sweep(controllers, noises, bootreps: int, Nspin: int, inspin: int, outspin: int, *, alpha: float = 0.05,
+              seed: int = 0, fused: bool = True, model: int = engine.MODEL_COMPLEX3, zz: bool = False):
+    """RIM (and the other 14 statistics) of every controller at every simulation noise level:
+    returns a dict key -> ndarray [S][C] with the reference's metric names (mcsim.py:178-183)."""
+    eps = float(compute_dkw_error(alpha, bootreps))
+    if fused:
+        st = engine.fidelity_stats(controllers, noises, bootreps, Nspin, inspin, outspin, dkw_eps=eps, seed=seed,
+                                   model=model, zz=zz)
+    else:
+        f = engine.fidelity_mc(controllers, noises, bootreps, Nspin, inspin, outspin, seed=seed, model=model, zz=zz)
+        st = engine.stats(f, eps)
+    st = st.cpu().numpy()
+    return {k: st[i] for i, k in enumerate(engine.STAT_KEYS)}

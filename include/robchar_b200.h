@@ -1,0 +1,130 @@
+/* robchar_b200 — C-ABI of the B200-native RobChar Monte-Carlo robustness hot path.
+ *
+ * The reference (qyber-black/Code-RobChar) has no FFI layer: its boundary is Python call
+ * signatures.  Each entry point below names the reference interface it stands behind
+ * (file:line in the upstream repo).  All pointers are plain; "dev" pointers are CUDA device
+ * addresses (e.g. torch.Tensor.data_ptr()), "host" pointers are ordinary host memory.  `stream`
+ * is a cudaStream_t passed as void* (NULL = default stream).  Every function returns an int
+ * status (RC_OK = 0) and records a message retrievable with rc_last_error() (thread local).
+ * The library owns no persistent state; scratch memory is caller-provided (size-query calls) in
+ * the device API and stream-ordered internal allocations in the *_host API.
+ *
+ * Tensor layouts (row-major, float64 unless noted):
+ *   ctrl    [C][N+1]        N biases then the evolution time (sign ignored, noise_model.py:99)
+ *   sigma   [S]             simulation noise levels (mcsim.py:204, 424-425)
+ *   replay  [S][C][B][K]    STANDARD normals in the reference's draw order, K = 3N (complex model,
+ *                           (z_ii, nn_i, nn2_i) per site, noise_model.py:135-147) or 2N (real
+ *                           model, qnewton.py:366-379); the device scales them by sigma
+ *   fids    [S][C][B]       fidelity samples (mcsim.py:423 `allfids`)
+ *   stats   [15][S][C]      metric tensors in the reference's .mcm key order (mcsim.py:178-183,
+ *                           487-498): for each of W, Q0.95, Q0.98, std, worst-case: centre,
+ *                           upper, lower
+ */
+#ifndef ROBCHAR_B200_H
+#define ROBCHAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RC_OK 0
+#define RC_ERR_BAD_ARG 1      /* bad nspin / inspin / outspin / sizes / model            */
+#define RC_ERR_NULL 2         /* required pointer is NULL                                */
+#define RC_ERR_CUDA 3         /* CUDA runtime error (message in rc_last_error)           */
+#define RC_ERR_NONCONV 4      /* eigensolver non-convergence count > 0 (host API only)   */
+#define RC_ERR_ILLEGAL_FIDS 5 /* fidelity outside [0,1]: wd_sortof_fast_implementation.py:23-25 */
+#define RC_ERR_WORKSPACE 6    /* workspace too small                                     */
+
+#define RC_MODEL_COMPLEX3 0 /* structured_perturbation.perturbation, noise_model.py:122-147 */
+#define RC_MODEL_REAL2 1    /* LBFGS.structured_perturabation, qnewton.py:366-379            */
+
+#define RC_NUM_STATS 15
+#define RC_MAX_NSPIN 32
+
+int rc_version(void);
+const char* rc_last_error(void);
+/* SM count and compute capability of the current device. */
+int rc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Evolution + fidelity for every (sigma level, controller, draw).
+ * Stands behind MCDataSim.get_algo_fid_dist's triple loop (mcsim.py:422-456) calling
+ * noise_model_base.evaluate_noisy_fidelity(x, ham_noisy=True) (noise_model.py:98-109), and
+ * LBFGS.fidelity_ss(x, ham_noisy=True) (qnewton.py:383-400) for RC_MODEL_REAL2 / zz.
+ * replay_dev == NULL: noise from in-kernel Philox4x32-10 keyed by `seed`, counters from the
+ * GLOBAL indices (sigma idx, c_offset + c, b_offset + b) — sharding invariant.
+ * NaN controller rows give NaN fidelities (mcsim.py:369-374, 443).
+ * nonconv_dev: optional device counter (uint64) incremented per non-converged evaluation. */
+int rc_fidelity_mc(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
+                   const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed,
+                   int64_t c_offset, int64_t b_offset, const double* replay_dev, double* fids_dev,
+                   unsigned long long* nonconv_dev, void* stream);
+
+/* The standard normals rc_fidelity_mc's Philox mode uses, written in replay layout [S][C][B][K]
+ * (discarded site-0 coupling slots are zero).  Lets callers replay a GPU sweep through the
+ * reference CPU path. */
+int rc_philox_normals(int64_t C, int nspin, int S, int64_t B, int model, uint64_t seed, int64_t c_offset,
+                      int64_t b_offset, double* normals_dev, void* stream);
+
+/* Statistics of each (sigma, controller) segment of B samples: segmented sort + fused
+ * 1-Wasserstein/RIM, Q-threshold, std and worst-case reductions for the centre and the two
+ * DKW-shifted variants.  Stands behind wd_from_ideal (wd_sortof_fast_implementation.py:82-116),
+ * the metric registry (mcsim.py:144-183) and get_metrics_dict's DKW loop (mcsim.py:482-498).
+ * dkw_eps = compute_dkw_error(alpha, B) (wd_sortof_fast_implementation.py:38-39); pass 0 for none.
+ * sorted_dev: optional [nseg][B] output of the ascending-sorted samples (may alias fids_dev:
+ * wd_from_ideal sorts its argument in place).  illegal_dev: optional uint64 device counter of
+ * samples violating |f - 1e-8| <= 1.  stats_dev: [15][nseg]. */
+size_t rc_stats_workspace_bytes(int64_t nseg, int64_t B);
+int rc_stats(const double* fids_dev, int64_t nseg, int64_t B, double dkw_eps, double* stats_dev,
+             double* sorted_dev, unsigned long long* illegal_dev, void* workspace_dev, size_t workspace_bytes,
+             void* stream);
+
+/* Fused evolution + statistics that never materialises the fidelity tensor (streaming moments;
+ * W = mean(1 - f), identical to the sorted formula up to rounding).  Same arguments as
+ * rc_fidelity_mc; stats_dev [15][S][C].  workspace: rc_fidelity_stats_workspace_bytes(S*C). */
+size_t rc_fidelity_stats_workspace_bytes(int64_t nseg, int64_t B);
+int rc_fidelity_stats(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
+                      const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed,
+                      int64_t c_offset, int64_t b_offset, const double* replay_dev, double dkw_eps,
+                      double* stats_dev, unsigned long long* nonconv_dev, void* workspace_dev,
+                      size_t workspace_bytes, void* stream);
+
+/* Ordinal ranks 0..n-1 of each row, ascending, NaN last, ties by index (stable).
+ * MCDataSim.get_ranks (mcsim.py:513-518).  values [R][n] -> ranks int64 [R][n]. */
+size_t rc_ranks_workspace_bytes(int64_t R, int64_t n);
+int rc_ranks(const double* values_dev, int64_t R, int64_t n, int64_t* ranks_dev, void* workspace_dev,
+             size_t workspace_bytes, void* stream);
+
+/* Clustered ranks with discrepancy radius r_row = alpha * (max - min) of the row, or the fixed
+ * radius `r_fixed` when alpha < 0.  get_ranks_clustered_little
+ * (generate_fig4_kendallrankanalysis.py:146-164).  values [R][n] -> double [R][n]. */
+int rc_clustered_ranks(const double* values_dev, int64_t R, int64_t n, double alpha, double r_fixed,
+                       double* cranks_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Kendall tau-b matrix tau[j][i] between x rows j (double ranks, ties allowed) and y rows i
+ * (int64 ranks): scipy.stats.kendalltau as called by jkt_or_ordinaltau_pairwise
+ * (generate_fig4_kendallrankanalysis.py:94-120).  Integer pair counts, then
+ * (tot - xtie - ytie + ntie - 2 dis) / sqrt(tot - xtie) / sqrt(tot - ytie).
+ * counts_dev: scratch int64 [Rx][Ry][4]. */
+int rc_kendall_tau_b(const double* x_dev, int64_t Rx, const int64_t* y_dev, int64_t Ry, int64_t n,
+                     double* tau_dev, long long* counts_dev, void* stream);
+
+/* Whole sweep with HOST buffers: H2D of controllers/sigmas(/replay), evolution, statistics, D2H of
+ * the 15 metric tensors (and of the fidelity tensor when fids_host != NULL).  This is what
+ * MCDataSim.get_metrics_dict (mcsim.py:463-510) computes from scratch.
+ * Returns RC_ERR_NONCONV / RC_ERR_ILLEGAL_FIDS after completing if either counter is non-zero. */
+int rc_mc_sweep_host(const double* ctrl_host, int64_t C, int nspin, int inspin, int outspin,
+                     const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
+                     int64_t c_offset, int64_t b_offset, const double* replay_host, double dkw_eps,
+                     int fused, double* fids_host, double* stats_host, void* stream);
+
+/* FP64 FMA throughput micro-benchmark of the current device (TFLOP/s, 2 flops per DFMA); used as
+ * the roofline denominator of the evolution kernel. */
+int rc_fp64_peak_tflops(double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROBCHAR_B200_H */

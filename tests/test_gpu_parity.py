@@ -1,0 +1,384 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything calls the product through the C-ABI
+(engine -> ctypes -> librobchar_b200.so) and compares with the CPU oracle / committed goldens.
+
+Tolerances (north star): fidelity 1e-10 absolute in fp64, RIM 1e-9, rankings bit-exact
+(modulo exact ties, which both sides break by index)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.stats
+
+from conftest import load_golden
+from oracle import robchar_oracle as orc
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+FID_TOL = 1e-10
+RIM_TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import robchar_b200
+    assert torch.cuda.is_available()
+    return robchar_b200
+
+
+def nominal(rb, ctrl, n, i, o, **kw):
+    return rb.engine.fidelity_mc(ctrl, np.zeros(1), 1, n, i, o, **kw).cpu().numpy()[0, :, 0]
+
+
+def test_kat_bestfid(rb):
+    g = load_golden("kat_bestfid.npz")
+    total = 0
+    for key, n, i, o in g["meta"]:
+        n, i, o = int(n), int(i), int(o)
+        f = nominal(rb, g[key + "_ctrl"], n, i, o)
+        assert np.abs(f - g[key + "_best_fid"]).max() < FID_TOL, key
+        total += len(f)
+    assert total >= 700
+
+
+def test_kat_mc_zero_rows(rb):
+    g = load_golden("kat_mc_zero.npz")
+    for key, n, i, o in g["meta"]:
+        n, i, o = int(n), int(i), int(o)
+        f = nominal(rb, g[key + "_ctrl"], n, i, o)
+        ref = g[key + "_fid0"]
+        assert np.array_equal(np.isnan(f), np.isnan(ref)), key
+        ok = ~np.isnan(ref)
+        assert np.abs(f[ok] - ref[ok]).max() < FID_TOL, key
+
+
+@pytest.mark.parametrize("name", ["replay_n4_0_2", "replay_n5_0_4", "replay_n6_0_3", "replay_n7_0_6"])
+def test_replay_reference_run(rb, name):
+    """Same seeded stream as the unmodified reference run: fidelities, 15 metrics, ranks, Kendall."""
+    g = load_golden(name + ".npz")
+    n, i, o = (int(v) for v in g["nio"])
+    ref = g["fids"]
+    S, C, B = ref.shape
+    f = rb.engine.fidelity_mc(g["ctrl"], g["sigmas"], B, n, i, o, replay=g["normals"]).cpu().numpy()
+    assert np.array_equal(np.isnan(f), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.abs(f[ok] - ref[ok]).max() < FID_TOL
+    eps = float(orc.compute_dkw_error(float(g["alpha"]), B))
+    st = rb.engine.stats(torch.as_tensor(f).cuda(), eps).cpu().numpy()
+    names = [str(s) for s in g["metric_names"]]
+    assert names == rb.engine.STAT_KEYS
+    for k, nm in enumerate(names):
+        a, b = st[k], g["metrics"][k]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), nm
+        okm = ~np.isnan(b)
+        if nm.startswith("Q th."):
+            assert np.array_equal(a[okm], b[okm]), nm          # integer counts / B: exact
+            assert np.array_equal(np.signbit(a), np.signbit(b)), nm
+        else:
+            assert np.abs(a[okm] - b[okm]).max() < RIM_TOL, nm
+    # fused streaming path on the same replayed stream
+    stf = rb.engine.fidelity_stats(g["ctrl"], g["sigmas"], B, n, i, o, dkw_eps=eps, replay=g["normals"]).cpu().numpy()
+    for k, nm in enumerate(names):
+        okm = ~np.isnan(g["metrics"][k])
+        assert np.array_equal(np.isnan(stf[k]), ~okm), nm
+        assert np.abs(stf[k][okm] - g["metrics"][k][okm]).max() < RIM_TOL, nm
+    # ranking stage on the reference's RIM matrix: bit-exact
+    W = g["metrics"][names.index(orc.METRIC_W)]
+    Wc = np.ascontiguousarray(W[:, ~np.isnan(W[0])])
+    assert np.array_equal(rb.engine.ranks(Wc[0]).cpu().numpy(), g["ranks_row0"])
+    cr = rb.engine.clustered_ranks(Wc, alpha=0.05).cpu().numpy()
+    assert np.array_equal(cr[3], g["clustered_row3"])
+    tau = rb.engine.kendall_matrix(Wc, alpha=0.05).cpu().numpy()
+    assert np.array_equal(tau, g["kendall"], equal_nan=True)
+    # and end to end from the device's own RIMs: rankings identical
+    Wd = np.ascontiguousarray(st[0][:, ~np.isnan(W[0])])
+    assert np.array_equal(rb.engine.ranks(Wd).cpu().numpy(), np.stack([orc.get_ranks(r) for r in Wc]))
+
+
+def test_real2_and_zz(rb):
+    g = load_golden("replay_real2_zz.npz")
+    for tag in ("n5", "n6zz", "n16zz"):
+        n, i, o, zz = (int(v) for v in g[tag + "_meta"])
+        ctrl, nrm = g[tag + "_ctrl"], g[tag + "_normals"]
+        Cn, B, K = nrm.shape
+        f = rb.engine.fidelity_mc(ctrl, [float(g[tag + "_sigma"])], B, n, i, o, model=rb._lib.MODEL_REAL2, zz=bool(zz),
+                                  replay=nrm.reshape(1, Cn, B, K)).cpu().numpy()[0]
+        assert np.abs(f - g[tag + "_fids"]).max() < FID_TOL, tag
+        f0 = nominal(rb, ctrl, n, i, o, model=rb._lib.MODEL_REAL2, zz=bool(zz))
+        assert np.abs(f0 - g[tag + "_nominal"]).max() < FID_TOL, tag
+
+
+def test_large_n_reference(rb):
+    g = load_golden("replay_large_n.npz")
+    for n in (10, 16, 32):
+        ctrl, nrm = g[f"n{n}_ctrl"], g[f"n{n}_normals"]
+        Cn, B, K = nrm.shape
+        f = rb.engine.fidelity_mc(ctrl, [float(g["sigma"])], B, n, 0, n - 1, replay=nrm.reshape(1, Cn, B, K)).cpu().numpy()[0]
+        assert np.abs(f - g[f"n{n}_fids"]).max() < FID_TOL, n
+        assert np.abs(nominal(rb, ctrl, n, 0, n - 1) - g[f"n{n}_nominal"]).max() < FID_TOL, n
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8, 9, 11, 13, 16, 17, 20, 24, 32])
+@pytest.mark.parametrize("model", [0, 1])
+def test_every_chain_length_vs_oracle(rb, n, model):
+    rs = np.random.RandomState(100 + n)
+    C, B, S = 7, 37, 3                       # ragged sizes: tiles not multiples of the CTA
+    ctrl = orc.synthetic_controllers(C, n, seed=n)
+    ctrl[2, -1] *= -1                        # abs(T) (noise_model.py:99)
+    sig = np.array([0.0, 0.05, 0.1])
+    K = (3 if model == 0 else 2) * n
+    nrm = rs.standard_normal((S, C, B, K))
+    i, o = rs.randint(0, n), rs.randint(0, n)
+    zz = bool(n % 2)
+    f = rb.engine.fidelity_mc(ctrl, sig, B, n, i, o, model=model, zz=zz, replay=nrm).cpu().numpy()
+    ref = orc.fidelity_mc_replay(ctrl, sig, nrm, n, i, o, model=model, zz=zz)
+    assert np.abs(f - ref).max() < FID_TOL
+
+
+def test_nan_controllers_and_empty(rb):
+    n = 5
+    ctrl = orc.synthetic_controllers(6, n)
+    ctrl[1] = np.nan
+    ctrl[4, 2] = np.nan
+    f = rb.engine.fidelity_mc(ctrl, [0.0, 0.05], 9, n, 0, 4, seed=1).cpu().numpy()
+    assert np.isnan(f[:, [1, 4]]).all() and np.isfinite(f[:, [0, 2, 3, 5]]).all()
+    assert rb.engine.fidelity_mc(ctrl[:0], [0.05], 4, n, 0, 4).shape == (1, 0, 4)
+    assert rb.engine.fidelity_mc(ctrl, [0.05], 0, n, 0, 4).shape == (1, 6, 0)
+    with pytest.raises(ValueError):
+        rb.engine.fidelity_mc(ctrl, [0.05], 4, n, 0, 7)
+    with pytest.raises(ValueError):
+        rb.engine.fidelity_mc(orc.synthetic_controllers(2, 40), [0.05], 4, 40, 0, 7)
+
+
+def test_philox_mode_matches_oracle_on_its_own_draws(rb):
+    """Philox mode == replay of the normals rc_philox_normals reports == oracle on those normals."""
+    for n, model in [(4, 0), (7, 0), (7, 1), (12, 0), (20, 0)]:
+        C, B = 5, 70
+        ctrl = orc.synthetic_controllers(C, n, seed=3)
+        sig = np.array([0.0, 0.03, 0.1])
+        kw = dict(model=model, seed=12345, c_offset=11, b_offset=5)
+        z = rb.engine.philox_normals(C, n, 3, B, **kw)
+        f = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, n - 1, **kw)
+        f2 = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, n - 1, model=model, replay=z)
+        assert torch.equal(f, f2)
+        ref = orc.fidelity_mc_replay(ctrl, sig, z.cpu().numpy(), n, 0, n - 1, model=model)
+        assert np.abs(f.cpu().numpy() - ref).max() < FID_TOL
+
+
+def test_philox_normals_distribution_and_sharding(rb):
+    n = 7
+    z = rb.engine.philox_normals(64, n, 2, 500, seed=7).cpu().numpy()
+    used = np.ones(3 * n, bool); used[[1, 2]] = False      # discarded site-0 coupling draws
+    assert np.all(z[..., ~used] == 0)
+    v = z[..., used].reshape(-1)
+    assert abs(v.mean()) < 5e-3 and abs(v.std() - 1) < 5e-3
+    assert scipy.stats.kstest(v[:200000], "norm").pvalue > 1e-3
+    assert abs(np.corrcoef(v[:-1], v[1:])[0, 1]) < 5e-3
+    # sharding invariance: controller block [20, 40) computed alone equals the slice of the whole
+    ctrl = orc.synthetic_controllers(64, n)
+    sig = np.array([0.02, 0.08])
+    whole = rb.engine.fidelity_mc(ctrl, sig, 50, n, 0, 6, seed=99)
+    part = rb.engine.fidelity_mc(ctrl[20:40], sig, 50, n, 0, 6, seed=99, c_offset=20)
+    assert torch.equal(whole[:, 20:40], part)
+    draws = rb.engine.fidelity_mc(ctrl, sig, 20, n, 0, 6, seed=99, b_offset=30)
+    assert torch.equal(whole[:, :, 30:50], draws)
+    other = rb.engine.fidelity_mc(ctrl, sig, 50, n, 0, 6, seed=100)
+    assert not torch.equal(whole, other)
+
+
+@pytest.mark.parametrize("B", [1, 2, 31, 100, 1000, 4096, 5000])
+def test_stats_vs_oracle(rb, B):
+    rs = np.random.RandomState(B)
+    S, C = 3, 17
+    f = np.clip(rs.normal(0.93, 0.05, (S, C, B)), 0, 1)
+    f[0, 3] = 1.0
+    f[1, 5] = 0.0
+    f[2, 7] = np.nan
+    f[1, 9] = 0.95
+    eps = float(orc.compute_dkw_error(0.05, B))
+    st = rb.engine.stats(torch.as_tensor(f).cuda(), eps).cpu().numpy()
+    m = orc.metrics(f.copy(), 0.05)
+    for k, key in enumerate(rb.engine.STAT_KEYS):
+        a, b = st[k], m[key]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), key
+        ok = ~np.isnan(b)
+        if key.startswith("Q th."):
+            assert np.array_equal(a[ok], b[ok]), key
+        else:
+            assert np.abs(a[ok] - b[ok]).max() < 1e-12, key
+    # in-place sort side effect of wd_from_ideal (wd_sortof_fast_implementation.py:105)
+    t = torch.as_tensor(f[:2]).cuda().contiguous()
+    rb.engine.stats(t, 0.0, sort_inplace=True)
+    assert np.array_equal(t.cpu().numpy(), np.sort(f[:2], axis=-1))
+
+
+def test_stats_illegal_fids_raise(rb):
+    with pytest.raises(AssertionError):
+        rb.engine.stats(torch.tensor([[0.5, 2.5, 0.1]], dtype=torch.float64).cuda())
+    with pytest.raises(AssertionError):
+        rb.wd_from_ideal(np.array([0.5, -1.5]))
+
+
+def test_wd_api_kats(rb):
+    g = load_golden("kat_wd.npz")
+    for k in g["names"]:
+        k = str(k)
+        v = g[k]
+        assert abs(rb.wd_from_ideal(v.copy()) - float(g[k + "_wd"])) < 1e-13
+        assert abs(rb.wd_from_ideal_zero(v.copy()) - float(g[k + "_wd0"])) < 1e-13
+        for p in (1, 2, 3):
+            assert abs(rb.RIM_p(v.copy(), p) - float(g[f"{k}_rim{p}"])) < 1e-13
+    X = g["X"].copy()[::-1].copy()
+    assert abs(rb.wd_from_ideal(X) - 0.507069833) < 1e-9      # wd_sortof_fast_implementation.py:184-198
+    assert np.array_equal(X, np.sort(g["X"]))                  # argument sorted in place
+    assert abs(rb.wd_from_ideal(0.76) - 0.24) < 1e-15          # scalar (…:241-245)
+    assert abs(rb.wd_from_ideal([1, 0, 1, 1, 0]) - 0.4) < 1e-15
+    assert rb.RIM_p(X, 0) == 1
+
+
+@pytest.mark.parametrize("n", [2, 7, 100, 1000, 5000])
+def test_ranks_clustered_kendall_vs_oracle(rb, n):
+    rs = np.random.RandomState(n)
+    R = 4
+    v = rs.uniform(0, 0.3, (R, n))
+    v[1, : n // 2] = np.round(v[1, : n // 2], 2)          # exact ties
+    v[2] = v[2, 0]                                        # a fully tied row -> NaN tau
+    if n > 5:
+        v[3, 2] = np.nan
+    rk = rb.engine.ranks(v).cpu().numpy()
+    for r in range(R):
+        assert np.array_equal(rk[r], orc.get_ranks(v[r])), r
+    vv = v[:3]
+    cr = rb.engine.clustered_ranks(vv, alpha=0.05).cpu().numpy()
+    for r in range(3):
+        rr = 0.05 * (vv[r].max() - vv[r].min())
+        assert np.array_equal(cr[r], orc.get_ranks_clustered_little(vv[r], r=rr)), r
+    cr2 = rb.engine.clustered_ranks(vv, r=1e-3).cpu().numpy()
+    assert np.array_equal(cr2[0], orc.get_ranks_clustered_little(vv[0], r=1e-3))
+    if n <= 1000:
+        tau = rb.engine.kendall_matrix(vv, alpha=0.05).cpu().numpy()
+        want = np.array([[scipy.stats.kendalltau(cr[j], rk[i] + 1).correlation for i in range(3)] for j in range(3)])
+        assert np.array_equal(tau, want, equal_nan=True)
+    else:
+        tau = rb.engine.kendall_tau_b(cr[:1], rk[:1] + 1).cpu().numpy()
+        assert tau[0, 0] == scipy.stats.kendalltau(cr[0], rk[0] + 1).correlation
+
+
+def test_host_buffer_sweep_equals_device_path(rb):
+    n = 6
+    ctrl = orc.synthetic_controllers(40, n)
+    sig = np.linspace(0, 0.1, 4)
+    B = 64
+    eps = float(orc.compute_dkw_error(0.05, B))
+    st_h, f_h = rb.engine.mc_sweep_host(ctrl, sig, B, n, 0, 3, dkw_eps=eps, seed=5, want_fids=True)
+    f_d = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, 3, seed=5)
+    assert np.array_equal(f_h, f_d.cpu().numpy())
+    assert np.array_equal(st_h, rb.engine.stats(f_d, eps).cpu().numpy())
+    st_f, _ = rb.engine.mc_sweep_host(ctrl, sig, B, n, 0, 3, dkw_eps=eps, seed=5, fused=True)
+    assert np.abs(st_f - st_h).max() < 1e-12
+
+
+def test_fused_equals_materialised_large_B(rb):
+    n = 7
+    ctrl = orc.synthetic_controllers(6, n)
+    sig = np.array([0.0, 0.05])
+    B = 10000
+    eps = float(orc.compute_dkw_error(0.05, B))
+    f = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, 6, seed=8)
+    a = rb.engine.stats(f, eps).cpu().numpy()
+    b = rb.engine.fidelity_stats(ctrl, sig, B, n, 0, 6, dkw_eps=eps, seed=8).cpu().numpy()
+    assert np.abs(a - b).max() < 1e-12
+    m = orc.metrics(f.cpu().numpy()[:, :2], 0.05)
+    for k, key in enumerate(rb.engine.STAT_KEYS):
+        assert np.abs(a[k][:, :2] - m[key]).max() < 1e-12, key
+    # sigma = 0 row: every draw equals the nominal fidelity, std exactly 0
+    assert np.all(b[9][0] == 0.0) and np.all(a[9][0] == 0.0)
+    assert np.abs(a[0][0] - (1 - orc.fidelity_batch(ctrl, n, 0, 6))).max() < FID_TOL
+
+
+def test_noise_model_api_drop_in(rb):
+    """structured_perturbation.evaluate_noisy_fidelity consumes np.random exactly like upstream."""
+    n = 5
+    x = orc.synthetic_controllers(1, n)[0]
+    m = rb.structured_perturbation(Nspin=n, inspin=0, outspin=4, noise=0.05)
+    port = orc.ReferencePathPort(n, 0, 4, 0.05)
+    np.random.seed(42)
+    got = [m.evaluate_noisy_fidelity(x, True) for _ in range(5)]
+    m.rng(scale=0.1)
+    got += [m.evaluate_noisy_fidelity(list(x), True) for _ in range(3)]
+    np.random.seed(42)
+    want = [port.evaluate_noisy_fidelity(x, True) for _ in range(5)]
+    port.rng(scale=0.1)
+    want += [port.evaluate_noisy_fidelity(x, True) for _ in range(3)]
+    assert np.abs(np.array(got) - np.array(want)).max() < FID_TOL
+    assert abs(m.evaluate_noisy_fidelity(x) - orc.evaluate_fidelity(x, n, 0, 4)) < FID_TOL
+    u = rb.structured_perturbation(Nspin=n, inspin=0, outspin=4, rng=rb.noise_function(np.random.uniform, low=0, high=0.2))
+    np.random.seed(1)
+    z = u.perturbation()
+    assert np.allclose(z, z.conj().T) and z.dtype == np.complex128
+    fb = m.evaluate_noisy_fidelity_batch(orc.synthetic_controllers(3, n), draws=16, noises=[0.0, 0.05], seed=2)
+    assert fb.shape == (2, 3, 16) and np.all((fb >= 0) & (fb <= 1))
+
+
+def test_mcdatasim_reproduces_reference_run(rb, tmp_path, monkeypatch):
+    """MCDataSim(rng_mode='numpy') under the golden's seed reproduces the unmodified reference's
+    .mc tensor and .mcm metrics (config 1: N=4 0->2 LBFGS controllers, incl. NaN padding)."""
+    g = load_golden("replay_n4_0_2.npz")
+    n, i, o = (int(v) for v in g["nio"])
+    S, C, B = g["fids"].shape
+    ctrl = g["ctrl"]
+    conts = [list(map(float, c)) for c in ctrl[~np.isnan(ctrl).any(axis=1)]]
+    os.makedirs(tmp_path / "experiments" / "golden")
+    json.dump({"lbfgs": {str(n): {"controller": conts}}},
+              open(tmp_path / "experiments" / "golden" / f"ppo_spin_{n}_{i}-{o}_c_{C}", "w"))
+    monkeypatch.chdir(tmp_path)
+    sim = rb.MCDataSim(experiment_name="golden", Nspin=n, inspin=i, outspin=o, noises=g["sigmas"], bootreps=B,
+                       numcontrollers=C, topk=10, rng_mode="numpy")
+    np.random.seed(int(g["seed"]))
+    md = sim.get_metrics_dict(None, g["sigmas"], algoname="lbfgs")
+    assert os.path.exists(sim.get_mcname(None, g["sigmas"])) and os.path.exists(sim.get_mcname(None, g["sigmas"]) + "m")
+    fids = np.array(json.load(open(sim.get_mcname(None, g["sigmas"])))["lbfgs"], dtype=np.float64)
+    ok = ~np.isnan(g["fids"])
+    assert np.array_equal(np.isnan(fids), ~ok)
+    assert np.abs(fids[ok] - g["fids"][ok]).max() < FID_TOL
+    assert list(md["lbfgs"].keys()) == [str(s) for s in g["metric_names"]]
+    for k, nm in enumerate(g["metric_names"]):
+        a = np.array(md["lbfgs"][str(nm)], dtype=np.float64)
+        okm = ~np.isnan(g["metrics"][k])
+        assert np.abs(a[okm] - g["metrics"][k][okm]).max() < RIM_TOL, nm
+    # cache hit path returns the stored dict
+    assert sim.get_metrics_dict(None, g["sigmas"], algoname="lbfgs") == json.load(open(sim.get_mcname(None, g["sigmas"]) + "m"))
+    W = np.array(md["lbfgs"][orc.METRIC_W])
+    c, u, l = sim.get_top_k_by_fid(W[:, :100], W[:, :100], W[:, :100], 10, fid_thres=None)
+    assert c.shape == (S, 10)
+    out = sim.get_best_controller_perf(W[:, :100], contcount=100)
+    want = orc.best_controller_perf(W[:, :100])
+    for a, b in zip(out, want):
+        assert np.array_equal(a, b)
+
+
+def test_full_size_properties_nspin7(rb):
+    """Headline size (N=7 0->6, S=11, B=100, 19 000 controllers): size-independent properties."""
+    n, C, B = 7, 19000, 100
+    ctrl = orc.synthetic_controllers(C, n)
+    sig = np.linspace(0, 0.1, 11)
+    eps = float(orc.compute_dkw_error(0.05, B))
+    f = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, 6, seed=1)
+    f2 = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, 6, seed=1)
+    assert torch.equal(f, f2)                                           # deterministic
+    assert bool(((f >= 0) & (f <= 1 + 1e-12)).all())
+    assert bool((f[0] == f[0, :, :1]).all())                            # sigma = 0: all draws identical
+    sub = np.arange(0, C, 997)
+    assert np.abs(f[0, sub, 0].cpu().numpy() - orc.fidelity_batch(ctrl[sub], n, 0, 6)).max() < FID_TOL
+    st = rb.engine.stats(f, eps)
+    W = st[0]
+    assert torch.allclose(W, 1 - f.mean(dim=2), atol=1e-12, rtol=0)      # W1 to delta(1) == mean infidelity
+    assert bool((st[1] >= st[0] - 1e-15).all()) and bool((st[2] <= st[0] + 1e-15).all())   # upper/lower bracket
+    rk = rb.engine.ranks(W)
+    assert torch.equal(torch.sort(rk, dim=1).values, torch.arange(C, device=rk.device).expand(11, C))
+    assert bool((torch.gather(W, 1, torch.argsort(rk, dim=1)).diff(dim=1) >= 0).all())      # sortedness
+    top = torch.nonzero(rk[0] <= 99).reshape(-1)
+    tau = rb.engine.kendall_matrix(W[:, top].contiguous(), alpha=0.05).cpu().numpy()
+    assert tau.shape == (11, 11) and np.all(np.abs(tau[np.isfinite(tau)]) <= 1)
+    assert tau[0, 0] > 0.9
