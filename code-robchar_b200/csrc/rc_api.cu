@@ -15,6 +15,24 @@ struct DevBuf {
     template <class T> T* as() { return (T*)p; }
 };
 
+// Stream-ordered scratch comes from the device's default memory pool; keep freed blocks cached in
+// the pool (default behaviour returns them to the OS at every synchronisation, which makes each
+// sweep pay cudaMalloc/cudaFree of the fidelity tensor again).
+static cudaError_t keep_pool_memory() {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || done[dev]) return cudaSuccess;
+    cudaMemPool_t pool;
+    e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (e != cudaSuccess) return e;
+    unsigned long long thr = ~0ull;
+    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
+}
+
 // 8 independent dependent-FMA chains per thread; 2 flops per DFMA.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -67,6 +85,7 @@ extern "C" int rc_mc_sweep_host(const double* ctrl_host, int64_t C, int nspin, i
     if (!stats_host && !fids_host) return set_error(RC_ERR_NULL, "rc_mc_sweep_host: no output requested");
     if (fused && fids_host) return set_error(RC_ERR_BAD_ARG, "rc_mc_sweep_host: fused mode does not materialise fidelities");
     cudaStream_t st = (cudaStream_t)stream;
+    RC_CUDA_TRY(keep_pool_memory());
     const int K = (model == RC_MODEL_COMPLEX3 ? 3 : 2) * nspin;
     DevBuf ctrl(st), sigma(st), replay(st), fids(st), stats(st), ws(st), counters(st);
     RC_CUDA_TRY(ctrl.alloc((size_t)C * (nspin + 1) * 8));

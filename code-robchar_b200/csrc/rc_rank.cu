@@ -102,10 +102,11 @@ __global__ void __launch_bounds__(KT_THREADS) kendall_count_kernel(const double*
                                                                    unsigned long long* __restrict__ counts) {
     __shared__ double sx[KT_THREADS];
     __shared__ long long sy[KT_THREADS];
+    const long long grp = blockIdx.z;
     const long long pair = blockIdx.y;
     const long long j = pair / Ry, i = pair - j * Ry;
-    const double* xr = x + j * n;
-    const long long* yr = y + i * n;
+    const double* xr = x + (grp * Rx + j) * n;
+    const long long* yr = y + (grp * Ry + i) * n;
     const long long a = (long long)blockIdx.x * KT_THREADS + threadIdx.x;
     const double xa = a < n ? xr[a] : 0.0;
     const long long ya = a < n ? yr[a] : 0;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(KT_THREADS) kendall_count_kernel(const double*
         nt += __shfl_down_sync(0xffffffffu, nt, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        unsigned long long* c = counts + pair * 4;
+        unsigned long long* c = counts + (grp * Rx * Ry + pair) * 4;
         if (dis) atomicAdd(c + 0, dis);
         if (xt) atomicAdd(c + 1, xt);
         if (yt) atomicAdd(c + 2, yt);
@@ -252,22 +253,27 @@ extern "C" int rc_clustered_ranks(const double* values_dev, int64_t R, int64_t n
     return RC_OK;
 }
 
-extern "C" int rc_kendall_tau_b(const double* x_dev, int64_t Rx, const int64_t* y_dev, int64_t Ry, int64_t n,
-                                double* tau_dev, long long* counts_dev, void* stream) {
-    if (Rx < 0 || Ry < 0 || n < 0) return set_error(RC_ERR_BAD_ARG, "rc_kendall_tau_b: negative size");
-    if (Rx == 0 || Ry == 0) return RC_OK;
+extern "C" int rc_kendall_tau_b_batched(const double* x_dev, const int64_t* y_dev, int64_t G, int64_t Rx, int64_t Ry,
+                                        int64_t n, double* tau_dev, long long* counts_dev, void* stream) {
+    if (G < 0 || Rx < 0 || Ry < 0 || n < 0) return set_error(RC_ERR_BAD_ARG, "rc_kendall_tau_b: negative size");
+    if (G == 0 || Rx == 0 || Ry == 0) return RC_OK;
     if (!x_dev || !y_dev || !tau_dev || !counts_dev) return set_error(RC_ERR_NULL, "rc_kendall_tau_b: null pointer");
-    if (Rx * Ry > 65535) return set_error(RC_ERR_BAD_ARG, "rc_kendall_tau_b: more than 65535 row pairs");
+    if (Rx * Ry > 65535 || G > 65535) return set_error(RC_ERR_BAD_ARG, "rc_kendall_tau_b: more than 65535 row pairs or groups");
     cudaStream_t st = (cudaStream_t)stream;
-    RC_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, (size_t)Rx * Ry * 4 * sizeof(long long), st));
+    const long long np = G * Rx * Ry;
+    RC_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, (size_t)np * 4 * sizeof(long long), st));
     if (n >= 2) {
-        dim3 grid((unsigned)((n + KT_THREADS - 1) / KT_THREADS), (unsigned)(Rx * Ry));
+        dim3 grid((unsigned)((n + KT_THREADS - 1) / KT_THREADS), (unsigned)(Rx * Ry), (unsigned)G);
         kendall_count_kernel<<<grid, KT_THREADS, 0, st>>>(x_dev, Rx, (const long long*)y_dev, Ry, n,
                                                          (unsigned long long*)counts_dev);
         RC_CUDA_TRY(cudaGetLastError());
     }
-    long long np = Rx * Ry;
     kendall_finalize_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>((const unsigned long long*)counts_dev, np, n, tau_dev);
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
+}
+
+extern "C" int rc_kendall_tau_b(const double* x_dev, int64_t Rx, const int64_t* y_dev, int64_t Ry, int64_t n,
+                                double* tau_dev, long long* counts_dev, void* stream) {
+    return rc_kendall_tau_b_batched(x_dev, y_dev, 1, Rx, Ry, n, tau_dev, counts_dev, stream);
 }

@@ -20,6 +20,15 @@ METRIC_NAMES = [METRIC_W, "Q th. 0.95", "Q th. 0.98", "std", "worst case fid"]
 STAT_KEYS = [m + s for m in METRIC_NAMES for s in ("", " upper", " lower")]
 
 
+# kernels launched by this process through the C-ABI (bench.py reports it as gpu_launches)
+LAUNCHES = 0
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def require_cuda() -> torch.device:
     if not torch.cuda.is_available():
         raise _lib.RobcharLibraryError("robchar_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
@@ -94,6 +103,7 @@ def fidelity_mc(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, *, 
     check(lib().rc_fidelity_mc(_ptr(ctrl), Cn, nspin, inspin, outspin, _ptr(sigmas), S, B, model, int(bool(zz)),
                                C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, _ptr(replay), _ptr(out),
                                counters.nonconv_ptr, _stream()))
+    _count(1)
     if own and check_convergence:
         counters.raise_if_set()
     return out
@@ -125,6 +135,7 @@ def stats(fids: torch.Tensor, dkw_eps: float = 0.0, *, sort_inplace: bool = Fals
     cnt = Counters(dev)
     check(lib().rc_stats(_ptr(fids), nseg, B, float(dkw_eps), _ptr(out), _ptr(fids) if sort_inplace else C.c_void_p(0),
                          cnt.illegal_ptr, _ptr(ws), wb, _stream()))
+    _count(1 if B <= 4096 else 2 * max(1, -(-nseg // max(1, (1 << 28) // B))))
     if check_legal:
         cnt.raise_if_set()
     return out
@@ -147,6 +158,7 @@ def fidelity_stats(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, 
     check(lib().rc_fidelity_stats(_ptr(ctrl), Cn, nspin, inspin, outspin, _ptr(sigmas), S, B, model, int(bool(zz)),
                                   C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, _ptr(replay), float(dkw_eps),
                                   _ptr(out), cnt.nonconv_ptr, _ptr(ws), wb, _stream()))
+    _count(2)
     if check_convergence:
         cnt.raise_if_set()
     return out
@@ -165,6 +177,7 @@ def ranks(values) -> torch.Tensor:
         raise ValueError("ranking problem too large")
     ws = torch.empty(wb, dtype=torch.uint8, device=dev)
     check(lib().rc_ranks(_ptr(v2), R, n, _ptr(out), _ptr(ws), wb, _stream()))
+    _count(2 if n <= 4096 else 3)
     return out.reshape(v.shape)
 
 
@@ -180,6 +193,7 @@ def clustered_ranks(values, alpha: float | None = 0.05, r: float | None = None) 
     ws = torch.empty(wb, dtype=torch.uint8, device=dev)
     a, rf = (-1.0, float(r)) if r is not None else (float(alpha), 0.0)
     check(lib().rc_clustered_ranks(_ptr(v2), R, n, a, rf, _ptr(out), _ptr(ws), wb, _stream()))
+    _count(2 if n <= 4096 else 3)
     return out.reshape(v.shape)
 
 
@@ -197,7 +211,47 @@ def kendall_tau_b(x, y) -> torch.Tensor:
     tau = torch.empty((Rx, Ry), dtype=torch.float64, device=dev)
     counts = torch.empty((Rx, Ry, 4), dtype=torch.int64, device=dev)
     check(lib().rc_kendall_tau_b(_ptr(x2), Rx, _ptr(y2), Ry, n, _ptr(tau), _ptr(counts), _stream()))
+    _count(2)
     return tau
+
+
+def kendall_tau_b_batched(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """x [G][Rx][n] double ranks, y [G][Ry][n] int64 ranks -> tau [G][Rx][Ry] (one launch for all groups)."""
+    dev = require_cuda()
+    x = _f64(x, dev)
+    y = y.to(device=dev, dtype=torch.int64).contiguous()
+    G, Rx, n = x.shape
+    Ry = y.shape[1]
+    if y.shape[0] != G or y.shape[2] != n:
+        raise ValueError("x and y must share group count and row length")
+    tau = torch.empty((G, Rx, Ry), dtype=torch.float64, device=dev)
+    counts = torch.empty((G, Rx, Ry, 4), dtype=torch.int64, device=dev)
+    check(lib().rc_kendall_tau_b_batched(_ptr(x), _ptr(y), G, Rx, Ry, n, _ptr(tau), _ptr(counts), _stream()))
+    _count(2)
+    return tau
+
+
+def grouped_rank_consistency(W: torch.Tensor, groups: int, topk: int = 100, alpha: float = 0.05):
+    """The paper's fig-4 analysis for `groups` controller sets at once.  W: RIM matrix [S][groups*Cg].
+    Per group: keep the topk controllers with the smallest RIM at sigma_sim index 0
+    (mcsim.py:651-660), then the S x S Kendall matrix of clustered vs ordinal ranks
+    (generate_fig4_kendallrankanalysis.py:94-120).  Returns (tau [G][S][S], selected column index
+    [G][topk] within the group, W_topk [G][S][topk]).  Index bookkeeping (reshape / gather) is
+    torch plumbing; every comparison-based result comes from the rank / Kendall kernels."""
+    dev = require_cuda()
+    W = _f64(W, dev)
+    S, Ctot = W.shape
+    if Ctot % groups:
+        raise ValueError("controller count must be a multiple of the group count")
+    Cg = Ctot // groups
+    k = min(topk, Cg)
+    Wg = W.reshape(S, groups, Cg).permute(1, 0, 2).contiguous()          # [G][S][Cg]
+    rk0 = ranks(Wg[:, 0, :].contiguous())                               # [G][Cg]
+    sel = torch.nonzero(rk0 <= k - 1)[:, 1].reshape(groups, k)           # original column order kept
+    Wsel = torch.gather(Wg, 2, sel[:, None, :].expand(groups, S, k)).contiguous()
+    cr = clustered_ranks(Wsel.reshape(groups * S, k), alpha=alpha).reshape(groups, S, k)
+    rk = (ranks(Wsel.reshape(groups * S, k)) + 1).reshape(groups, S, k)
+    return kendall_tau_b_batched(cr, rk), sel, Wsel
 
 
 def kendall_matrix(wd_data_c, alpha: float = 0.05) -> torch.Tensor:
@@ -229,6 +283,7 @@ def mc_sweep_host(ctrl: np.ndarray, sigmas: np.ndarray, B: int, nspin: int, insp
     check(lib().rc_mc_sweep_host(vp(ctrl), Cn, nspin, inspin, outspin, vp(sigmas), S, B, model, int(bool(zz)),
                                  C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, vp(replay), float(dkw_eps),
                                  int(bool(fused)), vp(fids_out), vp(stats_out), _stream()))
+    _count(2)
     return stats_out, fids_out
 
 

@@ -32,3 +32,20 @@ def rim_sweep(controllers, noises, bootreps: int, Nspin: int, inspin: int, outsp
         st = engine.stats(f, eps)
     st = st.cpu().numpy()
     return {k: st[i] for i, k in enumerate(engine.STAT_KEYS)}
+
+
+def robustness_sweep(controllers: np.ndarray, noises: np.ndarray, bootreps: int, Nspin: int, inspin: int, outspin: int,
+                     *, groups: int = 1, topk: int = 100, alpha_dkw: float = 0.05, alpha_cluster: float = 0.05,
+                     seed: int = 0, fused: bool = False, model: int = engine.MODEL_COMPLEX3, zz: bool = False) -> dict:
+    """The paper's fig-4/5 sweep for `groups` controller sets given as HOST arrays: evolution,
+    the 15 statistics, per-group top-k selection and Kendall matrices.  Host in, host out: the
+    controllers travel to the device and the statistics / tau matrices come back (the end-to-end
+    call bench.py times).  Returns {"stats": {key: [S][C]}, "tau": [G][S][S], "topk_idx": [G][k]}."""
+    import torch
+    eps = float(compute_dkw_error(alpha_dkw, bootreps))
+    st, _ = engine.mc_sweep_host(np.asarray(controllers), np.asarray(noises), bootreps, Nspin, inspin, outspin,
+                                 dkw_eps=eps, seed=seed, fused=fused, model=model, zz=zz)
+    W = torch.as_tensor(st[0]).cuda()
+    tau, sel, _ = engine.grouped_rank_consistency(W, groups, topk=topk, alpha=alpha_cluster)
+    return {"stats": {k: st[i] for i, k in enumerate(engine.STAT_KEYS)}, "tau": tau.cpu().numpy(),
+            "topk_idx": sel.cpu().numpy()}

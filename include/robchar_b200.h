@@ -111,6 +111,12 @@ int rc_clustered_ranks(const double* values_dev, int64_t R, int64_t n, double al
 int rc_kendall_tau_b(const double* x_dev, int64_t Rx, const int64_t* y_dev, int64_t Ry, int64_t n,
                      double* tau_dev, long long* counts_dev, void* stream);
 
+/* Same for G independent controller groups at once: x [G][Rx][n], y [G][Ry][n] -> tau [G][Rx][Ry]
+ * (one group = one (algorithm, training noise) controller set of the paper's fig. 4 sweep).
+ * counts_dev: scratch int64 [G][Rx][Ry][4]. */
+int rc_kendall_tau_b_batched(const double* x_dev, const int64_t* y_dev, int64_t G, int64_t Rx, int64_t Ry,
+                             int64_t n, double* tau_dev, long long* counts_dev, void* stream);
+
 /* Whole sweep with HOST buffers: H2D of controllers/sigmas(/replay), evolution, statistics, D2H of
  * the 15 metric tensors (and of the fidelity tensor when fids_host != NULL).  This is what
  * MCDataSim.get_metrics_dict (mcsim.py:463-510) computes from scratch.
