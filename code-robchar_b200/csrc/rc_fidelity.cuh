@@ -69,30 +69,25 @@ __device__ __forceinline__ void build_tridiagonal(const double* __restrict__ x, 
     e[N - 1] = 0.0;
 }
 
+// Philox mode: this lane writes the standard normals of its evaluation into its own staged row, in
+// reference draw order (the discarded site-0 coupling slots are left untouched and never read).
+// The pair loop is deliberately NOT unrolled: one copy of Philox + log + sqrt + sincospi in the
+// instruction stream (code size matters more than the loop overhead, see rc_ql.cuh).
 template <int N, int MODEL>
-struct PhiloxDraws {
-    // Lazy pairwise generation.  Compact order = reference order minus the discarded site-0
-    // coupling draws; build_tridiagonal consumes draws in ascending order, so after unrolling
-    // every index below is a compile-time constant and only one pair is live at a time.
-    static constexpr int P = draws_per_site(MODEL);
-    uint32_t k0, k1, s;
-    uint64_t c, b;
-    double za, zb;
-    __device__ __forceinline__ double operator()(int j) {
-        const int jc = j == 0 ? 0 : j - (P - 1);
-        if ((jc & 1) == 0) {
-            normal_pair(k0, k1, s, c, b, (uint32_t)(jc >> 1), za, zb);
-            return za;
-        }
-        return zb;
+__device__ __forceinline__ void philox_fill_row(const FidArgs& a, long long s, long long c, long long b, double* row) {
+    constexpr int P = draws_per_site(MODEL);
+    constexpr int NC = P * N - (P - 1);  // compact count: reference order minus discarded draws
+    const uint64_t cg = (uint64_t)(c + a.c_offset), bg = (uint64_t)(b + a.b_offset);
+#pragma unroll 1
+    for (int p = 0; p < (NC + 1) / 2; ++p) {
+        double z0, z1;
+        normal_pair(a.seed_lo, a.seed_hi, (uint32_t)s, cg, bg, (uint32_t)p, z0, z1);
+        const int jc = 2 * p;
+        row[jc == 0 ? 0 : jc + (P - 1)] = z0;
+        if (jc + 1 < NC) row[jc + 1 + (P - 1)] = z1;
     }
-};
+}
 
-// ---------------------------------------------------------------------------------------------
-// Register-resident kernel, N <= REG_MAX_N.  Persistent grid-stride over tiles of blockDim evals.
-// Replay mode stages the tile's contiguous [evals][K] normals through shared memory with
-// coalesced loads (row pitch padded to an odd number of doubles: conflict-free 64-bit reads).
-// ---------------------------------------------------------------------------------------------
 // Coalesced staging of `nvalid` consecutive replay rows (K doubles each) into padded shared rows.
 template <int K>
 __device__ __forceinline__ void stage_replay_rows(const double* __restrict__ src, int nvalid, double* stage) {
@@ -105,25 +100,21 @@ __device__ __forceinline__ void stage_replay_rows(const double* __restrict__ src
     __syncthreads();
 }
 
-// One evaluation, register resident.  `row` = this lane's staged replay row (REPLAY only).
+// One evaluation, register resident.  `row` = this lane's private shared-memory row (K|1 doubles):
+// holds the standard normals on entry (staged replay or Philox) and is reused as the eigenvalue /
+// weight scratch of the eigensolver (2N <= K doubles).
 template <int N, int MODEL, bool REPLAY>
-__device__ __forceinline__ double eval_reg(const FidArgs& a, long long s, long long c, long long b,
-                                           const double* row) {
+__device__ __forceinline__ double eval_reg(const FidArgs& a, long long s, long long c, long long b, double* row) {
     const double* x = a.ctrl + c * (N + 1);
     double xr[N + 1];
 #pragma unroll
     for (int i = 0; i <= N; ++i) xr[i] = __ldg(x + i);
     const double sigma = __ldg(a.sigma + s);
+    if (!REPLAY) philox_fill_row<N, MODEL>(a, s, c, b, row);
     double d[N], ee[N];
-    if (REPLAY) {
-        build_tridiagonal<N, MODEL>(xr, sigma, a.zz, [&](int j) { return row[j]; }, d, ee);
-    } else {
-        PhiloxDraws<N, MODEL> pd{a.seed_lo, a.seed_hi, (uint32_t)s, (uint64_t)(c + a.c_offset),
-                                 (uint64_t)(b + a.b_offset), 0.0, 0.0};
-        build_tridiagonal<N, MODEL>(xr, sigma, a.zz, pd, d, ee);
-    }
+    build_tridiagonal<N, MODEL>(xr, sigma, a.zz, [&](int j) { return row[j]; }, d, ee);
     int fail = 0;
-    double f = fidelity_reg<N>(d, ee, a.in, a.out, fabs(xr[N]), &fail);
+    double f = fidelity_reg_compact<N>(d, ee, a.in, a.out, fabs(xr[N]), row, 1, &fail);
     if (fail && a.nonconv) atomicAdd(a.nonconv, 1ull);
     return f;
 }

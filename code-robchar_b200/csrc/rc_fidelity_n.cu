@@ -15,7 +15,7 @@ static cudaError_t launch_reg(const FidArgs& a, int sm_count, cudaStream_t st) {
     constexpr int N = RC_NSPIN;
     constexpr int K = draws_per_site(MODEL) * N;
     const int threads = 128;
-    size_t smem = REPLAY ? (size_t)threads * (K | 1) * sizeof(double) : 0;
+    size_t smem = (size_t)threads * (K | 1) * sizeof(double);  // one private row per lane
     auto kern = fidelity_reg_kernel<N, MODEL, REPLAY>;
     cudaError_t err;
     if (smem > 40 * 1024) {
@@ -40,7 +40,7 @@ static cudaError_t launch_fused_reg(const FusedArgs& g, int sm_count, cudaStream
     constexpr int N = RC_NSPIN;
     constexpr int K = draws_per_site(MODEL) * N;
     const int threads = 128;
-    size_t smem = REPLAY ? (size_t)threads * (K | 1) * sizeof(double) : 0;
+    size_t smem = (size_t)threads * (K | 1) * sizeof(double);  // one private row per lane
     auto kern = fidelity_stats_reg_kernel<N, MODEL, REPLAY>;
     cudaError_t err;
     if (smem > 40 * 1024) {

@@ -181,6 +181,81 @@ RC_HD double fidelity_reg(double (&d)[N], double (&e)[N], int in, int out, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
+// Compact register-resident variant (the one the kernels use).
+//
+// The fully recursive version above instantiates one sweep body per eigenvalue index (N(N-1)/2
+// rotation bodies: 90 KB of SASS at N=7, which thrashes the instruction cache — ncu showed
+// `no_instruction` as the top stall).  Here the active block always starts at position 0: when
+// e[0] becomes negligible, eigenvalue d[0] and its weight zi[0]*zo[0] are written to a per-lane
+// scratch row and all four arrays are shifted down by one (register moves).  There is a single
+// sweep body (N-1 predicated rotation slots, compile-time indices), every lane runs its own
+// sequence of sweeps, and a warp iterates max-over-lanes(total sweeps) times.
+// scratch: 2N doubles per lane, element k at scratch[k * sstride].
+// ---------------------------------------------------------------------------------------------
+template <int N>
+RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int out, double T, double* scratch,
+                                  int sstride, int* fail
+#ifdef RC_QL_STATS
+                                  , QlStats* st
+#endif
+) {
+    double zi[N], zo[N];
+    double anorm = 0.0, chk = T;
+    e[N - 1] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        zi[k] = (k == in) ? 1.0 : 0.0;
+        zo[k] = (k == out) ? 1.0 : 0.0;
+        anorm = fmax(anorm, fabs(d[k]) + fabs(e[k]));
+        chk += d[k] + e[k];
+    }
+    *fail = 0;
+    if (!(fabs(chk) <= DBL_MAX)) return NAN;  // NaN / Inf controller or draw (mcsim.py:369-374)
+    const double tol = DBL_EPSILON * anorm;
+    int nact = N, ndone = 0, it = 0, bad = 0;
+    while (nact > 1) {
+        if (fabs(e[0]) <= tol) {
+            // deflate: eigenvalue d[0] with weight V[in,k] V[out,k]
+            scratch[(size_t)ndone * sstride] = d[0];
+            scratch[(size_t)(N + ndone) * sstride] = zi[0] * zo[0];
+            ++ndone; --nact; it = 0;
+#pragma unroll
+            for (int i = 0; i < N - 1; ++i) { d[i] = d[i + 1]; e[i] = e[i + 1]; zi[i] = zi[i + 1]; zo[i] = zo[i + 1]; }
+        }
+        // sweep in the same trip unless the new leading off-diagonal is negligible as well
+        if (nact > 1 && !(fabs(e[0]) <= tol)) {
+            // first negligible off-diagonal inside the active block (descending scan: smallest wins)
+            int m = nact - 1;
+#pragma unroll
+            for (int i = N - 2; i >= 1; --i)
+                if (i < nact - 1 && fabs(e[i]) <= tol) m = i;
+            double dm = d[N - 1];
+#pragma unroll
+            for (int i = N - 2; i >= 1; --i)
+                if (i == m) dm = d[i];
+            if (++it > QL_MAX_SWEEPS) { bad = 1; break; }
+            QlSweep<N, 0>::run(d, e, zi, zo, m, dm);
+            RC_STAT(st->total_sweeps++; st->rotations += m;)
+        }
+    }
+    if (bad) { *fail = 1; return NAN; }
+    scratch[(size_t)ndone * sstride] = d[0];
+    scratch[(size_t)(N + ndone) * sstride] = zi[0] * zo[0];
+    double re = 0.0, im = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = 0; k < N; ++k) {
+        double sn, cs;
+        sincos(scratch[(size_t)k * sstride] * T, &sn, &cs);
+        const double w = scratch[(size_t)(N + k) * sstride];
+        re = fma(w, cs, re);
+        im = fma(-w, sn, im);
+    }
+    return re * re + im * im;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Strided-memory variant for large N: arrays live in shared (or any) memory with element stride
 // `ld` between consecutive matrix positions (column = this lane), dynamic loop bounds.
 // Holds the "i+1" elements in registers while chasing upwards to halve the memory traffic.

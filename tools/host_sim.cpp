@@ -20,13 +20,14 @@ void run(FILE* fi, FILE* fo, int in, int out, int count, int strided) {
         e[N - 1] = 0;
         int fail = 0;
         double f;
-        if (strided) {
+        if (strided == 1) {
             double zi[N], zo[N];
             for (int i = 0; i < N; ++i) { zi[i] = (i == in); zo[i] = (i == out); }
             f = rc::fidelity_strided(d, e, zi, zo, 1, N, T, &fail);
         } else {
             rc::QlStats st; memset(&st, 0, sizeof st);
-            f = rc::fidelity_reg<N>(d, e, in, out, T, &fail, &st);
+            if (strided == 2) { double scr[2 * N]; f = rc::fidelity_reg_compact<N>(d, e, in, out, T, scr, 1, &fail, &st); }
+            else f = rc::fidelity_reg<N>(d, e, in, out, T, &fail, &st);
             totsweeps += st.total_sweeps; totrot += st.rotations;
             if (st.total_sweeps > maxsweeps) maxsweeps = st.total_sweeps;
             hist[st.total_sweeps < 63 ? st.total_sweeps : 63]++;
@@ -35,7 +36,7 @@ void run(FILE* fi, FILE* fo, int in, int out, int count, int strided) {
         if (fail) fprintf(stderr, "nonconvergence at %d\n", k);
         fwrite(&f, sizeof(double), 1, fo);
     }
-    if (!strided) {
+    if (strided != 1) {
         fprintf(stderr, "N=%d mean sweeps %.3f max %d mean rotations %.2f\n per-l mean:", N, (double)totsweeps / count, maxsweeps, (double)totrot / count);
         for (int l = 0; l < N; ++l) fprintf(stderr, " %.2f", (double)perl[l] / count);
         fprintf(stderr, "\n");

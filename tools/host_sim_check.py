@@ -25,16 +25,16 @@ if __name__ == "__main__":
         g = np.load(f"tests/golden/{name}.npz")
         n, i, o = map(int, g["nio"])
         ctrl = g["ctrl"][None, :, None, :]
-        for strided in (0, 1):
+        for strided in (0, 1, 2):
             f = run(n, i, o, ctrl, g["normals"], g["sigmas"][:, None, None, None, None], strided)
             ok = ~np.isnan(g["fids"])
-            print(name, "strided" if strided else "reg", "max |diff| vs reference run:", np.abs(f[ok] - g["fids"][ok]).max(),
+            print(name, ["reg","strided","compact"][strided], "max |diff| vs reference run:", np.abs(f[ok] - g["fids"][ok]).max(),
                   "nan match", np.array_equal(np.isnan(f), np.isnan(g["fids"])))
     gl = np.load("tests/golden/replay_large_n.npz")
     for n in (10, 16, 32):
-        for strided in (0, 1):
+        for strided in (0, 1, 2):
             f = run(n, 0, n - 1, gl[f"n{n}_ctrl"][:, None, :], gl[f"n{n}_normals"], 0.05, strided)
-            print("N", n, "strided" if strided else "reg", np.abs(f - gl[f"n{n}_fids"]).max())
+            print("N", n, ["reg","strided","compact"][strided], np.abs(f - gl[f"n{n}_fids"]).max())
     # sweep statistics on synthetic controllers, N=7
     rs = np.random.RandomState(1)
     for n in (4, 7, 16):
