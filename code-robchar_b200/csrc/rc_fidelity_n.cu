@@ -1,5 +1,6 @@
 // One translation unit per chain length: compiled with -DRC_NSPIN=<N> for N = 2..REG_MAX_N so the
 // fully unrolled register-resident eigensolvers build in parallel.
+#include <stdlib.h>
 #include "rc_fidelity.cuh"
 
 #ifndef RC_NSPIN
@@ -10,11 +11,22 @@
 
 namespace rc {
 
+// CTA size of the register-resident kernels (RC_FID_THREADS overrides for tuning: 32..128).
+static int reg_threads() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("RC_FID_THREADS");
+        v = e ? atoi(e) : 128;
+        if (v < 32 || v > 128 || (v % 32)) v = 128;
+    }
+    return v;
+}
+
 template <int MODEL, bool REPLAY>
 static cudaError_t launch_reg(const FidArgs& a, int sm_count, cudaStream_t st) {
     constexpr int N = RC_NSPIN;
     constexpr int K = draws_per_site(MODEL) * N;
-    const int threads = 128;
+    const int threads = reg_threads();
     size_t smem = (size_t)threads * (K | 1) * sizeof(double);  // one private row per lane
     auto kern = fidelity_reg_kernel<N, MODEL, REPLAY>;
     cudaError_t err;
@@ -39,7 +51,7 @@ template <int MODEL, bool REPLAY>
 static cudaError_t launch_fused_reg(const FusedArgs& g, int sm_count, cudaStream_t st) {
     constexpr int N = RC_NSPIN;
     constexpr int K = draws_per_site(MODEL) * N;
-    const int threads = 128;
+    const int threads = reg_threads();
     size_t smem = (size_t)threads * (K | 1) * sizeof(double);  // one private row per lane
     auto kern = fidelity_stats_reg_kernel<N, MODEL, REPLAY>;
     cudaError_t err;

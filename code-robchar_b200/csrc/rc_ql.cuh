@@ -31,11 +31,31 @@ namespace rc {
 
 constexpr int QL_MAX_SWEEPS = 40;  // per eigenvalue (EISPACK uses 30)
 
+// 1/sqrt(h) for normal positive h: hardware seed (MUFU.RSQ64H, ~2^-22) + one cubic correction
+// y1 = y0 (1 + e/2 + 3 e^2/8), e = 1 - h y0^2  (error ~ e^3: full double precision), 5 DFMA-class
+// ops instead of the library routine's special-case handling.
 RC_HD double rc_rsqrt(double h) {
 #if defined(__CUDA_ARCH__)
-    return rsqrt(h);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(h));
+    const double t = h * y;
+    const double e = fma(-t, y, 1.0);
+    const double q = e * fma(0.375, e, 0.5);
+    return fma(y, q, y);
 #else
     return 1.0 / sqrt(h);
+#endif
+}
+
+// 1/t to ~2^-44 (seed + one Newton step): only used for the Wilkinson shift, whose accuracy affects
+// the convergence rate but never the result (the similarity transform is orthogonal for any shift).
+RC_HD double rc_rcp_approx(double t) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
+    return fma(y, fma(-t, y, 1.0), y);
+#else
+    return 1.0 / t;
 #endif
 }
 
@@ -47,10 +67,11 @@ struct QlStats { int sweeps_per_l[64]; int total_sweeps; int rotations; };
 #endif
 
 RC_HD double wilkinson_g(double dl, double dl1, double el, double dm) {
-    double delta = 0.5 * (dl1 - dl);
-    double e2 = el * el;
-    double t = delta + copysign(sqrt(fma(delta, delta, e2)), delta);
-    return (dm - dl) + e2 / t;
+    const double delta = 0.5 * (dl1 - dl);
+    const double e2 = el * el;
+    const double q = fma(delta, delta, e2);          // > 0: el is not negligible inside the block
+    const double t = delta + copysign(q * rc_rsqrt(q), delta);
+    return (dm - dl) + e2 * rc_rcp_approx(t);
 }
 
 // One implicit QL sweep on the unreduced block [L, m] (m found by the caller), L compile time.
@@ -68,13 +89,14 @@ struct QlSweep {
             if (i < m) {
                 double f = s * e[i];
                 double b = c * e[i];
-                double h = f * f + g * g;
+                // h >= tol^2-ish inside an unreduced block; the tiny offset only keeps the (measure-zero)
+                // total-cancellation case finite instead of branching on it in the hot loop
+                double h = fma(f, f, g * g) + 1e-280;
                 double rinv = rc_rsqrt(h);
                 r = h * rinv;
-                if (!(h > 0.0)) { rinv = 0.0; r = 0.0; }  // underflow guard: identity-like step
                 e[i + 1] = r;
                 s = f * rinv;
-                c = (h > 0.0) ? g * rinv : 1.0;
+                c = g * rinv;
                 g = d[i + 1] - p;
                 r = (d[i] - g) * s + 2.0 * c * b;
                 p = s * r;
