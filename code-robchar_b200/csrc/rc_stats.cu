@@ -9,6 +9,7 @@
 //                        shared memory, statistics straight from shared memory (one HBM read).
 //   larger B           : cub::DeviceSegmentedRadixSort in chunks, then a streaming statistics
 //                        kernel over the sorted chunk (second pass served by L2).
+#include <stdlib.h>
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
@@ -104,6 +105,149 @@ __device__ __forceinline__ void sorted_segment_stats(At at, long long B, double 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One WARP per segment, B <= 32*E: keys live in registers (element g = j*32 + lane), bitonic
+// network with register exchanges for distances >= 32 and xor-shuffles below; no shared memory,
+// no CTA barriers.  Statistics by warp shuffles.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int E>
+__global__ void __launch_bounds__(128) sort_stats_warp_kernel(const double* __restrict__ fids, long long nseg, int B,
+                                                              double eps, double* __restrict__ stats, double* sorted_out,
+                                                              unsigned long long* illegal) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long seg = warp0; seg < nseg; seg += nwarps) {
+        const double* src = fids + seg * (long long)B;
+        unsigned long long v[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int g = j * 32 + lane;
+            v[j] = g < B ? f2key(__ldcs(src + g)) : ~0ull;
+        }
+        // bitonic sort, ascending in g
+#pragma unroll
+        for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+            for (int dist = k >> 1; dist > 0; dist >>= 1) {
+                if (dist >= 32) {
+                    const int dj = dist >> 5;
+#pragma unroll
+                    for (int j = 0; j < E; ++j) {
+                        if ((j & dj) == 0) {
+                            const bool up = ((j * 32) & k) == 0;  // k >= 64 here: direction depends on j only
+                            const unsigned long long a = v[j], b = v[j | dj];
+                            const bool sw = (a > b) == up;
+                            v[j] = sw ? b : a;
+                            v[j | dj] = sw ? a : b;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < E; ++j) {
+                        const unsigned long long a = v[j];
+                        const unsigned long long b = __shfl_xor_sync(0xffffffffu, a, dist);
+                        const bool up = (((j * 32 + lane) & k) == 0);
+                        const bool lower = (lane & dist) == 0;
+                        const bool take_min = (lower == up);
+                        v[j] = ((a < b) == take_min) ? a : b;
+                    }
+                }
+            }
+        }
+        if (sorted_out) {
+            double* dst = sorted_out + seg * (long long)B;
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                const int g = j * 32 + lane;
+                if (g < B) dst[g] = key2f(v[j]);
+            }
+        }
+        // statistics (same arithmetic as sorted_segment_stats)
+        double acc[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+        unsigned bad = 0;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int g = j * 32 + lane;
+            const double f = key2f(v[j]);
+            double fn = __shfl_down_sync(0xffffffffu, f, 1);
+            const double f_first_next = (j + 1 < E) ? __shfl_sync(0xffffffffu, key2f(v[j + 1 < E ? j + 1 : j]), 0) : 1.0;
+            if (lane == 31) fn = f_first_next;
+            if (g < B) {
+                const bool last = (g + 1 >= B);
+                const double cdf = (double)(g + 1) / (double)B;
+                const double vv[3] = {f, clip01(f - eps), clip01(f + eps)};
+                const double vn[3] = {last ? 1.0 : fn, last ? 1.0 : clip01(fn - eps), last ? 1.0 : clip01(fn + eps)};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    acc[k] += (vn[k] - vv[k]) * cdf;
+                    acc[3 + k] += vv[k];
+                    acc[6 + k] += (vv[k] >= 0.95) ? 1.0 : 0.0;
+                    acc[9 + k] += (vv[k] >= 0.98) ? 1.0 : 0.0;
+                }
+                if (fabs(f - 1e-8) > 1.0) ++bad;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc[k] = warp_sum(acc[k]);
+        bad = __reduce_add_sync(0xffffffffu, bad);
+        if (bad && illegal && lane == 0) atomicAdd(illegal, (unsigned long long)bad);
+        double m2[3] = {0.0, 0.0, 0.0};
+        const double mean[3] = {acc[3] / (double)B, acc[4] / (double)B, acc[5] / (double)B};
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int g = j * 32 + lane;
+            if (g < B) {
+                const double f = key2f(v[j]);
+                const double vv[3] = {f, clip01(f - eps), clip01(f + eps)};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double dlt = vv[k] - mean[k];
+                    m2[k] += dlt * dlt;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) m2[k] = warp_sum(m2[k]);
+        const double f0 = __shfl_sync(0xffffffffu, key2f(v[0]), 0);
+        if (lane < 3) {
+            const int k = lane;
+            const double mn = k == 0 ? f0 : (k == 1 ? clip01(f0 - eps) : clip01(f0 + eps));
+            const double a0 = k == 0 ? acc[0] : (k == 1 ? acc[1] : acc[2]);
+            const double a6 = k == 0 ? acc[6] : (k == 1 ? acc[7] : acc[8]);
+            const double a9 = k == 0 ? acc[9] : (k == 1 ? acc[10] : acc[11]);
+            const double mm = k == 0 ? m2[0] : (k == 1 ? m2[1] : m2[2]);
+            stats[(0 + k) * nseg + seg] = a0;
+            stats[(3 + k) * nseg + seg] = -1.0 * (a6 / (double)B);
+            stats[(6 + k) * nseg + seg] = -1.0 * (a9 / (double)B);
+            stats[(9 + k) * nseg + seg] = sqrt(mm / (double)B);
+            stats[(12 + k) * nseg + seg] = -mn;
+        }
+    }
+}
+
+template <int E>
+static cudaError_t launch_sort_stats_warp(const double* fids, long long nseg, int B, double eps, double* stats,
+                                          double* sorted_out, unsigned long long* illegal, int sm, cudaStream_t st) {
+    int occ = 0;
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sort_stats_warp_kernel<E>, 128, 0);
+    if (err != cudaSuccess) return err;
+    if (occ < 1) occ = 1;
+    long long grid = (long long)sm * occ;
+    const long long need = (nseg + 3) / 4;
+    if (grid > need) grid = need;
+    sort_stats_warp_kernel<E><<<(unsigned)grid, 128, 0, st>>>(fids, nseg, B, eps, stats, sorted_out, illegal);
+    return cudaGetLastError();
+}
+
 // One CTA per segment: bitonic sort in shared memory, then statistics.
 __global__ void __launch_bounds__(512) sort_stats_small_kernel(const double* __restrict__ fids, long long nseg, int B,
                                                                int P /* pow2 >= B */, double eps,
@@ -187,11 +331,24 @@ extern "C" int rc_stats(const double* fids_dev, int64_t nseg, int64_t B, double 
     if (!fids_dev || !stats_dev) return set_error(RC_ERR_NULL, "rc_stats: null fids/stats pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int sm = device_sm_count();
+    if (B <= 512 && !getenv("RC_STATS_NO_WARP")) {
+        cudaError_t err;
+        const int b = (int)B;
+        if (b <= 32) err = launch_sort_stats_warp<1>(fids_dev, nseg, b, dkw_eps, stats_dev, sorted_dev, illegal_dev, sm, st);
+        else if (b <= 64) err = launch_sort_stats_warp<2>(fids_dev, nseg, b, dkw_eps, stats_dev, sorted_dev, illegal_dev, sm, st);
+        else if (b <= 128) err = launch_sort_stats_warp<4>(fids_dev, nseg, b, dkw_eps, stats_dev, sorted_dev, illegal_dev, sm, st);
+        else if (b <= 256) err = launch_sort_stats_warp<8>(fids_dev, nseg, b, dkw_eps, stats_dev, sorted_dev, illegal_dev, sm, st);
+        else err = launch_sort_stats_warp<16>(fids_dev, nseg, b, dkw_eps, stats_dev, sorted_dev, illegal_dev, sm, st);
+        RC_CUDA_TRY(err);
+        return RC_OK;
+    }
     if (B <= SMEM_SORT_MAX) {
         int P = 1;
         while (P < B) P <<= 1;
         if (P < 2) P = 2;
-        int threads = P / 2;
+        // one warp per small segment (CTA barrier == warp barrier), more warps only for long segments
+        int threads = P / 8;
+        if (const char* e = getenv("RC_STATS_DIV")) threads = P / atoi(e);
         if (threads < 32) threads = 32;
         if (threads > 512) threads = 512;
         size_t smem = (size_t)P * sizeof(unsigned long long);
