@@ -32,8 +32,9 @@ def all_gather_stats(local: torch.Tensor, C_total: int, group=None) -> torch.Ten
     K, S = local.shape[0], local.shape[1]
     pad = torch.zeros((K, S, cmax), dtype=local.dtype, device=local.device)
     pad[:, :, :local.shape[2]] = local
-    out = torch.empty((world, K, S, cmax), dtype=local.dtype, device=local.device)
-    td.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    out = torch.empty((world * K, S, cmax), dtype=local.dtype, device=local.device)
+    td.all_gather_into_tensor(out, pad.contiguous(), group=group)   # concatenated along dim 0 in rank order
+    out = out.reshape(world, K, S, cmax)
     return torch.cat([out[r, :, :, :sizes[r]] for r in range(world)], dim=2).contiguous()
 
 

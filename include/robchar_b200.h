@@ -3,7 +3,7 @@
  * The reference (qyber-black/Code-RobChar) has no FFI layer: its boundary is Python call
  * signatures.  Each entry point below names the reference interface it stands behind
  * (file:line in the upstream repo).  All pointers are plain; "dev" pointers are CUDA device
- * addresses (e.g. torch.Tensor.data_ptr()), "host" pointers are ordinary host memory.  `stream`
+ * addresses (any CUDA allocation), "host" pointers are ordinary host memory.  `stream`
  * is a cudaStream_t passed as void* (NULL = default stream).  Every function returns an int
  * status (RC_OK = 0) and records a message retrievable with rc_last_error() (thread local).
  * The library owns no persistent state; scratch memory is caller-provided (size-query calls) in

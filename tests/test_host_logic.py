@@ -1,0 +1,198 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the host-side mirror of
+the reference interface behaves like the reference, and nothing computes without a GPU."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from oracle import robchar_oracle as orc
+
+import robchar_b200 as rb
+
+
+def test_library_exports_every_declared_symbol():
+    syms = rb._lib.declared_symbols()
+    assert len(syms) >= 16 and "rc_fidelity_mc" in syms and "rc_mc_sweep_host" in syms
+    lib = rb._lib.lib()
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert set(rb._lib._SIGNATURES) == set(syms)          # every declared entry point is bound
+    assert lib.rc_version() >= 100
+    assert isinstance(rb._lib.last_error(), str)
+
+
+def test_header_cites_reference_interfaces():
+    text = open(os.path.join(ROOT, "include", "robchar_b200.h")).read()
+    for cite in ["mcsim.py:422", "noise_model.py:98", "wd_sortof_fast_implementation.py:82", "mcsim.py:513",
+                 "generate_fig4_kendallrankanalysis.py:146", "qnewton.py:366"]:
+        assert cite in text, cite
+    assert "#include <torch" not in text and "at::Tensor" not in text     # plain pointers and sizes only
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(rb._lib.RobcharLibraryError):
+        rb.engine.fidelity_mc(np.zeros((1, 5)), [0.0], 1, 4, 0, 2)
+    with pytest.raises(rb._lib.RobcharLibraryError):
+        rb.wd_from_ideal(np.array([0.5, 0.6]))
+    m = rb.structured_perturbation(Nspin=4, inspin=0, outspin=2)
+    with pytest.raises(rb._lib.RobcharLibraryError):
+        m.evaluate_noisy_fidelity(np.zeros(5), True)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "code-robchar_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+                assert "/root/reference" not in src, fn
+
+
+def test_status_codes_map_to_reference_exceptions():
+    lib = rb._lib
+    with pytest.raises(AssertionError):
+        lib.check(lib.RC_ERR_ILLEGAL_FIDS)            # wd_sortof_fast_implementation.py:25
+    with pytest.raises(ValueError):
+        lib.check(lib.RC_ERR_BAD_ARG)
+    with pytest.raises(lib.EigensolverNonConvergence):
+        lib.check(lib.RC_ERR_NONCONV)
+    with pytest.raises(lib.RobcharLibraryError):
+        lib.check(lib.RC_ERR_CUDA)
+    lib.check(lib.RC_OK)
+
+
+def test_noise_function_semantics():
+    """noise_model.py:21-46: every call updates the stored kwargs and draws."""
+    calls = []
+    nf = rb.noise_function(lambda **kw: calls.append(dict(kw)) or kw.get("scale", 0), scale=0.02)
+    assert nf() == 0.02
+    assert nf(scale=0.07) == 0.07 and nf.args == {"scale": 0.07}
+    assert nf(size=2) == 0.07 and calls[-1] == {"scale": 0.07, "size": 2}
+    np.random.seed(3)
+    g = rb.noise_function(np.random.normal, scale=0.05)
+    a = [g() for _ in range(3)]
+    np.random.seed(3)
+    assert a == list(0.05 * np.random.standard_normal(3))
+
+
+def test_structured_perturbation_draw_order_matches_reference_port():
+    """noise_model.py:135-147: (z_ii, nn_i, nn2_i) per site, site-0 couplings discarded."""
+    n = 6
+    m = rb.structured_perturbation(Nspin=n, inspin=0, outspin=3, noise=0.05)
+    assert m.HH.dtype == np.complex128 and len(m.CC) == n and m.CC[2][2, 2] == 1
+    np.random.seed(9)
+    z = m.perturbation()
+    stream = np.random.RandomState(9).standard_normal(3 * n) * 0.05
+    want = orc.perturbation_from_draws(stream, n)
+    assert np.array_equal(z, want)
+    row = m._replay_row_from_matrix(z)
+    used = np.ones(3 * n, bool); used[[1, 2]] = False
+    assert np.array_equal(row[used], stream[used]) and np.all(row[~used] == 0)
+    with pytest.raises(NotImplementedError):
+        bad = z.copy(); bad[0, 3] = 1.0
+        m._replay_row_from_matrix(bad)
+    ring = rb.structured_perturbation(Nspin=4, topo="ring")
+    assert ring.HH[3, 0] == 1 and ring.HH[0, 3] == 1
+    with pytest.raises(NotImplementedError):
+        ring.evaluate_noisy_fidelity(np.zeros(5))
+    d = rb.directional_perturbation(Nspin=5, outspin=4)
+    assert len(d.directions) == 2 + 3 * 3 + 4
+    np.random.seed(1)
+    zz = d.perturbation()
+    assert np.count_nonzero(zz) in (1, 2)
+
+
+def test_experiment_namer_and_mc_file_names(tmp_path, monkeypatch):
+    """File-name grammar of mcsim.py:351-356 / noise_analysis.py:33-49 resolves the reference's files."""
+    monkeypatch.chdir(tmp_path)
+    nm = rb.noise_analysis.ExperimentNamer(experiment_name="pipeline_nmplus2", Nspin=4, inspin=0, outspin=2,
+                                           numcontrollers=1000)
+    assert nm() == "experiments/pipeline_nmplus2/ppo_spin_4_0-2_c_1000"
+    assert os.path.isdir("experiments/pipeline_nmplus2")
+    json.dump({"lbfgs": {"4": {"controller": [[0.0] * 5]}}, "empty": {}},
+              open("experiments/pipeline_nmplus2/ppo_spin_4_0-2_c_1000.le", "w"))
+    sim = rb.MCDataSim(experiment_name="pipeline_nmplus2", Nspin=4, inspin=0, outspin=2, bootreps=1,
+                       numcontrollers=1000, filemarker=".le")
+    assert sim.algos == ["lbfgs"]                                      # empty containers purged (mcsim.py:339-343)
+    # the exact name of a cache file shipped with the reference (experiments/pipeline_nmplus2/)
+    want = ("experiments/pipeline_nmplus2/ppo_spin_4_0-2_c_1000.le_tn0.01_br_1_nlvl"
+            "[0.   0.01 0.02 0.03 0.04 0.05 0.06 0.07 0.08 0.09 0.1 ].mc")
+    assert sim.get_mcname(0.01, np.linspace(0, 0.1, 11)) == want
+    assert sim.get_mcname(None, np.linspace(0, 0.1, 11)).startswith("experiments/pipeline_nmplus2/ppo_spin_4_0-2_c_1000.le_tnNone_br_1_")
+    c = sim._controller_matrix("lbfgs", None)
+    assert c.shape == (1000, 5) and np.isnan(c[1:]).all() and not np.isnan(c[0]).any()   # NaN padding (mcsim.py:436-443)
+    missing = rb.MCDataSim(experiment_name="nothing_here", Nspin=4)
+    assert missing.controllers is None and missing.algos is None       # FileNotFoundError swallowed (mcsim.py:231-237)
+    with pytest.raises(rb.noise_analysis.DirectoryDoesNotExistError):
+        sim.get_path("does_not_exist")
+    with pytest.raises(TypeError):
+        sim.ctrlnames(3)
+
+
+def test_numpy_stream_replay_layout(tmp_path, monkeypatch):
+    """rng_mode='numpy' consumes np.random like mcsim.py:424-456 (one discarded draw per level, none for NaN rows)."""
+    monkeypatch.chdir(tmp_path)
+    sim = rb.MCDataSim(experiment_name="x", Nspin=4, inspin=0, outspin=2, bootreps=3, numcontrollers=3, rng_mode="numpy")
+    ctrl = np.zeros((3, 5)); ctrl[1] = np.nan
+    np.random.seed(5)
+    z = sim._numpy_stream_replay(ctrl, np.array([0.0, 0.1]))
+    rs = np.random.RandomState(5)
+    for s in range(2):
+        rs.standard_normal()
+        for c in (0, 2):
+            assert np.array_equal(z[s, c], rs.standard_normal((3, 12)))
+    assert np.all(z[:, 1] == 0)
+    assert sim.noise_model.rng.args["scale"] == 0.1
+
+
+def test_metric_registry_names_and_helpers():
+    assert list(rb.mcsim.__metric_name_to_metric__) == orc.METRIC_NAMES
+    assert rb.engine.STAT_KEYS[:3] == [orc.METRIC_W, orc.METRIC_W + " upper", orc.METRIC_W + " lower"]
+    g = load_golden("kat_mcm_pairs.npz")
+    assert [str(s) for s in g["names"]] == rb.engine.STAT_KEYS       # key order of the reference's .mcm files
+    assert rb.compute_dkw_error(0.05, 100) == orc.compute_dkw_error(0.05, 100)
+    cdf, srt = rb.mcsim.get_cdf(np.array([0.3, 0.1, 0.6]))
+    assert np.allclose(cdf, [0.1, 0.4, 1.0]) and np.array_equal(srt, [0.1, 0.3, 0.6])
+    with pytest.raises(TypeError):
+        rb.mcsim.get_cdf([0.1, 0.2])
+    assert rb.mcsim.Q(np.array([0.9, 0.96, 0.99]), 0.95) == 2 / 3
+    rs = np.random.RandomState(0)
+    assert rb.mcsim.vn_test(rs.normal(0, 1, 50000), verbose=False)[0] is True       # mcsim.py:126-130
+    assert rb.mcsim.vn_test(np.arange(1000.0), verbose=False)[0] is False
+    lo, hi = rb.wd_sortof_fast_implementation.dkw_ecdf_bounds(np.array([0.2, 0.5, 0.9]), 0.95)
+    eps = orc.compute_dkw_error(0.05, 3)
+    assert np.allclose(lo, np.clip(np.array([0.2, 0.5, 0.9]) - eps, 0, 1)) and np.all(hi <= 1)
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 19000, 100001):
+        for w in (1, 2, 3, 8):
+            spans = [rb.dist.shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_reference_module_aliases():
+    import sys
+    saved = {k: sys.modules.get(k) for k in ("mcsim", "noise_model", "wd_sortof_fast_implementation", "noise_analysis")}
+    try:
+        rb.install_reference_module_aliases()
+        from mcsim import MCDataSim            # noqa: the unmodified analysis scripts' import lines
+        from noise_model import structured_perturbation  # noqa
+        from wd_sortof_fast_implementation import wd_from_ideal, compute_dkw_error  # noqa
+        assert MCDataSim is rb.MCDataSim
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
