@@ -336,7 +336,7 @@ def run_ours(args):
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_total_ms / args.steps,
-                "api": "robchar_b200.rim_analysis.robustness_sweep (rc_mc_sweep_host + rank/Kendall kernels)"},
+                "api": "robchar_b200.rim_analysis.robustness_sweep -> rc_robustness_sweep_host (one C call, host buffers in/out)"},
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_value, "unit": "evals/s", "cores": procs, "kind": "port",
                          "sample": f"{procs} procs x {args.cpu_evals} evals of the oracle's per-sample port of "

@@ -73,21 +73,24 @@ extern "C" int rc_fp64_peak_tflops(double* tflops, void* stream) {
     return RC_OK;
 }
 
-extern "C" int rc_mc_sweep_host(const double* ctrl_host, int64_t C, int nspin, int inspin, int outspin,
-                                const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
-                                int64_t c_offset, int64_t b_offset, const double* replay_host, double dkw_eps,
-                                int fused, double* fids_host, double* stats_host, void* stream) {
+static int sweep_host_impl(const double* ctrl_host, int64_t C, int nspin, int inspin, int outspin,
+                           const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
+                           int64_t c_offset, int64_t b_offset, const double* replay_host, double dkw_eps,
+                           int fused, double* fids_host, double* stats_host, int64_t G, int64_t topk,
+                           double alpha_cluster, double* tau_host, int64_t* sel_host, void* stream) {
     if (nspin < 2 || nspin > RC_MAX_NSPIN) return set_error(RC_ERR_BAD_ARG, "nspin=%d outside [2,%d]", nspin, RC_MAX_NSPIN);
-    if (C < 0 || S < 0 || B < 1) return set_error(RC_ERR_BAD_ARG, "rc_mc_sweep_host: bad sizes C=%lld S=%d B=%lld", (long long)C, S, (long long)B);
+    if (C < 0 || S < 0 || B < 1) return set_error(RC_ERR_BAD_ARG, "sweep: bad sizes C=%lld S=%d B=%lld", (long long)C, S, (long long)B);
     const long long nseg = (long long)S * C, total = nseg * B;
     if (total == 0) return RC_OK;
-    if (!ctrl_host || !sigma_host) return set_error(RC_ERR_NULL, "rc_mc_sweep_host: null ctrl/sigma");
-    if (!stats_host && !fids_host) return set_error(RC_ERR_NULL, "rc_mc_sweep_host: no output requested");
-    if (fused && fids_host) return set_error(RC_ERR_BAD_ARG, "rc_mc_sweep_host: fused mode does not materialise fidelities");
+    if (!ctrl_host || !sigma_host) return set_error(RC_ERR_NULL, "sweep: null ctrl/sigma");
+    if (!stats_host && !fids_host) return set_error(RC_ERR_NULL, "sweep: no output requested");
+    if (fused && fids_host) return set_error(RC_ERR_BAD_ARG, "sweep: fused mode does not materialise fidelities");
+    const bool want_rank = tau_host != nullptr;
+    if (want_rank && (G < 1 || C % G)) return set_error(RC_ERR_BAD_ARG, "sweep: C=%lld is not a multiple of G=%lld", (long long)C, (long long)G);
     cudaStream_t st = (cudaStream_t)stream;
     RC_CUDA_TRY(keep_pool_memory());
     const int K = (model == RC_MODEL_COMPLEX3 ? 3 : 2) * nspin;
-    DevBuf ctrl(st), sigma(st), replay(st), fids(st), stats(st), ws(st), counters(st);
+    DevBuf ctrl(st), sigma(st), replay(st), fids(st), stats(st), ws(st), counters(st), tau(st), sel(st), wsel(st), rws(st);
     RC_CUDA_TRY(ctrl.alloc((size_t)C * (nspin + 1) * 8));
     RC_CUDA_TRY(sigma.alloc((size_t)S * 8));
     RC_CUDA_TRY(counters.alloc(16));
@@ -100,7 +103,7 @@ extern "C" int rc_mc_sweep_host(const double* ctrl_host, int64_t C, int nspin, i
     }
     unsigned long long* nonconv = counters.as<unsigned long long>();
     unsigned long long* illegal = nonconv + 1;
-    if (stats_host) RC_CUDA_TRY(stats.alloc((size_t)RC_NUM_STATS * nseg * 8));
+    if (stats_host || want_rank) RC_CUDA_TRY(stats.alloc((size_t)RC_NUM_STATS * nseg * 8));
     int rcode;
     if (fused) {
         size_t wb = rc_fidelity_stats_workspace_bytes(nseg, B);
@@ -116,9 +119,9 @@ extern "C" int rc_mc_sweep_host(const double* ctrl_host, int64_t C, int nspin, i
         if (rcode) return rcode;
         // the reference dumps the UNSORTED tensor to .mc before any metric sorts it (mcsim.py:457-459)
         if (fids_host) RC_CUDA_TRY(cudaMemcpyAsync(fids_host, fids.p, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
-        if (stats_host) {
+        if (stats_host || want_rank) {
             size_t wb = rc_stats_workspace_bytes(nseg, B);
-            if (wb == 0) return set_error(RC_ERR_BAD_ARG, "rc_mc_sweep_host: B too large for the sort path");
+            if (wb == 0) return set_error(RC_ERR_BAD_ARG, "sweep: B too large for the sort path (use fused)");
             RC_CUDA_TRY(ws.alloc(wb));
             rcode = rc_stats(fids.as<double>(), nseg, B, dkw_eps, stats.as<double>(), nullptr, illegal, ws.p, wb, st);
             if (rcode) return rcode;
@@ -126,10 +129,42 @@ extern "C" int rc_mc_sweep_host(const double* ctrl_host, int64_t C, int nspin, i
     }
     if (stats_host)
         RC_CUDA_TRY(cudaMemcpyAsync(stats_host, stats.p, (size_t)RC_NUM_STATS * nseg * 8, cudaMemcpyDeviceToHost, st));
+    if (want_rank) {
+        const int64_t Cg = C / G, k = topk < Cg ? topk : Cg;
+        size_t wb = rc_rank_consistency_workspace_bytes(S, G, Cg, topk);
+        if (wb == 0) return set_error(RC_ERR_BAD_ARG, "sweep: ranking problem too large");
+        RC_CUDA_TRY(rws.alloc(wb));
+        RC_CUDA_TRY(tau.alloc((size_t)G * S * S * 8));
+        RC_CUDA_TRY(sel.alloc((size_t)G * k * 8));
+        RC_CUDA_TRY(wsel.alloc((size_t)G * S * k * 8));
+        rcode = rc_rank_consistency(stats.as<double>(), S, G, Cg, topk, alpha_cluster, tau.as<double>(), sel.as<int64_t>(),
+                                    wsel.as<double>(), rws.p, wb, st);
+        if (rcode) return rcode;
+        RC_CUDA_TRY(cudaMemcpyAsync(tau_host, tau.p, (size_t)G * S * S * 8, cudaMemcpyDeviceToHost, st));
+        if (sel_host) RC_CUDA_TRY(cudaMemcpyAsync(sel_host, sel.p, (size_t)G * k * 8, cudaMemcpyDeviceToHost, st));
+    }
     unsigned long long hc[2] = {0, 0};
     RC_CUDA_TRY(cudaMemcpyAsync(hc, counters.p, 16, cudaMemcpyDeviceToHost, st));
     RC_CUDA_TRY(cudaStreamSynchronize(st));
     if (hc[0]) return set_error(RC_ERR_NONCONV, "eigensolver did not converge for %llu evaluations (NaN written)", hc[0]);
     if (hc[1]) return set_error(RC_ERR_ILLEGAL_FIDS, "illegal fids values - must be in [0,1] (%llu samples)", hc[1]);
     return RC_OK;
+}
+
+extern "C" int rc_mc_sweep_host(const double* ctrl_host, int64_t C, int nspin, int inspin, int outspin,
+                                const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
+                                int64_t c_offset, int64_t b_offset, const double* replay_host, double dkw_eps,
+                                int fused, double* fids_host, double* stats_host, void* stream) {
+    return sweep_host_impl(ctrl_host, C, nspin, inspin, outspin, sigma_host, S, B, model, zz, seed, c_offset, b_offset,
+                           replay_host, dkw_eps, fused, fids_host, stats_host, 0, 0, 0.0, nullptr, nullptr, stream);
+}
+
+extern "C" int rc_robustness_sweep_host(const double* ctrl_host, int64_t C, int nspin, int inspin, int outspin,
+                                        const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
+                                        int64_t c_offset, int64_t b_offset, double dkw_eps, int fused, int64_t G,
+                                        int64_t topk, double alpha_cluster, double* stats_host, double* tau_host,
+                                        int64_t* sel_host, void* stream) {
+    if (!tau_host) return set_error(RC_ERR_NULL, "rc_robustness_sweep_host: null tau output");
+    return sweep_host_impl(ctrl_host, C, nspin, inspin, outspin, sigma_host, S, B, model, zz, seed, c_offset, b_offset,
+                           nullptr, dkw_eps, fused, nullptr, stats_host, G, topk, alpha_cluster, tau_host, sel_host, stream);
 }

@@ -66,11 +66,12 @@ struct RowOffset {
     __host__ __device__ int operator()(int i) const { return i * n; }
 };
 
-__global__ void scatter_ranks_kernel(const int* __restrict__ perm, long long R, long long n, long long* __restrict__ ranks) {
+__global__ void scatter_ranks_kernel(const int* __restrict__ perm, long long R, long long n, long long* __restrict__ ranks,
+                                     long long offset = 0) {
     const long long total = R * n;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         long long row = i / n, pos = i - row * n;
-        ranks[row * n + perm[i]] = pos;  // ranks[argranks] = arange(n)  (mcsim.py:516-517)
+        ranks[row * n + perm[i]] = pos + offset;  // ranks[argranks] = arange(n)  (mcsim.py:516-517)
     }
 }
 
@@ -161,6 +162,49 @@ __global__ void kendall_finalize_kernel(const unsigned long long* __restrict__ c
             t = fmin(1.0, fmax(-1.0, t));
         }
         tau[p] = t;
+    }
+}
+
+// ---- top-k selection per controller group (mcsim.py:651-660: mask = rank at sigma index 0 <= k-1,
+// columns kept in their original order) -------------------------------------------------------------
+__global__ void mark_topk_kernel(const int* __restrict__ perm, long long G, long long Cg, long long k,
+                                 unsigned char* __restrict__ mark) {
+    const long long total = G * k;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long g = i / k, j = i - g * k;
+        mark[g * Cg + perm[g * Cg + j]] = 1;
+    }
+}
+
+// one CTA per group: order-preserving compaction of the marked columns (tiled block scan)
+__global__ void __launch_bounds__(256) compact_topk_kernel(const unsigned char* __restrict__ mark, long long Cg,
+                                                           long long k, long long* __restrict__ sel) {
+    typedef cub::BlockScan<int, 256> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ int base;
+    const long long g = blockIdx.x;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (long long c0 = 0; c0 < Cg; c0 += 256) {
+        const long long c = c0 + threadIdx.x;
+        const int flag = (c < Cg) ? (int)mark[g * Cg + c] : 0;
+        int pos, tot;
+        Scan(tmp).ExclusiveSum(flag, pos, tot);
+        const int b = base;
+        if (flag) sel[g * k + b + pos] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) base = b + tot;
+        __syncthreads();
+    }
+}
+
+// Wsel[g][s][j] = W[s][g*Cg + sel[g][j]]
+__global__ void gather_topk_kernel(const double* __restrict__ W, long long S, long long G, long long Cg, long long k,
+                                   const long long* __restrict__ sel, double* __restrict__ Wsel) {
+    const long long total = G * S * k;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long j = i % k, gs = i / k, s = gs % S, g = gs / S;
+        Wsel[i] = W[s * (G * Cg) + g * Cg + sel[g * k + j]];
     }
 }
 
@@ -276,4 +320,61 @@ extern "C" int rc_kendall_tau_b_batched(const double* x_dev, const int64_t* y_de
 extern "C" int rc_kendall_tau_b(const double* x_dev, int64_t Rx, const int64_t* y_dev, int64_t Ry, int64_t n,
                                 double* tau_dev, long long* counts_dev, void* stream) {
     return rc_kendall_tau_b_batched(x_dev, y_dev, 1, Rx, Ry, n, tau_dev, counts_dev, stream);
+}
+
+// Workspace layout of rc_rank_consistency: [argsort workspace (max of the two problems)] [mark bytes]
+// [clustered ranks double G*S*k] [ordinal ranks int64 G*S*k] [kendall counts int64 G*S*S*4]
+extern "C" size_t rc_rank_consistency_workspace_bytes(int64_t S, int64_t G, int64_t Cg, int64_t topk) {
+    if (S <= 0 || G <= 0 || Cg <= 0) return 256;
+    const long long k = topk < Cg ? topk : Cg;
+    size_t a = rc_ranks_workspace_bytes(G, Cg), b = rc_ranks_workspace_bytes(G * S, k);
+    if (a == 0 || b == 0) return 0;
+    size_t ws = a > b ? a : b;
+    return align256(ws) + align256((size_t)G * Cg) + 2 * align256((size_t)G * S * k * 8) + align256((size_t)G * S * S * 4 * 8) + 256;
+}
+
+extern "C" int rc_rank_consistency(const double* W_dev, int64_t S, int64_t G, int64_t Cg, int64_t topk, double alpha,
+                                   double* tau_dev, int64_t* sel_dev, double* Wsel_dev, void* workspace_dev,
+                                   size_t workspace_bytes, void* stream) {
+    if (S < 0 || G < 0 || Cg < 0 || topk < 1) return set_error(RC_ERR_BAD_ARG, "rc_rank_consistency: bad sizes");
+    if (S == 0 || G == 0 || Cg == 0) return RC_OK;
+    if (!W_dev || !tau_dev || !sel_dev || !Wsel_dev || !workspace_dev) return set_error(RC_ERR_NULL, "rc_rank_consistency: null pointer");
+    const size_t need = rc_rank_consistency_workspace_bytes(S, G, Cg, topk);
+    if (need == 0) return set_error(RC_ERR_BAD_ARG, "rc_rank_consistency: problem too large");
+    if (workspace_bytes < need) return set_error(RC_ERR_WORKSPACE, "rc_rank_consistency: workspace %zu < %zu", workspace_bytes, need);
+    if (S * S > 65535 || G > 65535) return set_error(RC_ERR_BAD_ARG, "rc_rank_consistency: too many sigma pairs or groups");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long k = topk < Cg ? topk : Cg;
+    size_t a = rc_ranks_workspace_bytes(G, Cg), b = rc_ranks_workspace_bytes(G * S, k);
+    const size_t ws_sort = align256(a > b ? a : b);
+    char* p = (char*)workspace_dev;
+    void* sortws = p; p += ws_sort;
+    unsigned char* mark = (unsigned char*)p; p += align256((size_t)G * Cg);
+    double* cr = (double*)p; p += align256((size_t)G * S * k * 8);
+    long long* rk = (long long*)p; p += align256((size_t)G * S * k * 8);
+    long long* counts = (long long*)p;
+    const int sm = device_sm_count();
+    // 1. ranks of the sigma-index-0 row inside every group (W row 0 is [G][Cg] contiguous)
+    int rcode = argsort_rows(W_dev, G, Cg, sortws, ws_sort, st);
+    if (rcode) return rcode;
+    RC_CUDA_TRY(cudaMemsetAsync(mark, 0, (size_t)G * Cg, st));
+    long long blocks = (G * k + 255) / 256;
+    if (blocks > sm * 8) blocks = sm * 8;
+    mark_topk_kernel<<<(unsigned)blocks, 256, 0, st>>>((const int*)sortws, G, Cg, k, mark);
+    compact_topk_kernel<<<(unsigned)G, 256, 0, st>>>(mark, Cg, k, (long long*)sel_dev);
+    blocks = (G * S * k + 255) / 256;
+    if (blocks > sm * 8) blocks = sm * 8;
+    gather_topk_kernel<<<(unsigned)blocks, 256, 0, st>>>(W_dev, S, G, Cg, k, (const long long*)sel_dev, Wsel_dev);
+    RC_CUDA_TRY(cudaGetLastError());
+    // 2. clustered ranks (radius alpha*(max-min) per row) and ordinal ranks + 1 of every selected row
+    rcode = argsort_rows(Wsel_dev, G * S, k, sortws, ws_sort, st);
+    if (rcode) return rcode;
+    long long wb = (G * S + 31) / 32;
+    clustered_walk_kernel<<<(unsigned)wb, 32, 0, st>>>(Wsel_dev, (const int*)sortws, G * S, k, alpha, 0.0, cr);
+    blocks = (G * S * k + 255) / 256;
+    if (blocks > sm * 8) blocks = sm * 8;
+    scatter_ranks_kernel<<<(unsigned)blocks, 256, 0, st>>>((const int*)sortws, G * S, k, rk, 1);
+    RC_CUDA_TRY(cudaGetLastError());
+    // 3. S x S Kendall tau-b per group
+    return rc_kendall_tau_b_batched(cr, (const int64_t*)rk, G, S, S, k, tau_dev, counts, stream);
 }

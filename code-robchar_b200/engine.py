@@ -232,12 +232,11 @@ def kendall_tau_b_batched(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
 
 
 def grouped_rank_consistency(W: torch.Tensor, groups: int, topk: int = 100, alpha: float = 0.05):
-    """The paper's fig-4 analysis for `groups` controller sets at once.  W: RIM matrix [S][groups*Cg].
-    Per group: keep the topk controllers with the smallest RIM at sigma_sim index 0
-    (mcsim.py:651-660), then the S x S Kendall matrix of clustered vs ordinal ranks
-    (generate_fig4_kendallrankanalysis.py:94-120).  Returns (tau [G][S][S], selected column index
-    [G][topk] within the group, W_topk [G][S][topk]).  Index bookkeeping (reshape / gather) is
-    torch plumbing; every comparison-based result comes from the rank / Kendall kernels."""
+    """The paper's fig-4 analysis for `groups` controller sets at once (one C call).  W: RIM matrix
+    [S][groups*Cg].  Per group: keep the topk controllers with the smallest RIM at sigma_sim index 0
+    in their original column order (mcsim.py:651-660), then the S x S Kendall matrix of clustered vs
+    ordinal ranks (generate_fig4_kendallrankanalysis.py:94-120).  Returns (tau [G][S][S], selected
+    column index [G][k] within the group, W_topk [G][S][k])."""
     dev = require_cuda()
     W = _f64(W, dev)
     S, Ctot = W.shape
@@ -245,13 +244,17 @@ def grouped_rank_consistency(W: torch.Tensor, groups: int, topk: int = 100, alph
         raise ValueError("controller count must be a multiple of the group count")
     Cg = Ctot // groups
     k = min(topk, Cg)
-    Wg = W.reshape(S, groups, Cg).permute(1, 0, 2).contiguous()          # [G][S][Cg]
-    rk0 = ranks(Wg[:, 0, :].contiguous())                               # [G][Cg]
-    sel = torch.nonzero(rk0 <= k - 1)[:, 1].reshape(groups, k)           # original column order kept
-    Wsel = torch.gather(Wg, 2, sel[:, None, :].expand(groups, S, k)).contiguous()
-    cr = clustered_ranks(Wsel.reshape(groups * S, k), alpha=alpha).reshape(groups, S, k)
-    rk = (ranks(Wsel.reshape(groups * S, k)) + 1).reshape(groups, S, k)
-    return kendall_tau_b_batched(cr, rk), sel, Wsel
+    tau = torch.empty((groups, S, S), dtype=torch.float64, device=dev)
+    sel = torch.empty((groups, k), dtype=torch.int64, device=dev)
+    Wsel = torch.empty((groups, S, k), dtype=torch.float64, device=dev)
+    wb = lib().rc_rank_consistency_workspace_bytes(S, groups, Cg, topk)
+    if wb == 0:
+        raise ValueError("ranking problem too large")
+    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+    check(lib().rc_rank_consistency(_ptr(W), S, groups, Cg, topk, float(alpha), _ptr(tau), _ptr(sel), _ptr(Wsel),
+                                    _ptr(ws), wb, _stream()))
+    _count(10)
+    return tau, sel, Wsel
 
 
 def kendall_matrix(wd_data_c, alpha: float = 0.05) -> torch.Tensor:
@@ -285,6 +288,46 @@ def mc_sweep_host(ctrl: np.ndarray, sigmas: np.ndarray, B: int, nspin: int, insp
                                  int(bool(fused)), vp(fids_out), vp(stats_out), _stream()))
     _count(2)
     return stats_out, fids_out
+
+
+_PINNED = {}
+
+
+def _pinned(name, shape, dtype):
+    """Cached pinned host buffer (numpy view) so D2H copies run at full PCIe rate and asynchronously."""
+    key = (name, tuple(shape), dtype)
+    if key not in _PINNED:
+        _PINNED[key] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+    return _PINNED[key].numpy()
+
+
+def robustness_sweep_host(ctrl: np.ndarray, sigmas: np.ndarray, B: int, nspin: int, inspin: int, outspin: int, *,
+                          groups: int = 1, topk: int = 100, alpha_cluster: float = 0.05, dkw_eps: float = 0.0,
+                          model: int = MODEL_COMPLEX3, zz: bool = False, seed: int = 0, c_offset: int = 0,
+                          b_offset: int = 0, fused: bool = False, pinned_outputs: bool = True):
+    """Evolution + statistics + per-group top-k / Kendall matrices in ONE C call with host buffers
+    (rc_robustness_sweep_host).  Returns (stats [15][S][C], tau [G][S][S], sel [G][k]) as numpy arrays;
+    with pinned_outputs they are views of cached pinned buffers (copy them to keep across calls)."""
+    require_cuda()
+    ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+    sigmas = np.ascontiguousarray(sigmas, dtype=np.float64).reshape(-1)
+    Cn, S = ctrl.shape[0], sigmas.shape[0]
+    if Cn % groups:
+        raise ValueError("controller count must be a multiple of the group count")
+    k = min(topk, Cn // groups)
+    if pinned_outputs:
+        st = _pinned("stats", (NUM_STATS, S, Cn), torch.float64)
+        tau = _pinned("tau", (groups, S, S), torch.float64)
+        sel = _pinned("sel", (groups, k), torch.int64)
+    else:
+        st, tau, sel = np.empty((NUM_STATS, S, Cn)), np.empty((groups, S, S)), np.empty((groups, k), dtype=np.int64)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    check(lib().rc_robustness_sweep_host(vp(ctrl), Cn, nspin, inspin, outspin, vp(sigmas), S, B, model, int(bool(zz)),
+                                         C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, float(dkw_eps),
+                                         int(bool(fused)), groups, topk, float(alpha_cluster), vp(st), vp(tau), vp(sel),
+                                         _stream()))
+    _count(12)
+    return st, tau, sel
 
 
 def fp64_peak_tflops() -> float:

@@ -41,11 +41,8 @@ def robustness_sweep(controllers: np.ndarray, noises: np.ndarray, bootreps: int,
     the 15 statistics, per-group top-k selection and Kendall matrices.  Host in, host out: the
     controllers travel to the device and the statistics / tau matrices come back (the end-to-end
     call bench.py times).  Returns {"stats": {key: [S][C]}, "tau": [G][S][S], "topk_idx": [G][k]}."""
-    import torch
     eps = float(compute_dkw_error(alpha_dkw, bootreps))
-    st, _ = engine.mc_sweep_host(np.asarray(controllers), np.asarray(noises), bootreps, Nspin, inspin, outspin,
-                                 dkw_eps=eps, seed=seed, fused=fused, model=model, zz=zz)
-    W = torch.as_tensor(st[0]).cuda()
-    tau, sel, _ = engine.grouped_rank_consistency(W, groups, topk=topk, alpha=alpha_cluster)
-    return {"stats": {k: st[i] for i, k in enumerate(engine.STAT_KEYS)}, "tau": tau.cpu().numpy(),
-            "topk_idx": sel.cpu().numpy()}
+    st, tau, sel = engine.robustness_sweep_host(np.asarray(controllers), np.asarray(noises), bootreps, Nspin, inspin,
+                                                outspin, groups=groups, topk=topk, alpha_cluster=alpha_cluster,
+                                                dkw_eps=eps, seed=seed, fused=fused, model=model, zz=zz)
+    return {"stats": {k: st[i] for i, k in enumerate(engine.STAT_KEYS)}, "tau": tau, "topk_idx": sel}

@@ -117,6 +117,19 @@ int rc_kendall_tau_b(const double* x_dev, int64_t Rx, const int64_t* y_dev, int6
 int rc_kendall_tau_b_batched(const double* x_dev, const int64_t* y_dev, int64_t G, int64_t Rx, int64_t Ry,
                              int64_t n, double* tau_dev, long long* counts_dev, void* stream);
 
+/* The paper's fig-4 rank-consistency analysis for G controller groups in one call.
+ * W_dev: RIM matrix [S][G*Cg] (row 0 of the statistics tensor).  Per group: keep the topk
+ * controllers with the smallest RIM at sigma index 0, in their original column order
+ * (get_top_k_by_fid, mcsim.py:651-660 with fid_thres=None), then the S x S Kendall matrix of
+ * clustered ranks (radius alpha*(max-min)) against ordinal ranks + 1
+ * (jkt_or_ordinaltau_pairwise, generate_fig4_kendallrankanalysis.py:94-120).
+ * Outputs: tau_dev [G][S][S], sel_dev int64 [G][k] (column index inside the group),
+ * Wsel_dev [G][S][k], with k = min(topk, Cg). */
+size_t rc_rank_consistency_workspace_bytes(int64_t S, int64_t G, int64_t Cg, int64_t topk);
+int rc_rank_consistency(const double* W_dev, int64_t S, int64_t G, int64_t Cg, int64_t topk, double alpha,
+                        double* tau_dev, int64_t* sel_dev, double* Wsel_dev, void* workspace_dev,
+                        size_t workspace_bytes, void* stream);
+
 /* Whole sweep with HOST buffers: H2D of controllers/sigmas(/replay), evolution, statistics, D2H of
  * the 15 metric tensors (and of the fidelity tensor when fids_host != NULL).  This is what
  * MCDataSim.get_metrics_dict (mcsim.py:463-510) computes from scratch.
@@ -125,6 +138,16 @@ int rc_mc_sweep_host(const double* ctrl_host, int64_t C, int nspin, int inspin, 
                      const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
                      int64_t c_offset, int64_t b_offset, const double* replay_host, double dkw_eps,
                      int fused, double* fids_host, double* stats_host, void* stream);
+
+/* rc_mc_sweep_host followed by rc_rank_consistency on the device, everything returned to HOST
+ * buffers: stats_host [15][S][C], tau_host [G][S][S], sel_host int64 [G][k] (C = G*Cg).  This is the
+ * whole fig-4/5 sweep of one problem as a single call (pinned host buffers make the copies
+ * asynchronous up to the final synchronisation). */
+int rc_robustness_sweep_host(const double* ctrl_host, int64_t C, int nspin, int inspin, int outspin,
+                             const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
+                             int64_t c_offset, int64_t b_offset, double dkw_eps, int fused, int64_t G,
+                             int64_t topk, double alpha_cluster, double* stats_host, double* tau_host,
+                             int64_t* sel_host, void* stream);
 
 /* FP64 FMA throughput micro-benchmark of the current device (TFLOP/s, 2 flops per DFMA); used as
  * the roofline denominator of the evolution kernel. */

@@ -397,3 +397,30 @@ def test_full_size_properties_nspin7(rb):
     tau = rb.engine.kendall_matrix(W[:, top].contiguous(), alpha=0.05).cpu().numpy()
     assert tau.shape == (11, 11) and np.all(np.abs(tau[np.isfinite(tau)]) <= 1)
     assert tau[0, 0] > 0.5 and np.all(np.diag(tau) > 0.3)
+
+
+def test_rank_consistency_single_call(rb):
+    """rc_rank_consistency == per-group composition of the reference functions (top-k in original
+    column order, clustered vs ordinal ranks, Kendall matrix), incl. the host-buffer sweep call."""
+    rs = np.random.RandomState(5)
+    S, G, Cg, k = 5, 3, 37, 10
+    W = rs.uniform(0, 0.4, (S, G * Cg))
+    W[0, 5] = W[0, 6]                                   # exact tie at the selection row
+    tau, sel, Wsel = rb.engine.grouped_rank_consistency(W, G, topk=k, alpha=0.05)
+    tau, sel, Wsel = tau.cpu().numpy(), sel.cpu().numpy(), Wsel.cpu().numpy()
+    for g in range(G):
+        Wg = W[:, g * Cg:(g + 1) * Cg]
+        mask = orc.get_top_k_mask(Wg[0], k)
+        assert np.array_equal(sel[g], np.nonzero(mask)[0])
+        assert np.array_equal(Wsel[g], Wg[:, mask])
+        assert np.array_equal(tau[g], orc.kendall_matrix(Wg[:, mask], alpha=0.05), equal_nan=True)
+    n = 6
+    ctrl = orc.synthetic_controllers(G * Cg, n)
+    sig = np.linspace(0, 0.1, S)
+    eps = float(orc.compute_dkw_error(0.05, 50))
+    out = rb.rim_analysis.robustness_sweep(ctrl, sig, 50, n, 0, 5, groups=G, topk=k, seed=4)
+    f = rb.engine.fidelity_mc(ctrl, sig, 50, n, 0, 5, seed=4)
+    st = rb.engine.stats(f, eps).cpu().numpy()
+    assert np.array_equal(out["stats"][orc.METRIC_W], st[0])
+    t2, s2, _ = rb.engine.grouped_rank_consistency(st[0], G, topk=k)
+    assert np.array_equal(out["tau"], t2.cpu().numpy(), equal_nan=True) and np.array_equal(out["topk_idx"], s2.cpu().numpy())
