@@ -11,7 +11,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librobchar_b200.so")
+LIB_PATH = os.environ.get("RC_LIB_PATH") or os.path.join(_HERE, "librobchar_b200.so")  # override: tuning builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "robchar_b200.h")
 
 RC_OK = 0

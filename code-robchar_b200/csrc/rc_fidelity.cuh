@@ -60,7 +60,7 @@ __device__ __forceinline__ void build_tridiagonal(const double* __restrict__ x, 
             double a = __dadd_rn(1.0, __dmul_rn(sigma, get(P * i + 1)));
             if (MODEL == MODEL_COMPLEX3) {
                 double bb = __dmul_rn(sigma, get(P * i + 2));
-                e[i - 1] = sqrt(fma(a, a, bb * bb));  // |1 + nn + i nn2|
+                e[i - 1] = rc_sqrt(fma(a, a, bb * bb));  // |1 + nn + i nn2|
             } else {
                 e[i - 1] = a;
             }
@@ -119,8 +119,11 @@ __device__ __forceinline__ double eval_reg(const FidArgs& a, long long s, long l
     return f;
 }
 
+#ifndef RC_REG_MIN_BLOCKS
+#define RC_REG_MIN_BLOCKS 1
+#endif
 template <int N, int MODEL, bool REPLAY>
-__global__ void __launch_bounds__(128) fidelity_reg_kernel(FidArgs a) {
+__global__ void __launch_bounds__(128, RC_REG_MIN_BLOCKS) fidelity_reg_kernel(FidArgs a) {
     constexpr int K = draws_per_site(MODEL) * N;
     constexpr int KP = K | 1;
     extern __shared__ double stage[];
@@ -290,7 +293,7 @@ __device__ __forceinline__ double eval_smem(const FidArgs& a, long long s, long 
             double aa = __dadd_rn(1.0, __dmul_rn(sigma, get(P * i + 1)));
             if (MODEL == MODEL_COMPLEX3) {
                 double bb = __dmul_rn(sigma, get(P * i + 2));
-                e[(size_t)(i - 1) * ld] = sqrt(fma(aa, aa, bb * bb));
+                e[(size_t)(i - 1) * ld] = rc_sqrt(fma(aa, aa, bb * bb));
             } else {
                 e[(size_t)(i - 1) * ld] = aa;
             }

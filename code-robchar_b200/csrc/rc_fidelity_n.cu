@@ -29,6 +29,7 @@ static cudaError_t launch_reg(const FidArgs& a, int sm_count, cudaStream_t st) {
     const int threads = reg_threads();
     size_t smem = (size_t)threads * (K | 1) * sizeof(double);  // one private row per lane
     auto kern = fidelity_reg_kernel<N, MODEL, REPLAY>;
+    if (const char* e = getenv("RC_FID_SMEM_PAD")) smem += (size_t)atoi(e) * 1024;  // tuning: limits CTAs/SM
     cudaError_t err;
     if (smem > 40 * 1024) {
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

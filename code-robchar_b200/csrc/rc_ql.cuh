@@ -18,46 +18,17 @@
 #pragma once
 #include <math.h>
 #include <float.h>
+#include "rc_math.cuh"
 
 #if defined(__CUDACC__)
-#define RC_HD __host__ __device__ __forceinline__
 #define RC_D __device__ __forceinline__
 #else
-#define RC_HD inline
 #define RC_D inline
 #endif
 
 namespace rc {
 
 constexpr int QL_MAX_SWEEPS = 40;  // per eigenvalue (EISPACK uses 30)
-
-// 1/sqrt(h) for normal positive h: hardware seed (MUFU.RSQ64H, ~2^-22) + one cubic correction
-// y1 = y0 (1 + e/2 + 3 e^2/8), e = 1 - h y0^2  (error ~ e^3: full double precision), 5 DFMA-class
-// ops instead of the library routine's special-case handling.
-RC_HD double rc_rsqrt(double h) {
-#if defined(__CUDA_ARCH__)
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(h));
-    const double t = h * y;
-    const double e = fma(-t, y, 1.0);
-    const double q = e * fma(0.375, e, 0.5);
-    return fma(y, q, y);
-#else
-    return 1.0 / sqrt(h);
-#endif
-}
-
-// 1/t to ~2^-44 (seed + one Newton step): only used for the Wilkinson shift, whose accuracy affects
-// the convergence rate but never the result (the similarity transform is orthogonal for any shift).
-RC_HD double rc_rcp_approx(double t) {
-#if defined(__CUDA_ARCH__)
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
-    return fma(y, fma(-t, y, 1.0), y);
-#else
-    return 1.0 / t;
-#endif
-}
 
 #ifdef RC_QL_STATS
 struct QlStats { int sweeps_per_l[64]; int total_sweeps; int rotations; };
@@ -91,7 +62,7 @@ struct QlSweep {
                 double b = c * e[i];
                 // h >= tol^2-ish inside an unreduced block; the tiny offset only keeps the (measure-zero)
                 // total-cancellation case finite instead of branching on it in the hot loop
-                double h = fma(f, f, g * g) + 1e-280;
+                double h = fma(f, f, fma(g, g, 1e-280));
                 double rinv = rc_rsqrt(h);
                 r = h * rinv;
                 e[i + 1] = r;
@@ -269,7 +240,7 @@ RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int ou
 #endif
     for (int k = 0; k < N; ++k) {
         double sn, cs;
-        sincos(scratch[(size_t)k * sstride] * T, &sn, &cs);
+        rc_sincos(scratch[(size_t)k * sstride] * T, &sn, &cs);
         const double w = scratch[(size_t)(N + k) * sstride];
         re = fma(w, cs, re);
         im = fma(-w, sn, im);
