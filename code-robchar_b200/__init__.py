@@ -6,7 +6,7 @@ include/robchar_b200.h.  Importing the package does not need a GPU; calling any 
 point without the built library or without a CUDA device raises (no CPU fallback).
 """
 from . import _lib, engine  # noqa: F401
-from . import noise_model, wd_sortof_fast_implementation, rim_analysis, noise_analysis, mcsim, kendall, dist  # noqa: F401
+from . import noise_model, wd_sortof_fast_implementation, rim_analysis, noise_analysis, mcsim, kendall, dist, arim, qnewton  # noqa: F401
 from .mcsim import MCDataSim  # noqa: F401
 from .noise_model import noise_function, structured_perturbation, directional_perturbation  # noqa: F401
 from .wd_sortof_fast_implementation import wd_from_ideal, wd_from_ideal_zero, RIM_p, compute_dkw_error  # noqa: F401

@@ -1,0 +1,164 @@
+"""Fidelity evaluator with the interface of upstream's ``qnewton.LBFGS`` (the optimisers' objective).
+
+Mirrors the evaluator half of ``qnewton.py``: constructor arguments (:28-42), ``sys_hamiltonian``
+(:140-151, incl. the Heisenberg/Z diagonal), ``controls`` (:153-159), ``structured_perturabation``
+(:366-379, real symmetric, two draws per site), ``randHset_constructor`` (:122-137, seed 4),
+``fidelity_ss`` (:383-423 incl. binomial shot noise), ``fidelity_ss_av`` (:425-444) and ``wass_cost``
+(:447-455).  All propagators run on the GPU (RC_MODEL_REAL2 replay rows); random numbers are drawn on
+the host from ``np.random`` in upstream's order so a seeded run reproduces upstream's values.
+The optimiser loops themselves (``run``) are CPU control flow and out of scope: an optimiser can be
+pointed at this class as a drop-in objective (ppo.py:179 builds ``LBFGS(nspin, In, Out, noise=noise)``).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import engine
+from ._lib import MODEL_REAL2
+
+
+class LBFGS(object):
+    def __init__(self, nspin, in_spin, out_spin, bmin=-10, bmax=10, max_time=30, repeats=1000000, fid_threshold=0.98,
+                 topo="linear", noisy=False, fid_noisy=False, draws=10, ham_noisy=False, verbose=False, adp_tol=0.05,
+                 adaptive=False, noise=0.05, use_wass_cost=False, heisenberg_int: bool = False,
+                 use_fixed_ham: bool = False, opt_train_size: int = 100, opt_test_size: int = 10000, **_ignored):
+        if topo == "ring":
+            raise NotImplementedError("only the open chain is on the GPU path")
+        self.topo = topo
+        self.heisenberg_int = heisenberg_int
+        self.Nspin, self.In, self.Out = nspin, in_spin, out_spin
+        self.Tmin, self.Tmax, self.Bmin, self.Bmax = 0, max_time, bmin, bmax
+        self.repeats = repeats
+        self.HH = self.sys_hamiltonian()
+        self.CC = self.controls()
+        self.fid_threshold = fid_threshold
+        self.draws = draws
+        self.ham_noisy = ham_noisy
+        self.fid_noisy = fid_noisy
+        self.verbose = verbose
+        self.adp_tol = adp_tol
+        self.adaptive = adaptive
+        self.adp_func_calls_increment = self.draws
+        self.noise = noise
+        self.use_wass_cost = use_wass_cost
+        self.val_bounds = [(self.Bmin, self.Bmax)] * self.Nspin + [(self.Tmin, self.Tmax)]
+        self.use_fixed_ham = use_fixed_ham
+        self.train_size = opt_train_size
+        self.randH, self.randH_test = self.randHset_constructor(train_size=opt_train_size, test_size=opt_test_size)
+        self._rows_train = self._rows_test = None
+
+    # ---- model -------------------------------------------------------------------------------------
+    def sys_hamiltonian(self):
+        n = self.Nspin
+        HH = np.zeros((n, n), dtype=np.complex128)
+        for l in range(1, n):
+            HH[l - 1, l] = 1
+            HH[l, l - 1] = 1
+        if self.heisenberg_int:
+            t = 0.5 * np.triu(HH).sum().sum() * np.ones(n) - np.sum(HH, axis=1)
+            HH += np.diag(t)
+        return HH
+
+    def controls(self):
+        CC = []
+        for k in range(self.Nspin):
+            CM = np.zeros((self.Nspin, self.Nspin))
+            CM[k, k] = 1
+            CC.append(CM)
+        return CC
+
+    def structured_perturabation(self):
+        """qnewton.py:366-379: (z_ii, nn_i) per site, nn_0 consumed and discarded."""
+        n = self.Nspin
+        z = np.zeros((n, n), dtype=np.complex128)
+        for i in range(n):
+            z[i][i] = np.random.normal(scale=self.noise)
+            nn = np.random.normal(scale=self.noise)
+            if i >= 1:
+                z[i][i - 1] = nn
+                z[i - 1][i] = nn
+        return z
+
+    def randHset_constructor(self, train_size=1000, test_size=10000):
+        """qnewton.py:122-137 (fixed seed 4, train then test)."""
+        np.random.seed(4)
+        out_train = np.zeros((train_size, self.Nspin, self.Nspin), dtype="complex128")
+        for i in range(train_size):
+            out_train[i] = self.HH + self.structured_perturabation()
+        out_test = np.zeros((test_size, self.Nspin, self.Nspin), dtype="complex128")
+        for i in range(test_size):
+            out_test[i] = self.HH + self.structured_perturabation()
+        return out_train, out_test
+
+    # ---- packing of explicit Hamiltonians into replay rows (sigma = 1) -----------------------------------
+    def _rows_from_hamiltonians(self, H: np.ndarray) -> np.ndarray:
+        """[m][N][N] real-symmetric tridiagonal Hamiltonians (HH + perturbation) -> [m][2N] replay rows."""
+        H = np.asarray(H)
+        n = self.Nspin
+        rows = np.zeros((H.shape[0], 2 * n))
+        base = np.real(np.diag(self.HH))
+        rows[:, 0::2] = np.real(np.diagonal(H, axis1=1, axis2=2)) - base
+        lo = np.real(np.diagonal(H, offset=-1, axis1=1, axis2=2))
+        rows[:, 3::2] = lo - 1.0
+        return rows
+
+    def _eval_rows(self, x, rows: np.ndarray) -> torch.Tensor:
+        xa = np.asarray(x, dtype=np.float64).reshape(1, self.Nspin + 1)
+        m = rows.shape[0]
+        return engine.fidelity_mc(xa, np.ones(1), m, self.Nspin, self.In, self.Out, model=MODEL_REAL2,
+                                  zz=self.heisenberg_int, replay=rows.reshape(1, 1, m, 2 * self.Nspin)).reshape(-1)
+
+    # ---- objectives -------------------------------------------------------------------------------------
+    def _shot_noise(self, fid):
+        if not self.adaptive:
+            return np.random.binomial(self.draws, fid) / self.draws        # qnewton.py:407
+        a, b = 0.5, 0.5
+        mean = a / (a + b)
+        var = mean * (1 - mean) / (a + b + 1)
+        while np.sqrt(var) > self.adp_tol:                                 # qnewton.py:411-421
+            s = np.random.binomial(self.draws, fid)
+            a += s
+            b += (self.draws - s)
+            mean = (a + s) / (a + b + self.draws)
+            var = mean * (1 - mean) / (a + b + self.draws + 1)
+            self.adp_func_calls_increment += self.draws
+        return mean
+
+    def fidelity_ss(self, x, noisy=False, ham_noisy=False, use_fixed_ham=False, rH=None):
+        """qnewton.py:383-423."""
+        n = self.Nspin
+        if use_fixed_ham:
+            if rH is None:
+                raise AssertionError(f"H cannot be {type(rH)}")
+            rows = self._rows_from_hamiltonians(np.asarray(rH)[None])
+        else:
+            rows = np.zeros((1, 2 * n))
+            if ham_noisy:
+                rows = self._rows_from_hamiltonians((self.HH + self.structured_perturabation())[None])
+        fid = float(self._eval_rows(x, rows)[0].item())
+        return self._shot_noise(fid) if noisy else fid
+
+    def fidelity_ss_av(self, x, noisy=False, ham_noisy=False, reps=10, test=False):
+        """qnewton.py:425-444: mean over the first `reps` fixed training Hamiltonians (or the whole test set)."""
+        if self._rows_train is None:
+            self._rows_train = self._rows_from_hamiltonians(self.randH)
+            self._rows_test = self._rows_from_hamiltonians(self.randH_test)
+        rows = self._rows_test if test else self._rows_train[:reps]
+        f = self._eval_rows(x, rows)
+        if noisy:
+            f = torch.as_tensor(np.array([self._shot_noise(v) for v in f.cpu().numpy()]))
+        return float(f.mean().item())
+
+    def wass_cost(self, x, bootstrap_reps=5):
+        """qnewton.py:447-455: W1 to delta(1) of `bootstrap_reps` noisy fidelities (host draws in upstream order)."""
+        rows = np.stack([self._rows_from_hamiltonians((self.HH + self.structured_perturabation())[None])[0]
+                         for _ in range(bootstrap_reps)])
+        f = self._eval_rows(x, rows)
+        return float(engine.stats(f.reshape(1, -1), 0.0)[0, 0].item())
+
+    def infidelity(self, x):
+        return 1 - self.fidelity_ss(x, noisy=self.fid_noisy, ham_noisy=self.ham_noisy)
+
+    def run(self, *a, **k):
+        raise NotImplementedError("optimiser loops are out of scope; use this class as the objective evaluator")

@@ -269,6 +269,38 @@ def make_large_n():
     print("replay_large_n done")
 
 
+def make_objective_and_arim():
+    """Optimiser-side objectives (qnewton.py:425-455, :407) and ARIM + bootstrap std
+    (generate_arim_all_fig5.py:119-126, mcsim.py:267-275) from the unmodified reference."""
+    import qnewton as ref_q
+    out = {}
+    n, i, o = 5, 0, 4
+    env = ref_q.LBFGS(n, i, o, noise=0.05, opt_train_size=20)
+    rs = np.random.RandomState(77)
+    X = np.concatenate([rs.uniform(-10, 10, (4, n)), rs.uniform(1, 30, (4, 1))], axis=1)
+    out["obj_X"] = X; out["obj_meta"] = np.array([n, i, o, 20])
+    out["obj_av10"] = np.array([env.fidelity_ss_av(x, reps=10) for x in X])
+    out["obj_av_test"] = np.array([env.fidelity_ss_av(x, test=True) for x in X[:2]])
+    np.random.seed(11)
+    out["obj_wass7"] = np.array([env.wass_cost(x, 7) for x in X])
+    np.random.seed(12)
+    out["obj_shot"] = np.array([env.fidelity_ss(x, noisy=True, ham_noisy=True) for x in X])
+    env.adaptive = True
+    np.random.seed(13)
+    out["obj_adaptive"] = np.array([env.fidelity_ss(x, noisy=True, ham_noisy=False) for x in X])
+    out["obj_randH0"] = env.randH[0]
+    # ARIM
+    rs = np.random.RandomState(5)
+    wdd = rs.uniform(0, 0.5, (11, 100)) * np.linspace(0.2, 1, 11)[:, None]
+    out["arim_rims"] = wdd
+    out["arim_centre"] = np.array([ref_wd.wd_from_ideal_zero(wdd[j].copy()) for j in range(11)])
+    np.random.seed(21)
+    out["arim_std"] = np.array([ref_mc.MCDataSim.bootstrap_resampling_std(ref_wd.wd_from_ideal_zero, wdd[j].copy(), 100)
+                                for j in range(11)])
+    np.savez_compressed(f"{OUT}/objective_arim.npz", **out)
+    print("objective_arim done")
+
+
 if __name__ == "__main__":
     make_kat_bestfid()
     make_kat_mc_zero()
@@ -277,3 +309,4 @@ if __name__ == "__main__":
     make_replay()
     make_real2_and_zz()
     make_large_n()
+    make_objective_and_arim()

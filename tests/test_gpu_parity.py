@@ -424,3 +424,57 @@ def test_rank_consistency_single_call(rb):
     assert np.array_equal(out["stats"][orc.METRIC_W], st[0])
     t2, s2, _ = rb.engine.grouped_rank_consistency(st[0], G, topk=k)
     assert np.array_equal(out["tau"], t2.cpu().numpy(), equal_nan=True) and np.array_equal(out["topk_idx"], s2.cpu().numpy())
+
+
+def test_optimiser_objectives_match_reference(rb):
+    """LBFGS-compatible evaluator vs the unmodified qnewton.LBFGS (fidelity_ss_av, wass_cost, shot noise)."""
+    g = load_golden("objective_arim.npz")
+    n, i, o, train = (int(v) for v in g["obj_meta"])
+    env = rb.qnewton.LBFGS(n, i, o, noise=0.05, opt_train_size=train)
+    assert np.array_equal(env.randH[0], g["obj_randH0"])                       # np.random.seed(4) set (qnewton.py:124)
+    X = g["obj_X"]
+    av10 = np.array([env.fidelity_ss_av(x, reps=10) for x in X])
+    assert np.abs(av10 - g["obj_av10"]).max() < FID_TOL
+    avt = np.array([env.fidelity_ss_av(x, test=True) for x in X[:2]])
+    assert np.abs(avt - g["obj_av_test"]).max() < FID_TOL
+    np.random.seed(11)
+    w = np.array([env.wass_cost(x, 7) for x in X])
+    assert np.abs(w - g["obj_wass7"]).max() < RIM_TOL
+    np.random.seed(12)
+    shot = np.array([env.fidelity_ss(x, noisy=True, ham_noisy=True) for x in X])
+    assert np.array_equal(shot, g["obj_shot"])                                # binomial counts / draws: exact
+    env.adaptive = True
+    np.random.seed(13)
+    ad = np.array([env.fidelity_ss(x, noisy=True, ham_noisy=False) for x in X])
+    assert np.abs(ad - g["obj_adaptive"]).max() < 1e-12
+    hz = rb.qnewton.LBFGS(6, 0, 3, heisenberg_int=True, opt_train_size=2, opt_test_size=2)
+    x = orc.synthetic_controllers(1, 6)[0]
+    assert abs(hz.fidelity_ss(x) - orc.evaluate_fidelity(x, 6, 0, 3, zz=True)) < FID_TOL
+    with pytest.raises(NotImplementedError):
+        env.run()
+
+
+def test_arim_and_bootstrap_match_reference(rb):
+    g = load_golden("objective_arim.npz")
+    rims = g["arim_rims"]
+    assert np.abs(rb.arim.arim(rims) - g["arim_centre"]).max() < 1e-13
+    np.random.seed(21)
+    c, s = rb.arim.arim_bootstrap(rims, 100, rng_mode="numpy")
+    assert np.abs(c - g["arim_centre"]).max() < 1e-13
+    assert np.abs(s - g["arim_std"]).max() < 1e-13
+    c2, s2 = rb.arim.arim_bootstrap(rims, 2000, rng_mode="torch", seed=3)
+    assert np.abs(c2 - c).max() < 1e-13 and np.abs(s2 / g["arim_std"] - 1).max() < 0.2   # statistical agreement
+
+
+def test_get_rims_mean_only_statistic(rb, tmp_path, monkeypatch):
+    """NStochOpt.get_rims (gen_fig_8_arim_fcall_scaling.py:121-132): 1 - mean fidelity per sigma level."""
+    monkeypatch.chdir(tmp_path)
+    sim = rb.arim.NStochOpt(experiment_name="x", Nspin=5, inspin=0, outspin=4, bootreps=4096, numcontrollers=4,
+                            noises=np.linspace(0, 0.1, 3))
+    ctrl = orc.synthetic_controllers(4, 5)
+    r = sim.get_rims(ctrl[1], seed=9)
+    f = rb.engine.fidelity_mc(ctrl[1:2], np.linspace(0, 0.1, 3), 4096, 5, 0, 4, seed=9).cpu().numpy()[:, 0]
+    assert np.abs(r - (1 - f.mean(axis=1))).max() < 1e-12
+    assert abs(r[0] - (1 - orc.evaluate_fidelity(ctrl[1], 5, 0, 4))) < FID_TOL
+    rb_all = sim.get_rims_batch(ctrl, seed=9)
+    assert rb_all.shape == (4, 3) and np.array_equal(rb_all[0], sim.get_rims(ctrl[0], seed=9))   # same Philox counters (c = 0)

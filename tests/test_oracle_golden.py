@@ -152,3 +152,10 @@ def test_rl_env_kats():
     assert orc.evaluate_fidelity(bad, 6, 0, 2) < 0.9025
     x = np.array([0.0, 0.0, 0.0, np.pi / np.sqrt(2)])
     assert abs(orc.evaluate_fidelity(x, 3, 0, 2) - 1.0) < 1e-12
+
+
+def test_arim_golden():
+    """ARIM = wd_from_ideal_zero of the RIM vector (generate_arim_all_fig5.py:119) from the reference."""
+    g = load_golden("objective_arim.npz")
+    for j in range(g["arim_rims"].shape[0]):
+        assert abs(orc.arim(g["arim_rims"][j]) - g["arim_centre"][j]) < 1e-15
