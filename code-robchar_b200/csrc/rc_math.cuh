@@ -51,6 +51,32 @@ RC_HD double rc_rcp_approx(double t) {
 #endif
 }
 
+// log(x) for normal x in (0,1) (the Box-Muller radius): fdlibm's e_log.c algorithm (exponent split,
+// s = f/(2+f), degree-7 minimax in s^2; published constants) without its special cases; the
+// division is an approximate reciprocal plus one residual correction.  <= 1 ulp on (0,1).
+RC_HD double rc_log01(double x) {
+#if defined(__CUDA_ARCH__)
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int k = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;                 // mantissa in [1,2)
+    if ((hi & 0x000fffff) >= 0x6a09f) { hi -= 0x00100000; k += 1; }   // > sqrt(2): halve
+    const double f = __hiloint2double(hi, lo) - 1.0;
+    const double den = 2.0 + f;
+    const double rcp = rc_rcp_approx(den);
+    double s = f * rcp;
+    s = fma(fma(-s, den, f), rcp, s);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
+                              6.666666666666735130e-01);
+    const double R = t1 + t2, hfsq = 0.5 * f * f, dk = (double)k;
+    return fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
+#else
+    return log(x);
+#endif
+}
+
 // sin and cos of r in [-pi/4, pi/4] (Taylor to r^17 / r^16: truncation < 5e-17), rotated by quadrant q.
 RC_HD void rc_sincos_quadrant(double r, int q, double* sn, double* cs) {
     const double r2 = r * r;

@@ -58,7 +58,7 @@ RC_HD void normal_pair(uint32_t seed_lo, uint32_t seed_hi, uint32_t sidx, uint64
     Philox4 r = philox4x32_10(c, seed_lo, seed_hi);
     double u1 = u53(r.x, r.y);
     double u2 = u53(r.z, r.w);
-    double rad = rc_sqrt(-2.0 * log(u1));
+    double rad = rc_sqrt(-2.0 * rc_log01(u1));
     double sn, cs;
     rc_sincos_2pi(u2, &sn, &cs);
     z0 = rad * cs;

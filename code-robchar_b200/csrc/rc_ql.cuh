@@ -18,6 +18,7 @@
 #pragma once
 #include <math.h>
 #include <float.h>
+#include <string.h>
 #include "rc_math.cuh"
 
 #if defined(__CUDACC__)
@@ -37,6 +38,20 @@ struct QlStats { int sweeps_per_l[64]; int total_sweeps; int rotations; };
 #define RC_STAT(x)
 #endif
 
+// |x| < 2^-20-granular threshold test on the high words: (hi(x) & 0x7fffffff) < hi(tol).  Slightly
+// stricter than |x| <= tol (values whose high word equals tol's are kept); zero always passes.
+RC_HD int hi_word(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    long long b;
+    memcpy(&b, &x, 8);
+    return (int)(b >> 32);
+#endif
+}
+RC_HD int threshold_hi(double tol) { int h = hi_word(tol); return h < 1 ? 1 : h; }
+RC_HD bool negligible_hi(double x, int tolhi) { return (hi_word(x) & 0x7fffffff) < tolhi; }
+
 RC_HD double wilkinson_g(double dl, double dl1, double el, double dm) {
     const double delta = 0.5 * (dl1 - dl);
     const double e2 = el * el;
@@ -49,7 +64,8 @@ RC_HD double wilkinson_g(double dl, double dl1, double el, double dm) {
 // e[i] couples sites i and i+1; e[N-1] is a scratch slot.
 template <int N, int L>
 struct QlSweep {
-    static RC_HD void run(double (&d)[N], double (&e)[N], double (&zi)[N], double (&zo)[N], int m, double dm) {
+    static RC_HD void run(double (&d)[N], double (&e)[N], double (&zi)[N], double (&zo)[N], int m, double dm,
+                          int mend = -1, double tiny = 1e-280) {
         // Wilkinson shift from the leading 2x2 of the block, single-division form:
         // mu = d[L] - e^2 / (delta + sign(delta) sqrt(delta^2 + e^2)),  g = d[m] - mu
         double g = wilkinson_g(d[L], d[L + 1], e[L], dm);
@@ -62,7 +78,7 @@ struct QlSweep {
                 double b = c * e[i];
                 // h >= tol^2-ish inside an unreduced block; the tiny offset only keeps the (measure-zero)
                 // total-cancellation case finite instead of branching on it in the hot loop
-                double h = fma(f, f, fma(g, g, 1e-280));
+                double h = fma(f, f, fma(g, g, tiny));
                 double rinv = rc_rsqrt(h);
                 r = h * rinv;
                 e[i + 1] = r;
@@ -83,9 +99,13 @@ struct QlSweep {
         }
         d[L] -= p;
         e[L] = g;
+        // the first rotation wrote r into e[m]; that slot is scratch when m is the end of the active
+        // block (never read), so the zeroing select chain only runs for a genuine interior split
+        if (m != mend) {
 #pragma unroll
-        for (int i = L + 1; i < N; ++i)
-            if (i == m) e[i] = 0.0;
+            for (int i = L + 1; i < N; ++i)
+                if (i == m) e[i] = 0.0;
+        }
     }
 };
 
@@ -205,9 +225,11 @@ RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int ou
     *fail = 0;
     if (!(fabs(chk) <= DBL_MAX)) return NAN;  // NaN / Inf controller or draw (mcsim.py:369-374)
     const double tol = DBL_EPSILON * anorm;
+    const int tolhi = threshold_hi(tol);
+    const double tiny = fmin(tol, 1e-280);  // == 1e-280, kept in a register instead of re-materialised per rotation
     int nact = N, ndone = 0, it = 0, bad = 0;
     while (nact > 1) {
-        if (fabs(e[0]) <= tol) {
+        if (negligible_hi(e[0], tolhi)) {
             // deflate: eigenvalue d[0] with weight V[in,k] V[out,k]
             scratch[(size_t)ndone * sstride] = d[0];
             scratch[(size_t)(N + ndone) * sstride] = zi[0] * zo[0];
@@ -216,18 +238,21 @@ RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int ou
             for (int i = 0; i < N - 1; ++i) { d[i] = d[i + 1]; e[i] = e[i + 1]; zi[i] = zi[i + 1]; zo[i] = zo[i + 1]; }
         }
         // sweep in the same trip unless the new leading off-diagonal is negligible as well
-        if (nact > 1 && !(fabs(e[0]) <= tol)) {
-            // first negligible off-diagonal inside the active block (descending scan: smallest wins)
+        if (nact > 1 && !negligible_hi(e[0], tolhi)) {
+            // first negligible off-diagonal inside the active block (descending scan: smallest wins).
+            // The block handed to the sweep must be unreduced: a zero interior coupling would drive
+            // g to exactly 0 and break the next rotation, so this scan runs every trip; it compares
+            // the high words as integers (ALU pipe) instead of fp64 compares.
             int m = nact - 1;
 #pragma unroll
             for (int i = N - 2; i >= 1; --i)
-                if (i < nact - 1 && fabs(e[i]) <= tol) m = i;
+                if (i < nact - 1 && negligible_hi(e[i], tolhi)) m = i;
             double dm = d[N - 1];
 #pragma unroll
             for (int i = N - 2; i >= 1; --i)
                 if (i == m) dm = d[i];
             if (++it > QL_MAX_SWEEPS) { bad = 1; break; }
-            QlSweep<N, 0>::run(d, e, zi, zo, m, dm);
+            QlSweep<N, 0>::run(d, e, zi, zo, m, dm, nact - 1, tiny);
             RC_STAT(st->total_sweeps++; st->rotations += m;)
         }
     }

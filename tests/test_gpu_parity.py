@@ -478,3 +478,24 @@ def test_get_rims_mean_only_statistic(rb, tmp_path, monkeypatch):
     assert abs(r[0] - (1 - orc.evaluate_fidelity(ctrl[1], 5, 0, 4))) < FID_TOL
     rb_all = sim.get_rims_batch(ctrl, seed=9)
     assert rb_all.shape == (4, 3) and np.array_equal(rb_all[0], sim.get_rims(ctrl[0], seed=9))   # same Philox counters (c = 0)
+
+
+@pytest.mark.parametrize("n", [4, 7, 12, 20])
+def test_split_matrices_zero_and_tiny_couplings(rb, n):
+    """Interior off-diagonals that are exactly zero / below the deflation threshold (the chain splits):
+    the lazy split detection of the compact eigensolver must still converge to the right answer."""
+    rs = np.random.RandomState(n)
+    C, B = 6, 40
+    ctrl = orc.synthetic_controllers(C, n, seed=5)
+    nrm = rs.standard_normal((1, C, B, 2 * n))
+    sigma = 0.5
+    for b in range(B):
+        site = 1 + (b % (n - 1))                   # coupling between site-1 and site
+        nrm[0, :, b, 2 * site + 1] = -1.0 / sigma if b % 3 else (-1.0 + 1e-17) / sigma
+    f = rb.engine.fidelity_mc(ctrl, [sigma], B, n, 0, n - 1, model=rb._lib.MODEL_REAL2, replay=nrm).cpu().numpy()
+    ref = orc.fidelity_mc_replay(ctrl, [sigma], nrm, n, 0, n - 1, model=orc.MODEL_REAL2)
+    assert np.abs(f - ref).max() < FID_TOL
+    i, o = 1, n - 2                                 # in/out inside different blocks or the same block
+    f2 = rb.engine.fidelity_mc(ctrl, [sigma], B, n, i, o, model=rb._lib.MODEL_REAL2, replay=nrm).cpu().numpy()
+    ref2 = orc.fidelity_mc_replay(ctrl, [sigma], nrm, n, i, o, model=orc.MODEL_REAL2)
+    assert np.abs(f2 - ref2).max() < FID_TOL
