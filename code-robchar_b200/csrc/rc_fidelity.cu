@@ -48,9 +48,12 @@ static fused_launch_fn fused_table[REG_MAX_N + 1] = {
     launch_fused_reg_11, launch_fused_reg_12, launch_fused_reg_13, launch_fused_reg_14, launch_fused_reg_15,
     launch_fused_reg_16};
 
+// CTA size of the shared-memory kernels: 128 lanes while four [N][128] arrays leave room for >= 4 CTAs/SM
+static int smem_threads(int n) { return (size_t)4 * n * 128 * sizeof(double) <= 56 * 1024 ? 128 : 64; }
+
 template <int MODEL, bool REPLAY>
 static cudaError_t launch_smem(const FidArgs& a, int sm_count, cudaStream_t st) {
-    const int threads = 64;
+    const int threads = smem_threads(a.N);
     size_t smem = (size_t)4 * a.N * threads * sizeof(double);
     auto kern = fidelity_smem_kernel<MODEL, REPLAY>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -73,7 +76,7 @@ static int reg_crossover() {
     static int v = -1;
     if (v < 0) {
         const char* s = getenv("RC_REG_MAX_N");
-        v = s ? atoi(s) : REG_MAX_N;
+        v = s ? atoi(s) : REG_DEFAULT_N;
         if (v > REG_MAX_N) v = REG_MAX_N;
         if (v < 1) v = 1;
     }
@@ -91,7 +94,7 @@ cudaError_t launch_fidelity(const FidArgs& a, cudaStream_t st) {
 
 template <int MODEL, bool REPLAY>
 static cudaError_t launch_fused_smem(const FusedArgs& g, int sm_count, cudaStream_t st) {
-    const int threads = 64;
+    const int threads = smem_threads(g.f.N);
     size_t smem = (size_t)4 * g.f.N * threads * sizeof(double);
     auto kern = fidelity_stats_smem_kernel<MODEL, REPLAY>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -119,7 +122,7 @@ cudaError_t launch_fused(const FusedArgs& g, cudaStream_t st) {
 
 // chunking of the draw axis for the fused path: multiples of the CTA size, <= 4096 draws per item
 static void fused_chunking(int nspin, long long B, long long* chunk, long long* nchunks) {
-    const long long threads = nspin <= reg_crossover() ? 128 : 64;
+    const long long threads = nspin <= reg_crossover() ? 128 : smem_threads(nspin);
     long long ch = 4096;
     if (B < ch) ch = (B + threads - 1) / threads * threads;
     if (ch < threads) ch = threads;

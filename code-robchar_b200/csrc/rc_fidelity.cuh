@@ -14,7 +14,8 @@ namespace rc {
 
 constexpr int MODEL_COMPLEX3 = 0;  // noise_model.py:122-147: (z_ii, nn_i, nn2_i) per site
 constexpr int MODEL_REAL2 = 1;     // qnewton.py:366-379:     (z_ii, nn_i) per site
-constexpr int REG_MAX_N = 16;      // register-resident eigensolver up to here, shared memory above
+constexpr int REG_MAX_N = 16;      // register-resident eigensolver compiled up to here
+constexpr int REG_DEFAULT_N = 8;   // measured crossover on B200: registers win for N <= 8, shared memory above
 constexpr int MAX_N = 32;
 
 struct FidArgs {
@@ -265,6 +266,9 @@ __global__ void __launch_bounds__(128) fidelity_stats_reg_kernel(FusedArgs g) {
 // ---------------------------------------------------------------------------------------------
 // Shared-memory kernel for REG_MAX_N < N <= MAX_N: each lane owns a column of four [N] arrays.
 // ---------------------------------------------------------------------------------------------
+// One evaluation with the four [N] arrays in shared memory (column = this lane, stride blockDim).
+// Raw standard normals are first parked in the arrays themselves (d <- z_ii, e <- nn, zi <- nn2) by a
+// non-unrolled Philox pair loop (or read from the replay row), then transformed in place.
 template <int MODEL, bool REPLAY>
 __device__ __forceinline__ double eval_smem(const FidArgs& a, long long s, long long c, long long b,
                                             const double* row /* global replay row */, double* sm) {
@@ -276,28 +280,46 @@ __device__ __forceinline__ double eval_smem(const FidArgs& a, long long s, long 
     constexpr int P = draws_per_site(MODEL);
     const double* x = a.ctrl + c * (n + 1);
     const double sigma = __ldg(a.sigma + s);
-    const uint64_t cg = (uint64_t)(c + a.c_offset), bg = (uint64_t)(b + a.b_offset);
-    double zc[2] = {0.0, 0.0};  // current Philox pair
-    int have = -1;
-    auto get = [&](int j) -> double {
-        if (REPLAY) return __ldg(row + j);
-        int jc = j == 0 ? 0 : j - (P - 1);  // compact index
-        int p = jc >> 1;
-        if (p != have) { normal_pair(a.seed_lo, a.seed_hi, (uint32_t)s, cg, bg, p, zc[0], zc[1]); have = p; }
-        return zc[jc & 1];
-    };
+    if (REPLAY) {
+        for (int i = 0; i < n; ++i) {
+            d[(size_t)i * ld] = __ldg(row + P * i);
+            if (i >= 1) {
+                e[(size_t)(i - 1) * ld] = __ldg(row + P * i + 1);
+                if (MODEL == MODEL_COMPLEX3) zi[(size_t)i * ld] = __ldg(row + P * i + 2);
+            }
+        }
+    } else {
+        const uint64_t cg = (uint64_t)(c + a.c_offset), bg = (uint64_t)(b + a.b_offset);
+        const int nc = P * n - (P - 1);  // compact draw count
+#pragma unroll 1
+        for (int p = 0; p < (nc + 1) / 2; ++p) {
+            double z[2];
+            normal_pair(a.seed_lo, a.seed_hi, (uint32_t)s, cg, bg, (uint32_t)p, z[0], z[1]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int jc = 2 * p + h;  // compact index: 0 -> z_00, then (z_ii, nn_i[, nn2_i]) for i >= 1
+                if (jc < nc) {
+                    const int site = jc == 0 ? 0 : 1 + (jc - 1) / P, kind = jc == 0 ? 0 : (jc - 1) % P;
+                    double* dst = kind == 0 ? d + (size_t)site * ld : (kind == 1 ? e + (size_t)(site - 1) * ld : zi + (size_t)site * ld);
+                    *dst = z[h];
+                }
+            }
+        }
+    }
     for (int i = 0; i < n; ++i) {
-        double base = a.zz ? zz_diag(i, n) : 0.0;
-        d[(size_t)i * ld] = __dadd_rn(__dadd_rn(base, __dmul_rn(sigma, get(P * i))), __ldg(x + i));
+        const double base = a.zz ? zz_diag(i, n) : 0.0;
+        d[(size_t)i * ld] = __dadd_rn(__dadd_rn(base, __dmul_rn(sigma, d[(size_t)i * ld])), __ldg(x + i));
         if (i >= 1) {
-            double aa = __dadd_rn(1.0, __dmul_rn(sigma, get(P * i + 1)));
+            const double aa = __dadd_rn(1.0, __dmul_rn(sigma, e[(size_t)(i - 1) * ld]));
             if (MODEL == MODEL_COMPLEX3) {
-                double bb = __dmul_rn(sigma, get(P * i + 2));
+                const double bb = __dmul_rn(sigma, zi[(size_t)i * ld]);
                 e[(size_t)(i - 1) * ld] = rc_sqrt(fma(aa, aa, bb * bb));
             } else {
                 e[(size_t)(i - 1) * ld] = aa;
             }
         }
+    }
+    for (int i = 0; i < n; ++i) {
         zi[(size_t)i * ld] = (i == a.in) ? 1.0 : 0.0;
         zo[(size_t)i * ld] = (i == a.out) ? 1.0 : 0.0;
     }
@@ -308,7 +330,7 @@ __device__ __forceinline__ double eval_smem(const FidArgs& a, long long s, long 
 }
 
 template <int MODEL, bool REPLAY>
-__global__ void __launch_bounds__(64) fidelity_smem_kernel(FidArgs a) {
+__global__ void __launch_bounds__(128) fidelity_smem_kernel(FidArgs a) {
     extern __shared__ double sm[];
     const long long K = (long long)draws_per_site(MODEL) * a.N;
     const long long total = (long long)a.S * a.C * a.B;
@@ -320,9 +342,9 @@ __global__ void __launch_bounds__(64) fidelity_smem_kernel(FidArgs a) {
 }
 
 template <int MODEL, bool REPLAY>
-__global__ void __launch_bounds__(64) fidelity_stats_smem_kernel(FusedArgs g) {
+__global__ void __launch_bounds__(128) fidelity_stats_smem_kernel(FusedArgs g) {
     extern __shared__ double sm[];
-    __shared__ double scratch[2 * PART_DOUBLES];
+    __shared__ double scratch[4 * PART_DOUBLES];
     const FidArgs& a = g.f;
     const long long K = (long long)draws_per_site(MODEL) * a.N;
     const long long nseg = (long long)a.S * a.C;

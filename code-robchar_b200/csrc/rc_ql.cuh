@@ -288,12 +288,14 @@ RC_HD double fidelity_strided(double* d, double* e, double* zi, double* zo, int 
     }
     if (!(fabs(chk) <= DBL_MAX)) { *fail = 0; return NAN; }
     const double tol = DBL_EPSILON * anorm;
+    const int tolhi = threshold_hi(tol);
+    const double tiny = fmin(tol, 1e-280);
     int bad = 0;
     for (int l = 0; l < n - 1; ++l) {
         int it = 0;
         while (true) {
             int m = l;
-            while (m < n - 1 && !(fabs(AT(e, m)) <= tol)) ++m;
+            while (m < n - 1 && !negligible_hi(AT(e, m), tolhi)) ++m;
             if (m == l) break;
             if (++it > QL_MAX_SWEEPS) { bad = 1; break; }
             double g = wilkinson_g(AT(d, l), AT(d, l + 1), AT(e, l), AT(d, m));
@@ -303,14 +305,12 @@ RC_HD double fidelity_strided(double* d, double* e, double* zi, double* zo, int 
             for (int i = m - 1; i >= l; --i) {
                 double ei = AT(e, i), di = AT(d, i), zii = AT(zi, i), zoi = AT(zo, i);
                 double f = s * ei, b = c * ei;
-                double h = f * f + g * g;
+                double h = fma(f, f, fma(g, g, tiny));
                 double rinv = rc_rsqrt(h);
                 r = h * rinv;
-                bool okh = h > 0.0;
-                if (!okh) { rinv = 0.0; r = 0.0; }
                 AT(e, i + 1) = r;
                 s = f * rinv;
-                c = okh ? g * rinv : 1.0;
+                c = g * rinv;
                 g = d_up - p;
                 r = (di - g) * s + 2.0 * c * b;
                 p = s * r;
@@ -335,7 +335,7 @@ RC_HD double fidelity_strided(double* d, double* e, double* zi, double* zo, int 
     double re = 0.0, im = 0.0;
     for (int k = 0; k < n; ++k) {
         double sn, cs;
-        sincos(AT(d, k) * T, &sn, &cs);
+        rc_sincos(AT(d, k) * T, &sn, &cs);
         double w = AT(zo, k) * AT(zi, k);
         re = fma(w, cs, re);
         im = fma(-w, sn, im);
