@@ -120,6 +120,7 @@ template <int E>
 __global__ void __launch_bounds__(128) sort_stats_warp_kernel(const double* __restrict__ fids, long long nseg, int B,
                                                               double eps, double* __restrict__ stats, double* sorted_out,
                                                               unsigned long long* illegal) {
+    __shared__ unsigned long long srow[4 * 32 * E];
     const int lane = threadIdx.x & 31;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -131,35 +132,42 @@ __global__ void __launch_bounds__(128) sort_stats_warp_kernel(const double* __re
             const int g = j * 32 + lane;
             v[j] = g < B ? f2key(__ldcs(src + g)) : ~0ull;
         }
-        // bitonic sort, ascending in g
+        // bitonic sort, ascending in g.  Shuffle stages (distance < 32) run as rolled loops with
+        // runtime (k, dist) — one copy in the instruction stream; only the register-exchange stages
+        // (distance >= 32, compile-time register indices) are unrolled.
+        auto shuffle_stage = [&](int k, int dist) {
 #pragma unroll
-        for (int k = 2; k <= 32 * E; k <<= 1) {
+            for (int j = 0; j < E; ++j) {
+                const unsigned long long a = v[j];
+                const unsigned long long b = __shfl_xor_sync(0xffffffffu, a, dist);
+                const bool up = (((j * 32 + lane) & k) == 0);
+                const bool lower = (lane & dist) == 0;
+                v[j] = ((a < b) == (lower == up)) ? a : b;
+            }
+        };
+#pragma unroll 1
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll 1
+            for (int dist = k >> 1; dist > 0; dist >>= 1) shuffle_stage(k, dist);
+        }
 #pragma unroll
-            for (int dist = k >> 1; dist > 0; dist >>= 1) {
-                if (dist >= 32) {
-                    const int dj = dist >> 5;
+        for (int k = 64; k <= 32 * E; k <<= 1) {
 #pragma unroll
-                    for (int j = 0; j < E; ++j) {
-                        if ((j & dj) == 0) {
-                            const bool up = ((j * 32) & k) == 0;  // k >= 64 here: direction depends on j only
-                            const unsigned long long a = v[j], b = v[j | dj];
-                            const bool sw = (a > b) == up;
-                            v[j] = sw ? b : a;
-                            v[j | dj] = sw ? a : b;
-                        }
-                    }
-                } else {
+            for (int dist = k >> 1; dist >= 32; dist >>= 1) {
+                const int dj = dist >> 5;
 #pragma unroll
-                    for (int j = 0; j < E; ++j) {
-                        const unsigned long long a = v[j];
-                        const unsigned long long b = __shfl_xor_sync(0xffffffffu, a, dist);
-                        const bool up = (((j * 32 + lane) & k) == 0);
-                        const bool lower = (lane & dist) == 0;
-                        const bool take_min = (lower == up);
-                        v[j] = ((a < b) == take_min) ? a : b;
+                for (int j = 0; j < E; ++j) {
+                    if ((j & dj) == 0) {
+                        const bool up = ((j * 32) & k) == 0;  // k >= 64: direction depends on j only
+                        const unsigned long long a = v[j], b = v[j | dj];
+                        const bool sw = (a > b) == up;
+                        v[j] = sw ? b : a;
+                        v[j | dj] = sw ? a : b;
                     }
                 }
             }
+#pragma unroll 1
+            for (int dist = 16; dist > 0; dist >>= 1) shuffle_stage(k, dist);
         }
         if (sorted_out) {
             double* dst = sorted_out + seg * (long long)B;
@@ -169,44 +177,49 @@ __global__ void __launch_bounds__(128) sort_stats_warp_kernel(const double* __re
                 if (g < B) dst[g] = key2f(v[j]);
             }
         }
-        // statistics (same arithmetic as sorted_segment_stats)
-        double acc[12];
+        // park the sorted keys in this warp's shared-memory row so the statistics run as rolled loops
+        // over elements (one copy of the clip / accumulate code in the instruction stream)
+        unsigned long long* row = srow + (size_t)(threadIdx.x >> 5) * (32 * E);
+        __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+        for (int j = 0; j < E; ++j) row[j * 32 + lane] = v[j];
+        __syncwarp();
+        // statistics (same arithmetic as sorted_segment_stats; threshold counts by ballot + popc)
+        double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        int cnt[6] = {0, 0, 0, 0, 0, 0};
         unsigned bad = 0;
+#pragma unroll 1
+        for (int g0 = 0; g0 < B; g0 += 32) {
+            const int g = g0 + lane;
+            const bool in = g < B;
+            const bool last = (g + 1 >= B);
+            const double f = in ? key2f(row[g]) : 0.0;
+            const double fn = (in && !last) ? key2f(row[g + 1]) : 1.0;
+            const double cdf = (double)(g + 1) / (double)B;
+            const double vv[3] = {f, clip01(f - eps), clip01(f + eps)};
+            const double vn[3] = {fn, last ? 1.0 : clip01(fn - eps), last ? 1.0 : clip01(fn + eps)};
 #pragma unroll
-        for (int j = 0; j < E; ++j) {
-            const int g = j * 32 + lane;
-            const double f = key2f(v[j]);
-            double fn = __shfl_down_sync(0xffffffffu, f, 1);
-            const double f_first_next = (j + 1 < E) ? __shfl_sync(0xffffffffu, key2f(v[j + 1 < E ? j + 1 : j]), 0) : 1.0;
-            if (lane == 31) fn = f_first_next;
-            if (g < B) {
-                const bool last = (g + 1 >= B);
-                const double cdf = (double)(g + 1) / (double)B;
-                const double vv[3] = {f, clip01(f - eps), clip01(f + eps)};
-                const double vn[3] = {last ? 1.0 : fn, last ? 1.0 : clip01(fn - eps), last ? 1.0 : clip01(fn + eps)};
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
+            for (int k = 0; k < 3; ++k) {
+                if (in) {
                     acc[k] += (vn[k] - vv[k]) * cdf;
                     acc[3 + k] += vv[k];
-                    acc[6 + k] += (vv[k] >= 0.95) ? 1.0 : 0.0;
-                    acc[9 + k] += (vv[k] >= 0.98) ? 1.0 : 0.0;
                 }
-                if (fabs(f - 1e-8) > 1.0) ++bad;
+                cnt[k] += __popc(__ballot_sync(0xffffffffu, in && vv[k] >= 0.95));
+                cnt[3 + k] += __popc(__ballot_sync(0xffffffffu, in && vv[k] >= 0.98));
             }
+            if (in && fabs(f - 1e-8) > 1.0) ++bad;
         }
 #pragma unroll
-        for (int k = 0; k < 12; ++k) acc[k] = warp_sum(acc[k]);
+        for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);
         bad = __reduce_add_sync(0xffffffffu, bad);
         if (bad && illegal && lane == 0) atomicAdd(illegal, (unsigned long long)bad);
         double m2[3] = {0.0, 0.0, 0.0};
         const double mean[3] = {acc[3] / (double)B, acc[4] / (double)B, acc[5] / (double)B};
-#pragma unroll
-        for (int j = 0; j < E; ++j) {
-            const int g = j * 32 + lane;
+#pragma unroll 1
+        for (int g0 = 0; g0 < B; g0 += 32) {
+            const int g = g0 + lane;
             if (g < B) {
-                const double f = key2f(v[j]);
+                const double f = key2f(row[g]);
                 const double vv[3] = {f, clip01(f - eps), clip01(f + eps)};
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -222,8 +235,8 @@ __global__ void __launch_bounds__(128) sort_stats_warp_kernel(const double* __re
             const int k = lane;
             const double mn = k == 0 ? f0 : (k == 1 ? clip01(f0 - eps) : clip01(f0 + eps));
             const double a0 = k == 0 ? acc[0] : (k == 1 ? acc[1] : acc[2]);
-            const double a6 = k == 0 ? acc[6] : (k == 1 ? acc[7] : acc[8]);
-            const double a9 = k == 0 ? acc[9] : (k == 1 ? acc[10] : acc[11]);
+            const double a6 = (double)(k == 0 ? cnt[0] : (k == 1 ? cnt[1] : cnt[2]));
+            const double a9 = (double)(k == 0 ? cnt[3] : (k == 1 ? cnt[4] : cnt[5]));
             const double mm = k == 0 ? m2[0] : (k == 1 ? m2[1] : m2[2]);
             stats[(0 + k) * nseg + seg] = a0;
             stats[(3 + k) * nseg + seg] = -1.0 * (a6 / (double)B);
