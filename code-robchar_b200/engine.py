@@ -330,6 +330,39 @@ def robustness_sweep_host(ctrl: np.ndarray, sigmas: np.ndarray, B: int, nspin: i
     return st, tau, sel
 
 
+def expm_batch(A) -> torch.Tensor:
+    """expm of a batch of dense complex matrices [batch][M][M] (M <= 32) on the device (Pade-13 scaling and
+    squaring): the generality path for non-tridiagonal / non-Hermitian Hamiltonians."""
+    dev = require_cuda()
+    if not isinstance(A, torch.Tensor):
+        A = torch.as_tensor(np.asarray(A, dtype=np.complex128))
+    A = A.to(device=dev, dtype=torch.complex128).contiguous()
+    if A.dim() == 2:
+        A = A[None]
+    batch, M, M2 = A.shape
+    if M != M2:
+        raise ValueError("square matrices expected")
+    out = torch.empty_like(A)
+    check(lib().rc_expm_batch(_ptr(A), batch, M, _ptr(out), _stream()))
+    _count(1)
+    return out
+
+
+def dense_fidelity(H, T, inspin: int, outspin: int) -> torch.Tensor:
+    """|expm(-1j*T*H)[out, in]|^2 for a batch of dense complex Hamiltonians [batch][N][N] and times [batch]
+    (noise_model.py:105-109 verbatim, for Hamiltonians outside the tridiagonal fast path)."""
+    dev = require_cuda()
+    H = torch.as_tensor(np.asarray(H, dtype=np.complex128)) if not isinstance(H, torch.Tensor) else H
+    H = H.to(device=dev, dtype=torch.complex128)
+    if H.dim() == 2:
+        H = H[None]
+    Tt = torch.as_tensor(np.abs(np.asarray(T, dtype=np.float64)).reshape(-1)) if not isinstance(T, torch.Tensor) else T.abs().reshape(-1)
+    Tt = Tt.to(device=dev, dtype=torch.float64)
+    U = expm_batch(-1j * Tt[:, None, None] * H)
+    phi = U[:, outspin, inspin]
+    return phi.real * phi.real + phi.imag * phi.imag
+
+
 def fp64_peak_tflops() -> float:
     require_cuda()
     v = C.c_double(0.0)

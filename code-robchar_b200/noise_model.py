@@ -62,24 +62,34 @@ class noise_model_base:
     def evaluate_noisy_fidelity(self, x, ham_noisy: bool = False):
         """noise_model.py:98-109.  The perturbation is drawn on the host by ``self.perturbation()``
         (same generator calls, same order as upstream); the evolution runs on the GPU."""
-        if self.topo != "chain":
-            raise NotImplementedError("only topo='chain' is on the GPU path (ring couples sites 0 and N-1)")
         n = self.Nspin
-        row = np.zeros(3 * n)
-        if ham_noisy:
-            z = np.asarray(self.perturbation())
-            row = self._replay_row_from_matrix(z)
-        xa = np.asarray(x, dtype=np.float64).reshape(1, n + 1)
-        f = engine.fidelity_mc(xa, np.ones(1), 1, n, self.inspin, self.outspin, model=MODEL_COMPLEX3, zz=self.zz,
-                               replay=row.reshape(1, 1, 1, 3 * n))
-        return float(f.reshape(-1)[0].item())
+        z = np.asarray(self.perturbation()) if ham_noisy else None
+        if self.topo == "chain" and (z is None or self._is_hermitian_tridiagonal(z)):
+            row = self._replay_row_from_matrix(z) if z is not None else np.zeros(3 * n)
+            xa = np.asarray(x, dtype=np.float64).reshape(1, n + 1)
+            f = engine.fidelity_mc(xa, np.ones(1), 1, n, self.inspin, self.outspin, model=MODEL_COMPLEX3, zz=self.zz,
+                                   replay=row.reshape(1, 1, 1, 3 * n))
+            return float(f.reshape(-1)[0].item())
+        # generality path (ring topology, non-tridiagonal or non-Hermitian perturbations such as
+        # directional_perturbation's complex diagonal entries): dense expm on the device
+        H = self.HH.copy()
+        if self.zz:
+            H = H + np.diag(0.5 * np.triu(self.HH).sum().sum() * np.ones(n) - np.sum(self.HH, axis=1))
+        if z is not None:
+            H = H + z
+        H = H + np.diag(np.asarray(x[:n], dtype=np.float64))
+        return float(engine.dense_fidelity(H, abs(x[n]), self.inspin, self.outspin)[0].item())
+
+    def _is_hermitian_tridiagonal(self, z: np.ndarray) -> bool:
+        n = self.Nspin
+        band = np.abs(np.subtract.outer(np.arange(n), np.arange(n))) <= 1
+        return (not np.any(z[~band] != 0)) and np.array_equal(z, z.conj().T) and not np.any(np.diag(z).imag != 0)
 
     def _replay_row_from_matrix(self, z: np.ndarray) -> np.ndarray:
         """Pack a Hermitian tridiagonal perturbation matrix into one replay row (sigma = 1)."""
         n = self.Nspin
-        band = np.abs(np.subtract.outer(np.arange(n), np.arange(n))) <= 1
-        if np.any(z[~band] != 0) or not np.allclose(z, z.conj().T, rtol=0, atol=0) or np.any(np.diag(z).imag != 0):
-            raise NotImplementedError("GPU path needs a Hermitian tridiagonal perturbation")
+        if not self._is_hermitian_tridiagonal(z):
+            raise NotImplementedError("the eigensolver fast path needs a Hermitian tridiagonal perturbation")
         row = np.zeros(3 * n)
         row[0::3] = np.diag(z).real
         lo = np.diag(z, -1)  # z[i, i-1] = nn + 1j*nn2

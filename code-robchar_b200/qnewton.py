@@ -23,9 +23,7 @@ class LBFGS(object):
                  topo="linear", noisy=False, fid_noisy=False, draws=10, ham_noisy=False, verbose=False, adp_tol=0.05,
                  adaptive=False, noise=0.05, use_wass_cost=False, heisenberg_int: bool = False,
                  use_fixed_ham: bool = False, opt_train_size: int = 100, opt_test_size: int = 10000, **_ignored):
-        if topo == "ring":
-            raise NotImplementedError("only the open chain is on the GPU path")
-        self.topo = topo
+        self.topo = topo  # "ring" closes the chain (qnewton.py:145-147): evaluated on the dense-expm device path
         self.heisenberg_int = heisenberg_int
         self.Nspin, self.In, self.Out = nspin, in_spin, out_spin
         self.Tmin, self.Tmax, self.Bmin, self.Bmax = 0, max_time, bmin, bmax
@@ -55,6 +53,9 @@ class LBFGS(object):
         for l in range(1, n):
             HH[l - 1, l] = 1
             HH[l, l - 1] = 1
+        if self.topo == "ring":
+            HH[n - 1, 0] = 1
+            HH[0, n - 1] = 1
         if self.heisenberg_int:
             t = 0.5 * np.triu(HH).sum().sum() * np.ones(n) - np.sum(HH, axis=1)
             HH += np.diag(t)
@@ -106,8 +107,49 @@ class LBFGS(object):
     def _eval_rows(self, x, rows: np.ndarray) -> torch.Tensor:
         xa = np.asarray(x, dtype=np.float64).reshape(1, self.Nspin + 1)
         m = rows.shape[0]
+        if self.topo == "ring":  # not tridiagonal: dense expm path on explicit Hamiltonians
+            n = self.Nspin
+            H = np.broadcast_to(self.HH, (m, n, n)).copy()
+            idx = np.arange(n)
+            H[:, idx, idx] += rows[:, 0::2] + xa[0, :n]
+            lo = np.arange(1, n)
+            H[:, lo, lo - 1] += rows[:, 3::2]
+            H[:, lo - 1, lo] += rows[:, 3::2]
+            return engine.dense_fidelity(H, np.full(m, abs(xa[0, n])), self.In, self.Out)
         return engine.fidelity_mc(xa, np.ones(1), m, self.Nspin, self.In, self.Out, model=MODEL_REAL2,
                                   zz=self.heisenberg_int, replay=rows.reshape(1, 1, m, 2 * self.Nspin)).reshape(-1)
+
+    def eval_static_fidelity_gradient(self, x):
+        """qnewton.py:162-212: infidelity and its gradient w.r.t. biases and time.  Same construction as
+        upstream — N block exponentials expm([[TH, 0], [-iT C_l, TH]]) for the bias derivatives and H U for the
+        time derivative — with all N+1 matrix exponentials evaluated on the device (rc_expm_batch)."""
+        n = self.Nspin
+        if 2 * n > 32:
+            raise NotImplementedError("gradient path supports Nspin <= 16 (2N x 2N block exponentials)")
+        T = abs(x[n])
+        H = self.HH.copy()
+        for l in range(n):
+            H += x[l] * self.CC[l]
+        if self.ham_noisy:
+            H += self.structured_perturabation()
+        TH = -1j * T * H
+        A = np.zeros((n, 2 * n, 2 * n), dtype=np.complex128)
+        A[:, 0:n, 0:n] = TH
+        A[:, n:2 * n, n:2 * n] = TH
+        for l in range(n):
+            A[l, n:2 * n, 0:n] = -1j * T * self.CC[l]
+        PSI = engine.expm_batch(A).cpu().numpy()
+        U = PSI[0, 0:n, 0:n]
+        HU = np.dot(H, U)
+        grad = np.zeros(n + 1)
+        phi = U[self.Out, self.In]
+        err = (1 - (phi.real * phi.real + phi.imag * phi.imag))
+        for l in range(n):
+            z = PSI[l, n:2 * n, 0:n][self.Out, self.In] * phi.conjugate()
+            grad[l] -= 2 * z.real
+        z = HU[self.Out, self.In] * phi.conjugate()
+        grad[n] -= 2 * z.imag
+        return err, grad
 
     # ---- objectives -------------------------------------------------------------------------------------
     def _shot_noise(self, fid):

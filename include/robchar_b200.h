@@ -149,6 +149,14 @@ int rc_robustness_sweep_host(const double* ctrl_host, int64_t C, int nspin, int 
                              int64_t topk, double alpha_cluster, double* stats_host, double* tau_host,
                              int64_t* sel_host, void* stream);
 
+/* Dense complex matrix exponential of `batch` M x M matrices (M <= 32), interleaved (re, im) float64,
+ * row-major: out = expm(A).  The generality path behind the reference's scipy.linalg.expm calls whose
+ * argument is not Hermitian tridiagonal: topo="ring" (noise_model.py:83-85), the complex diagonal
+ * entries of directional_perturbation (noise_model.py:196-199), arbitrary perturbation() overrides
+ * and the 2N x 2N block matrices of the analytic gradient (qnewton.py:186-196).
+ * Scaling and squaring with the [13/13] Pade approximant; NaN/Inf input gives NaN output. */
+int rc_expm_batch(const double* A_dev, int64_t batch, int M, double* out_dev, void* stream);
+
 /* FP64 FMA throughput micro-benchmark of the current device (TFLOP/s, 2 flops per DFMA); used as
  * the roofline denominator of the evolution kernel. */
 int rc_fp64_peak_tflops(double* tflops, void* stream);

@@ -301,6 +301,39 @@ def make_objective_and_arim():
     print("objective_arim done")
 
 
+def make_dense_path():
+    """Reference outputs for the generality path: analytic gradient (qnewton.py:162-212), ring topology
+    (noise_model.py:83-85) and directional_perturbation incl. its complex-diagonal draws (:150-201)."""
+    import qnewton as ref_q
+    out = {}
+    env = ref_q.LBFGS(5, 0, 4, noise=0.05, opt_train_size=2)
+    rs = np.random.RandomState(31)
+    X = np.concatenate([rs.uniform(-10, 10, (3, 5)), rs.uniform(1, 30, (3, 1))], axis=1)
+    out["grad_X"] = X
+    eg = [env.eval_static_fidelity_gradient(x) for x in X]
+    out["grad_err"] = np.array([e for e, g in eg]); out["grad_g"] = np.array([g for e, g in eg])
+    ring = ref_nm.structured_perturbation(Nspin=6, inspin=0, outspin=3, noise=0.05, topo="ring")
+    Xr = np.concatenate([rs.uniform(-10, 10, (4, 6)), rs.uniform(1, 30, (4, 1))], axis=1)
+    out["ring_X"] = Xr
+    out["ring_nominal"] = np.array([ring.evaluate_noisy_fidelity(x, False) for x in Xr])
+    np.random.seed(41)
+    out["ring_noisy"] = np.array([ring.evaluate_noisy_fidelity(x, True) for x in Xr])
+    dp = ref_nm.directional_perturbation(Nspin=5, inspin=0, outspin=4, noise=0.1)
+    Xd = np.concatenate([rs.uniform(-10, 10, (1, 5)), rs.uniform(1, 30, (1, 1))], axis=1)[0]
+    out["dir_x"] = Xd
+    np.random.seed(42)
+    out["dir_noisy"] = np.array([dp.evaluate_noisy_fidelity(Xd, True) for _ in range(40)])
+    rs2 = np.random.RandomState(9)
+    mats = []
+    for M in (2, 5, 14, 32):
+        A = (rs2.standard_normal((3, M, M)) + 1j * rs2.standard_normal((3, M, M))) * np.array([0.01, 1.0, 20.0])[:, None, None] / np.sqrt(M)
+        out[f"expm_A{M}"] = A
+        import scipy.linalg
+        out[f"expm_E{M}"] = np.array([scipy.linalg.expm(a) for a in A])
+    np.savez_compressed(f"{OUT}/dense_path.npz", **out)
+    print("dense_path done")
+
+
 if __name__ == "__main__":
     make_kat_bestfid()
     make_kat_mc_zero()
@@ -310,3 +343,4 @@ if __name__ == "__main__":
     make_real2_and_zz()
     make_large_n()
     make_objective_and_arim()
+    make_dense_path()

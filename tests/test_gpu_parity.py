@@ -499,3 +499,34 @@ def test_split_matrices_zero_and_tiny_couplings(rb, n):
     f2 = rb.engine.fidelity_mc(ctrl, [sigma], B, n, i, o, model=rb._lib.MODEL_REAL2, replay=nrm).cpu().numpy()
     ref2 = orc.fidelity_mc_replay(ctrl, [sigma], nrm, n, i, o, model=orc.MODEL_REAL2)
     assert np.abs(f2 - ref2).max() < FID_TOL
+
+
+def test_dense_expm_generality_path(rb):
+    """rc_expm_batch vs scipy.linalg.expm; ring topology, directional perturbation (incl. its non-Hermitian
+    complex-diagonal draws) and the analytic gradient vs the unmodified reference."""
+    g = load_golden("dense_path.npz")
+    for M in (2, 5, 14, 32):
+        E = rb.engine.expm_batch(g[f"expm_A{M}"]).cpu().numpy()
+        ref = g[f"expm_E{M}"]
+        assert np.abs(E - ref).max() / max(1.0, np.abs(ref).max()) < 1e-12, M
+    bad = np.full((1, 3, 3), np.nan, dtype=np.complex128)
+    assert np.isnan(rb.engine.expm_batch(bad).cpu().numpy()).all()
+    ring = rb.structured_perturbation(Nspin=6, inspin=0, outspin=3, noise=0.05, topo="ring")
+    Xr = g["ring_X"]
+    assert np.abs(np.array([ring.evaluate_noisy_fidelity(x, False) for x in Xr]) - g["ring_nominal"]).max() < FID_TOL
+    np.random.seed(41)
+    assert np.abs(np.array([ring.evaluate_noisy_fidelity(x, True) for x in Xr]) - g["ring_noisy"]).max() < FID_TOL
+    dp = rb.directional_perturbation(Nspin=5, inspin=0, outspin=4, noise=0.1)
+    np.random.seed(42)
+    got = np.array([dp.evaluate_noisy_fidelity(g["dir_x"], True) for _ in range(40)])
+    assert np.abs(got - g["dir_noisy"]).max() < FID_TOL
+    env = rb.qnewton.LBFGS(5, 0, 4, noise=0.05, opt_train_size=2, opt_test_size=2)
+    for k, x in enumerate(g["grad_X"]):
+        err, grad = env.eval_static_fidelity_gradient(x)
+        assert abs(err - g["grad_err"][k]) < FID_TOL
+        assert np.abs(grad - g["grad_g"][k]).max() < 1e-9
+    rq = rb.qnewton.LBFGS(5, 0, 2, topo="ring", opt_train_size=3, opt_test_size=2)
+    x = g["grad_X"][0]
+    H = rq.HH + np.diag(x[:5])
+    assert abs(rq.fidelity_ss(x) - float(rb.engine.dense_fidelity(H, x[5], 0, 2)[0])) < 1e-14
+    assert abs(rq.fidelity_ss_av(x, reps=3) - np.mean([float(rb.engine.dense_fidelity(h + np.diag(x[:5]), x[5], 0, 2)[0]) for h in rq.randH])) < 1e-13

@@ -100,8 +100,6 @@ def test_structured_perturbation_draw_order_matches_reference_port():
         m._replay_row_from_matrix(bad)
     ring = rb.structured_perturbation(Nspin=4, topo="ring")
     assert ring.HH[3, 0] == 1 and ring.HH[0, 3] == 1
-    with pytest.raises(NotImplementedError):
-        ring.evaluate_noisy_fidelity(np.zeros(5))
     d = rb.directional_perturbation(Nspin=5, outspin=4)
     assert len(d.directions) == 2 + 3 * 3 + 4
     np.random.seed(1)
