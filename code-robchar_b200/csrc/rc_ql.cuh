@@ -302,25 +302,32 @@ RC_HD double fidelity_strided(double* d, double* e, double* zi, double* zo, int 
             double r;
             double s = 1.0, c = 1.0, p = 0.0;
             double d_up = AT(d, m), zi_up = AT(zi, m), zo_up = AT(zo, m);  // values at i+1
+            // running pointers to position i of each array (one subtraction per array per rotation
+            // instead of an index multiply per access)
+            double* pe = e + (size_t)(m - 1) * ld;
+            double* pd = d + (size_t)(m - 1) * ld;
+            double* pzi = zi + (size_t)(m - 1) * ld;
+            double* pzo = zo + (size_t)(m - 1) * ld;
             for (int i = m - 1; i >= l; --i) {
-                double ei = AT(e, i), di = AT(d, i), zii = AT(zi, i), zoi = AT(zo, i);
+                double ei = *pe, di = *pd, zii = *pzi, zoi = *pzo;
                 double f = s * ei, b = c * ei;
                 double h = fma(f, f, fma(g, g, tiny));
                 double rinv = rc_rsqrt(h);
                 r = h * rinv;
-                AT(e, i + 1) = r;
+                pe[ld] = r;
                 s = f * rinv;
                 c = g * rinv;
                 g = d_up - p;
                 r = (di - g) * s + 2.0 * c * b;
                 p = s * r;
-                AT(d, i + 1) = g + p;
+                pd[ld] = g + p;
                 g = c * r - b;
-                AT(zi, i + 1) = s * zii + c * zi_up;
+                pzi[ld] = s * zii + c * zi_up;
                 zi_up = c * zii - s * zi_up;
-                AT(zo, i + 1) = s * zoi + c * zo_up;
+                pzo[ld] = s * zoi + c * zo_up;
                 zo_up = c * zoi - s * zo_up;
                 d_up = di;
+                pe -= ld; pd -= ld; pzi -= ld; pzo -= ld;
             }
             AT(zi, l) = zi_up;
             AT(zo, l) = zo_up;
