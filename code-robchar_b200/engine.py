@@ -253,7 +253,7 @@ def grouped_rank_consistency(W: torch.Tensor, groups: int, topk: int = 100, alph
     ws = torch.empty(wb, dtype=torch.uint8, device=dev)
     check(lib().rc_rank_consistency(_ptr(W), S, groups, Cg, topk, float(alpha), _ptr(tau), _ptr(sel), _ptr(Wsel),
                                     _ptr(ws), wb, _stream()))
-    _count(10)
+    _count(9)   # 2 argsort, mark, compact, gather, clustered walk, scatter, Kendall count + finalize
     return tau, sel, Wsel
 
 
@@ -326,7 +326,7 @@ def robustness_sweep_host(ctrl: np.ndarray, sigmas: np.ndarray, B: int, nspin: i
                                          C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, float(dkw_eps),
                                          int(bool(fused)), groups, topk, float(alpha_cluster), vp(st), vp(tau), vp(sel),
                                          _stream()))
-    _count(12)
+    _count(11)  # evolution + sort/stats + the 9 ranking kernels
     return st, tau, sel
 
 
