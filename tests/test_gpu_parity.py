@@ -530,3 +530,31 @@ def test_dense_expm_generality_path(rb):
     H = rq.HH + np.diag(x[:5])
     assert abs(rq.fidelity_ss(x) - float(rb.engine.dense_fidelity(H, x[5], 0, 2)[0])) < 1e-14
     assert abs(rq.fidelity_ss_av(x, reps=3) - np.mean([float(rb.engine.dense_fidelity(h + np.diag(x[:5]), x[5], 0, 2)[0]) for h in rq.randH])) < 1e-13
+
+
+def test_parameter_extremes_vs_oracle(rb):
+    """Edge inputs the reference accepts: in == out, T = 0, negative / huge T, huge biases, sigma = 0 and
+    large sigma, single-element shapes."""
+    rs = np.random.RandomState(77)
+    for n in (2, 5, 8, 9, 16):
+        C, B = 8, 5
+        ctrl = orc.synthetic_controllers(C, n, seed=n)
+        ctrl[0, n] = 0.0            # T = 0: identity propagator
+        ctrl[1, n] = -17.5          # abs(T)
+        ctrl[2, n] = 3.0e4          # large time (library sincos path beyond 1e5 rad)
+        ctrl[3, :n] *= 1e3          # huge biases
+        ctrl[4, :n] = 0.0           # uniform chain
+        ctrl[5, :n] = 1e-300        # denormal-ish biases
+        sig = np.array([0.0, 1.0])  # noise comparable to the couplings
+        nrm = rs.standard_normal((2, C, B, 3 * n))
+        for (i, o) in [(0, n - 1), (n // 2, n // 2), (n - 1, 0)]:
+            f = rb.engine.fidelity_mc(ctrl, sig, B, n, i, o, replay=nrm).cpu().numpy()
+            ref = orc.fidelity_mc_replay(ctrl, sig, nrm, n, i, o)
+            tol = np.where(np.arange(C)[None, :, None] == 2, 5e-8, FID_TOL)   # |lambda T| ~ 1e6 rad: eps * 1e6 phase error on both sides
+            tol = np.where(np.arange(C)[None, :, None] == 3, 5e-8, tol)
+            assert (np.abs(f - ref) < tol).all(), (n, i, o, np.abs(f - ref).max(axis=(0, 2)))
+            assert np.abs(f[:, 0] - (1.0 if i == o else 0.0)).max() < 1e-14      # T = 0: sum_k V[o,k] V[i,k] = delta_io
+    one = rb.engine.fidelity_mc(orc.synthetic_controllers(1, 3), [0.05], 1, 3, 0, 2, seed=1)
+    assert one.shape == (1, 1, 1) and 0 <= float(one) <= 1
+    st = rb.engine.stats(one, 0.1).cpu().numpy()
+    assert st.shape == (15, 1, 1) and abs(st[0, 0, 0] - (1 - float(one))) < 1e-15 and st[9, 0, 0] == 0.0
