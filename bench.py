@@ -174,7 +174,7 @@ def workload_config(name, gpus):
     nspin, inspin, outspin, groups, cg, S, B, zz = WORKLOADS[name]
     return {"workload": f"{name}: nspin={nspin} {inspin}->{outspin}, {groups} controller groups x {cg} controllers per GPU, "
                         f"S={S} sigma_sim levels linspace(0,0.1), B={B} draws, complex 3-draw noise model"
-                        f"{', ZZ term on' if zz else ''}; fidelities + 15 statistics + top-100 + Kendall tau per group",
+                        f"{', ZZ term on' if zz else ''}; fidelities + 15 statistics + top-100 + Kendall tau + ARIM with bootstrap error bars per group",
             "nspin": nspin, "controllers_per_gpu": groups * cg, "sigma_levels": S, "draws": B,
             "evals_per_step": S * groups * cg * B * gpus, "noise": "in-kernel Philox4x32-10 + Box-Muller (fp64)",
             "l2": "256 MiB memset between steps (inside the timed region); per-step fidelity tensor "
@@ -225,7 +225,8 @@ def run_ours(args):
             if timed:
                 e1.record(); fid_events.append((e0, e1))
             st = eng.stats(fids, eps, check_legal=False)
-        tau, sel, _ = eng.grouped_rank_consistency(st[0], groups, topk=topk)
+        tau, sel, wsel = eng.grouped_rank_consistency(st[0], groups, topk=topk)
+        arim, arim_std = eng.arim_bootstrap_device(wsel, 100, seed=seed)     # fig-5 ARIM + bootstrap error bar
         if world > 1:
             st = rb.dist.all_gather_stats(st, C_total)
         return st, tau
@@ -269,7 +270,7 @@ def run_ours(args):
     ctrl_pinned = torch.as_tensor(ctrl_np).pin_memory()
     sig_host = np.ascontiguousarray(sig_np)
     h2d = ctrl_np.nbytes + sig_host.nbytes
-    d2h = 15 * S * C_local * 8 + groups * S * S * 8 + groups * topk * 8
+    d2h = 15 * S * C_local * 8 + groups * S * S * 8 + groups * topk * 8 + 2 * groups * S * 8
 
     def e2e_step(seed):
         return rb.rim_analysis.robustness_sweep(ctrl_pinned.numpy(), sig_host, B, nspin, inspin, outspin, groups=groups,

@@ -77,7 +77,8 @@ static int sweep_host_impl(const double* ctrl_host, int64_t C, int nspin, int in
                            const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
                            int64_t c_offset, int64_t b_offset, const double* replay_host, double dkw_eps,
                            int fused, double* fids_host, double* stats_host, int64_t G, int64_t topk,
-                           double alpha_cluster, double* tau_host, int64_t* sel_host, void* stream) {
+                           double alpha_cluster, double* tau_host, int64_t* sel_host, int nboot, double* arim_host,
+                           double* arim_std_host, void* stream) {
     if (nspin < 2 || nspin > RC_MAX_NSPIN) return set_error(RC_ERR_BAD_ARG, "nspin=%d outside [2,%d]", nspin, RC_MAX_NSPIN);
     if (C < 0 || S < 0 || B < 1) return set_error(RC_ERR_BAD_ARG, "sweep: bad sizes C=%lld S=%d B=%lld", (long long)C, S, (long long)B);
     const long long nseg = (long long)S * C, total = nseg * B;
@@ -90,7 +91,7 @@ static int sweep_host_impl(const double* ctrl_host, int64_t C, int nspin, int in
     cudaStream_t st = (cudaStream_t)stream;
     RC_CUDA_TRY(keep_pool_memory());
     const int K = (model == RC_MODEL_COMPLEX3 ? 3 : 2) * nspin;
-    DevBuf ctrl(st), sigma(st), replay(st), fids(st), stats(st), ws(st), counters(st), tau(st), sel(st), wsel(st), rws(st);
+    DevBuf ctrl(st), sigma(st), replay(st), fids(st), stats(st), ws(st), counters(st), tau(st), sel(st), wsel(st), rws(st), ar(st);
     RC_CUDA_TRY(ctrl.alloc((size_t)C * (nspin + 1) * 8));
     RC_CUDA_TRY(sigma.alloc((size_t)S * 8));
     RC_CUDA_TRY(counters.alloc(16));
@@ -142,6 +143,14 @@ static int sweep_host_impl(const double* ctrl_host, int64_t C, int nspin, int in
         if (rcode) return rcode;
         RC_CUDA_TRY(cudaMemcpyAsync(tau_host, tau.p, (size_t)G * S * S * 8, cudaMemcpyDeviceToHost, st));
         if (sel_host) RC_CUDA_TRY(cudaMemcpyAsync(sel_host, sel.p, (size_t)G * k * 8, cudaMemcpyDeviceToHost, st));
+        if (arim_host && arim_std_host) {
+            RC_CUDA_TRY(ar.alloc((size_t)2 * G * S * 8));
+            rcode = rc_arim_bootstrap(wsel.as<double>(), G * S, k, nboot > 0 ? nboot : 100, seed ^ 0x9E3779B97F4A7C15ull,
+                                      ar.as<double>(), ar.as<double>() + G * S, st);
+            if (rcode) return rcode;
+            RC_CUDA_TRY(cudaMemcpyAsync(arim_host, ar.p, (size_t)G * S * 8, cudaMemcpyDeviceToHost, st));
+            RC_CUDA_TRY(cudaMemcpyAsync(arim_std_host, ar.as<double>() + G * S, (size_t)G * S * 8, cudaMemcpyDeviceToHost, st));
+        }
     }
     unsigned long long hc[2] = {0, 0};
     RC_CUDA_TRY(cudaMemcpyAsync(hc, counters.p, 16, cudaMemcpyDeviceToHost, st));
@@ -156,15 +165,18 @@ extern "C" int rc_mc_sweep_host(const double* ctrl_host, int64_t C, int nspin, i
                                 int64_t c_offset, int64_t b_offset, const double* replay_host, double dkw_eps,
                                 int fused, double* fids_host, double* stats_host, void* stream) {
     return sweep_host_impl(ctrl_host, C, nspin, inspin, outspin, sigma_host, S, B, model, zz, seed, c_offset, b_offset,
-                           replay_host, dkw_eps, fused, fids_host, stats_host, 0, 0, 0.0, nullptr, nullptr, stream);
+                           replay_host, dkw_eps, fused, fids_host, stats_host, 0, 0, 0.0, nullptr, nullptr, 0, nullptr, nullptr,
+                           stream);
 }
 
 extern "C" int rc_robustness_sweep_host(const double* ctrl_host, int64_t C, int nspin, int inspin, int outspin,
                                         const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
                                         int64_t c_offset, int64_t b_offset, double dkw_eps, int fused, int64_t G,
                                         int64_t topk, double alpha_cluster, double* stats_host, double* tau_host,
-                                        int64_t* sel_host, void* stream) {
+                                        int64_t* sel_host, int nboot, double* arim_host, double* arim_std_host,
+                                        void* stream) {
     if (!tau_host) return set_error(RC_ERR_NULL, "rc_robustness_sweep_host: null tau output");
     return sweep_host_impl(ctrl_host, C, nspin, inspin, outspin, sigma_host, S, B, model, zz, seed, c_offset, b_offset,
-                           nullptr, dkw_eps, fused, nullptr, stats_host, G, topk, alpha_cluster, tau_host, sel_host, stream);
+                           nullptr, dkw_eps, fused, nullptr, stats_host, G, topk, alpha_cluster, tau_host, sel_host, nboot,
+                           arim_host, arim_std_host, stream);
 }

@@ -9,6 +9,7 @@
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 #include "rc_common.cuh"
+#include "rc_philox.cuh"
 
 namespace rc {
 
@@ -208,6 +209,56 @@ __global__ void gather_topk_kernel(const double* __restrict__ W, long long S, lo
     }
 }
 
+// ---- ARIM + bootstrap error bar (generate_arim_all_fig5.py:119-126, mcsim.py:267-275) --------------
+// One CTA per row (one (group, sigma) RIM vector of the top-k controllers).  ARIM = wd_from_ideal_zero of
+// the row = its mean; error bar = population std of the same statistic over `nboot` resamples with
+// replacement.  Resampling indices come from Philox4x32-10 keyed by (seed; row, resample, draw) —
+// device-side counterpart of upstream's np.random.randint stream (the numpy-stream variant lives in
+// the Python layer, arim.arim_bootstrap(rng_mode="numpy")).
+__global__ void __launch_bounds__(128) arim_bootstrap_kernel(const double* __restrict__ rims, long long R, int k, int nboot,
+                                                             uint32_t seed_lo, uint32_t seed_hi, double* __restrict__ arim,
+                                                             double* __restrict__ stdv) {
+    extern __shared__ double sh[];
+    double* row = sh;            // [k]
+    double* boot = sh + k;       // [nboot]
+    __shared__ double red[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < k; j += blockDim.x) row[j] = rims[r * k + j];
+        __syncthreads();
+        for (int b = warp; b < nboot; b += nwarp) {   // one warp per resample
+            double acc = 0.0;
+            for (int j0 = 0; j0 < k; j0 += 128) {      // 4 indices per Philox call, 32 lanes
+                Philox4 c;
+                c.x = (uint32_t)(j0 / 128 * 32 + lane); c.y = (uint32_t)b; c.z = (uint32_t)r; c.w = (uint32_t)(r >> 32);
+                Philox4 q = philox4x32_10(c, seed_lo, seed_hi);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int j = j0 + lane * 4 + t;
+                    if (j < k) acc += row[(int)(((unsigned long long)w[t] * (unsigned)k) >> 32)];   // uniform index in [0,k)
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) boot[b] = acc / (double)k;
+        }
+        __syncthreads();
+        // centre (mean of the row) and population std over the resamples: two passes by warp 0
+        if (warp == 0) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int j = lane; j < k; j += 32) s0 += row[j];
+            for (int b = lane; b < nboot; b += 32) s1 += boot[b];
+            for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+            const double mb = s1 / (double)nboot;
+            double m2 = 0.0;
+            for (int b = lane; b < nboot; b += 32) { const double dlt = boot[b] - mb; m2 += dlt * dlt; }
+            for (int o = 16; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+            if (lane == 0) { arim[r] = s0 / (double)k; stdv[r] = sqrt(m2 / (double)nboot); red[0] = 0.0; }
+        }
+    }
+}
+
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static size_t rank_cub_temp(long long R, long long n) {
@@ -377,4 +428,20 @@ extern "C" int rc_rank_consistency(const double* W_dev, int64_t S, int64_t G, in
     RC_CUDA_TRY(cudaGetLastError());
     // 3. S x S Kendall tau-b per group
     return rc_kendall_tau_b_batched(cr, (const int64_t*)rk, G, S, S, k, tau_dev, counts, stream);
+}
+
+extern "C" int rc_arim_bootstrap(const double* rims_dev, int64_t R, int64_t k, int nboot, uint64_t seed, double* arim_dev,
+                                 double* std_dev, void* stream) {
+    if (R < 0 || k < 1 || nboot < 1) return set_error(RC_ERR_BAD_ARG, "rc_arim_bootstrap: bad sizes");
+    if (R == 0) return RC_OK;
+    if (!rims_dev || !arim_dev || !std_dev) return set_error(RC_ERR_NULL, "rc_arim_bootstrap: null pointer");
+    size_t smem = (size_t)(k + nboot) * sizeof(double);
+    if (smem > 200 * 1024) return set_error(RC_ERR_BAD_ARG, "rc_arim_bootstrap: k + nboot too large for shared memory");
+    if (smem > 40 * 1024)
+        RC_CUDA_TRY(cudaFuncSetAttribute(arim_bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = R < (long long)device_sm_count() * 8 ? R : (long long)device_sm_count() * 8;
+    arim_bootstrap_kernel<<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(rims_dev, R, (int)k, nboot, (uint32_t)seed,
+                                                                               (uint32_t)(seed >> 32), arim_dev, std_dev);
+    RC_CUDA_TRY(cudaGetLastError());
+    return RC_OK;
 }

@@ -304,9 +304,9 @@ def _pinned(name, shape, dtype):
 def robustness_sweep_host(ctrl: np.ndarray, sigmas: np.ndarray, B: int, nspin: int, inspin: int, outspin: int, *,
                           groups: int = 1, topk: int = 100, alpha_cluster: float = 0.05, dkw_eps: float = 0.0,
                           model: int = MODEL_COMPLEX3, zz: bool = False, seed: int = 0, c_offset: int = 0,
-                          b_offset: int = 0, fused: bool = False, pinned_outputs: bool = True):
+                          b_offset: int = 0, fused: bool = False, pinned_outputs: bool = True, nboot: int = 100):
     """Evolution + statistics + per-group top-k / Kendall matrices in ONE C call with host buffers
-    (rc_robustness_sweep_host).  Returns (stats [15][S][C], tau [G][S][S], sel [G][k]) as numpy arrays;
+    (rc_robustness_sweep_host).  Returns (stats [15][S][C], tau [G][S][S], sel [G][k], arim [G][S], arim_std [G][S]) as numpy arrays;
     with pinned_outputs they are views of cached pinned buffers (copy them to keep across calls)."""
     require_cuda()
     ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
@@ -319,15 +319,32 @@ def robustness_sweep_host(ctrl: np.ndarray, sigmas: np.ndarray, B: int, nspin: i
         st = _pinned("stats", (NUM_STATS, S, Cn), torch.float64)
         tau = _pinned("tau", (groups, S, S), torch.float64)
         sel = _pinned("sel", (groups, k), torch.int64)
+        ar = _pinned("arim", (groups, S), torch.float64)
+        ars = _pinned("arim_std", (groups, S), torch.float64)
     else:
         st, tau, sel = np.empty((NUM_STATS, S, Cn)), np.empty((groups, S, S)), np.empty((groups, k), dtype=np.int64)
+        ar, ars = np.empty((groups, S)), np.empty((groups, S))
     vp = lambda a: C.c_void_p(a.ctypes.data)
     check(lib().rc_robustness_sweep_host(vp(ctrl), Cn, nspin, inspin, outspin, vp(sigmas), S, B, model, int(bool(zz)),
                                          C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, float(dkw_eps),
                                          int(bool(fused)), groups, topk, float(alpha_cluster), vp(st), vp(tau), vp(sel),
-                                         _stream()))
-    _count(11)  # evolution + sort/stats + the 9 ranking kernels
-    return st, tau, sel
+                                         int(nboot), vp(ar), vp(ars), _stream()))
+    _count(12)  # evolution + sort/stats + the 9 ranking kernels + ARIM bootstrap
+    return st, tau, sel, ar, ars
+
+
+def arim_bootstrap_device(rims, nboot: int = 100, seed: int = 0):
+    """(ARIM [R], bootstrap std [R]) of RIM rows [R][k] entirely on the device (rc_arim_bootstrap, Philox
+    resampling indices)."""
+    dev = require_cuda()
+    r = _f64(rims, dev)
+    r2 = r.reshape(-1, r.shape[-1])
+    R, k = r2.shape
+    a = torch.empty(R, dtype=torch.float64, device=dev)
+    s = torch.empty(R, dtype=torch.float64, device=dev)
+    check(lib().rc_arim_bootstrap(_ptr(r2), R, k, int(nboot), C.c_uint64(seed & (2**64 - 1)), _ptr(a), _ptr(s), _stream()))
+    _count(1)
+    return a.reshape(r.shape[:-1]), s.reshape(r.shape[:-1])
 
 
 def expm_batch(A) -> torch.Tensor:

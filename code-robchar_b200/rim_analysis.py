@@ -36,13 +36,17 @@ def rim_sweep(controllers, noises, bootreps: int, Nspin: int, inspin: int, outsp
 
 def robustness_sweep(controllers: np.ndarray, noises: np.ndarray, bootreps: int, Nspin: int, inspin: int, outspin: int,
                      *, groups: int = 1, topk: int = 100, alpha_dkw: float = 0.05, alpha_cluster: float = 0.05,
-                     seed: int = 0, fused: bool = False, model: int = engine.MODEL_COMPLEX3, zz: bool = False) -> dict:
+                     seed: int = 0, fused: bool = False, model: int = engine.MODEL_COMPLEX3, zz: bool = False,
+                     nboot: int = 100) -> dict:
     """The paper's fig-4/5 sweep for `groups` controller sets given as HOST arrays: evolution,
     the 15 statistics, per-group top-k selection and Kendall matrices.  Host in, host out: the
     controllers travel to the device and the statistics / tau matrices come back (the end-to-end
-    call bench.py times).  Returns {"stats": {key: [S][C]}, "tau": [G][S][S], "topk_idx": [G][k]}."""
+    call bench.py times).  Returns {"stats": {key: [S][C]}, "tau": [G][S][S], "topk_idx": [G][k], "arim": [G][S],
+    "arim_std": [G][S]} (ARIM and its bootstrap error bar over the top-k controllers, fig 5)."""
     eps = float(compute_dkw_error(alpha_dkw, bootreps))
-    st, tau, sel = engine.robustness_sweep_host(np.asarray(controllers), np.asarray(noises), bootreps, Nspin, inspin,
-                                                outspin, groups=groups, topk=topk, alpha_cluster=alpha_cluster,
-                                                dkw_eps=eps, seed=seed, fused=fused, model=model, zz=zz)
-    return {"stats": {k: st[i] for i, k in enumerate(engine.STAT_KEYS)}, "tau": tau, "topk_idx": sel}
+    st, tau, sel, ar, ars = engine.robustness_sweep_host(np.asarray(controllers), np.asarray(noises), bootreps, Nspin,
+                                                         inspin, outspin, groups=groups, topk=topk,
+                                                         alpha_cluster=alpha_cluster, dkw_eps=eps, seed=seed, fused=fused,
+                                                         model=model, zz=zz, nboot=nboot)
+    return {"stats": {k: st[i] for i, k in enumerate(engine.STAT_KEYS)}, "tau": tau, "topk_idx": sel, "arim": ar,
+            "arim_std": ars}

@@ -130,6 +130,13 @@ int rc_rank_consistency(const double* W_dev, int64_t S, int64_t G, int64_t Cg, i
                         double* tau_dev, int64_t* sel_dev, double* Wsel_dev, void* workspace_dev,
                         size_t workspace_bytes, void* stream);
 
+/* ARIM (algorithm-level RIM) of every row of rims_dev [R][k] and its bootstrap error bar:
+ * arim[r] = wd_from_ideal_zero(row) = mean(row) (generate_arim_all_fig5.py:119,166), std[r] = population
+ * std of that statistic over `nboot` resamples with replacement (MCDataSim.bootstrap_resampling_std,
+ * mcsim.py:267-275), resampling indices from Philox4x32-10 keyed by `seed`. */
+int rc_arim_bootstrap(const double* rims_dev, int64_t R, int64_t k, int nboot, uint64_t seed, double* arim_dev,
+                      double* std_dev, void* stream);
+
 /* Whole sweep with HOST buffers: H2D of controllers/sigmas(/replay), evolution, statistics, D2H of
  * the 15 metric tensors (and of the fidelity tensor when fids_host != NULL).  This is what
  * MCDataSim.get_metrics_dict (mcsim.py:463-510) computes from scratch.
@@ -140,14 +147,15 @@ int rc_mc_sweep_host(const double* ctrl_host, int64_t C, int nspin, int inspin, 
                      int fused, double* fids_host, double* stats_host, void* stream);
 
 /* rc_mc_sweep_host followed by rc_rank_consistency on the device, everything returned to HOST
- * buffers: stats_host [15][S][C], tau_host [G][S][S], sel_host int64 [G][k] (C = G*Cg).  This is the
- * whole fig-4/5 sweep of one problem as a single call (pinned host buffers make the copies
- * asynchronous up to the final synchronisation). */
+ * buffers: stats_host [15][S][C], tau_host [G][S][S], sel_host int64 [G][k] (C = G*Cg), and, when
+ * arim_host != NULL, the fig-5 ARIM [G][S] with its bootstrap std [G][S] over `nboot` resamples of the
+ * top-k RIMs.  This is the whole fig-4/5 sweep of one problem as a single call (pinned host buffers
+ * make the copies asynchronous up to the final synchronisation). */
 int rc_robustness_sweep_host(const double* ctrl_host, int64_t C, int nspin, int inspin, int outspin,
                              const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
                              int64_t c_offset, int64_t b_offset, double dkw_eps, int fused, int64_t G,
                              int64_t topk, double alpha_cluster, double* stats_host, double* tau_host,
-                             int64_t* sel_host, void* stream);
+                             int64_t* sel_host, int nboot, double* arim_host, double* arim_std_host, void* stream);
 
 /* Dense complex matrix exponential of `batch` M x M matrices (M <= 32), interleaved (re, im) float64,
  * row-major: out = expm(A).  The generality path behind the reference's scipy.linalg.expm calls whose

@@ -558,3 +558,25 @@ def test_parameter_extremes_vs_oracle(rb):
     assert one.shape == (1, 1, 1) and 0 <= float(one) <= 1
     st = rb.engine.stats(one, 0.1).cpu().numpy()
     assert st.shape == (15, 1, 1) and abs(st[0, 0, 0] - (1 - float(one))) < 1e-15 and st[9, 0, 0] == 0.0
+
+
+def test_arim_bootstrap_device(rb):
+    """rc_arim_bootstrap: centre exact (mean of the top-k RIMs == wd_from_ideal_zero), error bar statistically
+    consistent with the reference's numpy bootstrap; also returned by the one-call host sweep."""
+    g = load_golden("objective_arim.npz")
+    rims = g["arim_rims"]
+    a, s = rb.engine.arim_bootstrap_device(rims, 4000, seed=5)
+    a, s = a.cpu().numpy(), s.cpu().numpy()
+    assert np.abs(a - g["arim_centre"]).max() < 1e-15
+    assert np.abs(s / g["arim_std"] - 1).max() < 0.2            # the reference value is itself a 100-resample estimate
+    theory = rims.std(axis=1) / np.sqrt(rims.shape[1])           # std of the mean under resampling
+    assert np.abs(s / theory - 1).max() < 0.05
+    a2, s2 = rb.engine.arim_bootstrap_device(rims, 4000, seed=5)
+    assert torch.equal(a2.cpu(), torch.as_tensor(a)) and torch.equal(s2.cpu(), torch.as_tensor(s))   # deterministic
+    out = rb.rim_analysis.robustness_sweep(orc.synthetic_controllers(60, 5), np.linspace(0, 0.1, 4), 50, 5, 0, 4, groups=3,
+                                           topk=10, seed=1)
+    W = out["stats"][orc.METRIC_W]
+    for gi in range(3):
+        cols = gi * 20 + out["topk_idx"][gi]
+        assert np.abs(out["arim"][gi] - W[:, cols].mean(axis=1)).max() < 1e-15
+    assert out["arim_std"].shape == (3, 4) and np.all(out["arim_std"] >= 0)
