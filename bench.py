@@ -209,7 +209,7 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     fids = torch.empty((S, C_local, B), dtype=torch.float64, device=dev)
     topk = min(100, cg)
-    fused = B > 4096
+    fused = B > 512   # long segments: streaming statistics (no fidelity tensor); short ones: materialise + warp sort
     fid_events = []
 
     def step(seed, timed=False):
