@@ -176,7 +176,7 @@ def workload_config(name, gpus):
                         f"S={S} sigma_sim levels linspace(0,0.1), B={B} draws, complex 3-draw noise model"
                         f"{', ZZ term on' if zz else ''}; fidelities + 15 statistics + top-100 + Kendall tau + ARIM with bootstrap error bars per group",
             "nspin": nspin, "controllers_per_gpu": groups * cg, "sigma_levels": S, "draws": B,
-            "evals_per_step": S * groups * cg * B * gpus, "noise": "in-kernel Philox4x32-10 + Box-Muller (fp64)",
+            "evals_per_step": S * groups * cg * B * gpus, "noise": "in-kernel Philox4x32-10 + 1024-layer ziggurat (fp64)",
             "l2": "256 MiB memset between steps (inside the timed region); per-step fidelity tensor "
                   f"{S * groups * cg * B * 8 / 2**20:.0f} MiB", "parallelism": f"controller-sharded x{gpus}"}
 

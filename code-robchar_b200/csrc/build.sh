@@ -7,7 +7,7 @@ OUT=../librobchar_b200.so
 OBJ=_obj
 mkdir -p $OBJ
 NVCC=${NVCC:-nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --extended-lambda -Xcompiler -fPIC -diag-suppress 550"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --extended-lambda -Xcompiler -fPIC -diag-suppress 550,20091"
 cmds=()
 for n in $(seq 2 16); do
   cmds+=("$NVCC $FLAGS -DRC_NSPIN=$n -c rc_fidelity_n.cu -o $OBJ/rc_fidelity_$n.o")

@@ -28,11 +28,33 @@ int device_sm_count() {
     return sm;
 }
 
+}  // namespace rc
+#define RC_ZIG_QUAL static __device__
+#include "rc_zig_table.inc"
+namespace rc {
+
+// Device addresses of the ziggurat tables (one copy per device, defined in this translation unit).
+cudaError_t zig_tables_device(ZigTables* t) {
+    static ZigTables cached[64];
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    if (dev >= 0 && dev < 64 && cached[dev].kw) { *t = cached[dev]; return cudaSuccess; }
+    void *kw = nullptr, *y = nullptr;
+    err = cudaGetSymbolAddress(&kw, rc_zig_kw);
+    if (err != cudaSuccess) return err;
+    err = cudaGetSymbolAddress(&y, rc_zig_y);
+    if (err != cudaSuccess) return err;
+    t->kw = (const ZigEntry*)kw; t->y = (const double*)y;
+    if (dev >= 0 && dev < 64) cached[dev] = *t;
+    return cudaSuccess;
+}
+
 #define RC_DECL(n) cudaError_t launch_fid_reg_##n(const FidArgs&, int, cudaStream_t);
 RC_DECL(2) RC_DECL(3) RC_DECL(4) RC_DECL(5) RC_DECL(6) RC_DECL(7) RC_DECL(8) RC_DECL(9) RC_DECL(10)
 RC_DECL(11) RC_DECL(12) RC_DECL(13) RC_DECL(14) RC_DECL(15) RC_DECL(16)
 #undef RC_DECL
-#define RC_DECL(n) cudaError_t launch_fused_reg_##n(const FusedArgs&, int, cudaStream_t);
+#define RC_DECL(n) cudaError_t launch_fused_reg_##n(const FusedArgs&, int, int, cudaStream_t);
 RC_DECL(2) RC_DECL(3) RC_DECL(4) RC_DECL(5) RC_DECL(6) RC_DECL(7) RC_DECL(8) RC_DECL(9) RC_DECL(10)
 RC_DECL(11) RC_DECL(12) RC_DECL(13) RC_DECL(14) RC_DECL(15) RC_DECL(16)
 #undef RC_DECL
@@ -47,6 +69,29 @@ static fused_launch_fn fused_table[REG_MAX_N + 1] = {
     launch_fused_reg_6, launch_fused_reg_7, launch_fused_reg_8, launch_fused_reg_9, launch_fused_reg_10,
     launch_fused_reg_11, launch_fused_reg_12, launch_fused_reg_13, launch_fused_reg_14, launch_fused_reg_15,
     launch_fused_reg_16};
+
+int reg_threads_runtime(int n, bool replay) {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("RC_FID_THREADS");
+        env = e ? atoi(e) : 0;
+        if (env < 32 || (env % 32)) env = 0;
+    }
+    const int compiled = reg_cta_threads(n, replay);
+    return env && env < compiled ? env : compiled;
+}
+
+int fused_reg_threads(int n, bool replay, long long B) {
+    const int top = reg_threads_runtime(n, replay);
+    const int cand[4] = {top, 384, 256, 128};
+    for (int k = 0; k < 4; ++k) {
+        const long long t = cand[k];
+        if (t > top) continue;
+        const long long passes = (B + t - 1) / t;
+        if (B * 10 >= passes * t * 9) return (int)t;   // >= 90 % of the lanes busy
+    }
+    return top < 128 ? top : 128;
+}
 
 // CTA size of the shared-memory kernels: 128 lanes while four [N][128] arrays leave room for >= 4 CTAs/SM
 static int smem_threads(int n) { return (size_t)4 * n * 128 * sizeof(double) <= 56 * 1024 ? 128 : 64; }
@@ -113,22 +158,28 @@ static cudaError_t launch_fused_smem(const FusedArgs& g, int sm_count, cudaStrea
 
 cudaError_t launch_fused(const FusedArgs& g, cudaStream_t st) {
     int sm = device_sm_count();
-    if (g.f.N <= reg_crossover()) return fused_table[g.f.N](g, sm, st);
+    if (g.f.N <= reg_crossover())
+        return fused_table[g.f.N](g, fused_reg_threads(g.f.N, g.f.replay != nullptr, g.f.B), sm, st);
     const bool replay = g.f.replay != nullptr;
     if (g.f.model == MODEL_COMPLEX3)
         return replay ? launch_fused_smem<MODEL_COMPLEX3, true>(g, sm, st) : launch_fused_smem<MODEL_COMPLEX3, false>(g, sm, st);
     return replay ? launch_fused_smem<MODEL_REAL2, true>(g, sm, st) : launch_fused_smem<MODEL_REAL2, false>(g, sm, st);
 }
 
-// chunking of the draw axis for the fused path: multiples of the CTA size, <= 4096 draws per item
-static void fused_chunking(int nspin, long long B, long long* chunk, long long* nchunks) {
-    const long long threads = nspin <= reg_crossover() ? 128 : smem_threads(nspin);
-    long long ch = 4096;
+// chunking of the draw axis for the fused path: a multiple of the CTA size close to 4096 draws per item
+static void fused_chunking_threads(long long threads, long long B, long long* chunk, long long* nchunks) {
+    long long k = (4096 + threads / 2) / threads;
+    if (k < 1) k = 1;
+    long long ch = k * threads;
     if (B < ch) ch = (B + threads - 1) / threads * threads;
     if (ch < threads) ch = threads;
     *chunk = ch;
     *nchunks = (B + ch - 1) / ch;
     if (*nchunks < 1) *nchunks = 1;
+}
+static void fused_chunking(int nspin, bool replay, long long B, long long* chunk, long long* nchunks) {
+    const long long threads = nspin <= reg_crossover() ? fused_reg_threads(nspin, replay, B) : smem_threads(nspin);
+    fused_chunking_threads(threads, B, chunk, nchunks);
 }
 
 // One thread per segment merges its chunk partials in order and emits the 15 statistics.
@@ -165,7 +216,7 @@ int check_model_args(int64_t C, int nspin, int inspin, int outspin, int S, int64
 }
 
 __global__ void philox_normals_kernel(long long C, long long B, int S, int n, int model, uint32_t k0, uint32_t k1,
-                                      long long c_off, long long b_off, double* out) {
+                                      long long c_off, long long b_off, ZigTables zig, double* out) {
     const int P = model == MODEL_COMPLEX3 ? 3 : 2;
     const int K = P * n;
     const long long total = (long long)S * C * B;
@@ -174,14 +225,10 @@ __global__ void philox_normals_kernel(long long C, long long B, int S, int n, in
         EvalIndex ix = decode_eval(ev, C, B);
         double* row = out + ev * K;
         for (int j = 0; j < K; ++j) row[j] = 0.0;
-        const int nc = K - (P - 1);
-        for (int p = 0; p < (nc + 1) / 2; ++p) {
-            double z0, z1;
-            normal_pair(k0, k1, (uint32_t)ix.s, (uint64_t)(ix.c + c_off), (uint64_t)(ix.b + b_off), p, z0, z1);
-            int jc = 2 * p;
-            row[jc == 0 ? 0 : jc + (P - 1)] = z0;
-            if (jc + 1 < nc) row[jc + 1 + (P - 1)] = z1;
-        }
+        NoiseKey key;
+        key.seed_lo = k0; key.seed_hi = k1; key.sidx = (uint32_t)ix.s;
+        key.cidx = (uint64_t)(ix.c + c_off); key.bidx = (uint64_t)(ix.b + b_off);
+        normals_fill(key, K - (P - 1), zig, [&](int jc) -> double& { return row[jc == 0 ? 0 : jc + (P - 1)]; });
     }
 }
 
@@ -216,6 +263,7 @@ extern "C" int rc_fidelity_mc(const double* ctrl_dev, int64_t C, int nspin, int 
     a.C = C; a.B = B; a.S = S; a.N = nspin; a.in = inspin; a.out = outspin; a.model = model; a.zz = zz;
     a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
     a.c_offset = c_offset; a.b_offset = b_offset;
+    RC_CUDA_TRY(zig_tables_device(&a.zig));
     RC_CUDA_TRY(launch_fidelity(a, (cudaStream_t)stream));
     return RC_OK;
 }
@@ -229,21 +277,25 @@ extern "C" int rc_philox_normals(int64_t C, int nspin, int S, int64_t B, int mod
     if (!normals_dev) return set_error(RC_ERR_NULL, "rc_philox_normals: null output");
     long long blocks = (total + 127) / 128;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    ZigTables zig;
+    RC_CUDA_TRY(zig_tables_device(&zig));
     philox_normals_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(C, B, S, nspin, model, (uint32_t)seed,
                                                                               (uint32_t)(seed >> 32), c_offset, b_offset,
-                                                                              normals_dev);
+                                                                              zig, normals_dev);
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }
 
 extern "C" size_t rc_fidelity_stats_workspace_bytes(int64_t nseg, int64_t B) {
     if (nseg <= 0 || B <= 0) return 256;
-    long long chunk, nchunks;
-    fused_chunking(2, B, &chunk, &nchunks);  // 128-thread chunking gives the upper bound for both paths
-    long long ch64 = 4096;
-    if (B < ch64) ch64 = (B + 63) / 64 * 64;
-    long long n64 = (B + ch64 - 1) / ch64;
-    long long nmax = nchunks > n64 ? nchunks : n64;
+    // upper bound over every CTA size any path may pick
+    long long nmax = 1;
+    const long long sizes[6] = {64, 128, 256, 384, 768, RC_REG_THREADS ? RC_REG_THREADS : 768};
+    for (int k = 0; k < 6; ++k) {
+        long long chunk, nchunks;
+        fused_chunking_threads(sizes[k], B, &chunk, &nchunks);
+        if (nchunks > nmax) nmax = nchunks;
+    }
     return (size_t)nseg * nmax * PART_DOUBLES * sizeof(double) + 256;
 }
 
@@ -264,8 +316,9 @@ extern "C" int rc_fidelity_stats(const double* ctrl_dev, int64_t C, int nspin, i
     a.C = C; a.B = B; a.S = S; a.N = nspin; a.in = inspin; a.out = outspin; a.model = model; a.zz = zz;
     a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
     a.c_offset = c_offset; a.b_offset = b_offset;
+    RC_CUDA_TRY(zig_tables_device(&a.zig));
     g.eps = dkw_eps;
-    fused_chunking(nspin, B, &g.chunk, &g.nchunks);
+    fused_chunking(nspin, replay_dev != nullptr, B, &g.chunk, &g.nchunks);
     const size_t need = (size_t)nseg * g.nchunks * PART_DOUBLES * sizeof(double);
     if (!workspace_dev || workspace_bytes < need)
         return set_error(RC_ERR_WORKSPACE, "rc_fidelity_stats: workspace %zu < required %zu bytes", workspace_bytes, need);

@@ -28,6 +28,7 @@ struct FidArgs {
     int S, N, in, out, model, zz;
     uint32_t seed_lo, seed_hi;
     long long c_offset, b_offset;  // global index of this shard's first controller / draw (Philox counters)
+    ZigTables zig;                 // ziggurat tables in global memory (Philox mode), see zig_tables_device()
 };
 
 __host__ __device__ constexpr int draws_per_site(int model) { return model == MODEL_COMPLEX3 ? 3 : 2; }
@@ -70,23 +71,32 @@ __device__ __forceinline__ void build_tridiagonal(const double* __restrict__ x, 
     e[N - 1] = 0.0;
 }
 
+RC_HD NoiseKey noise_key(const FidArgs& a, long long s, long long c, long long b) {
+    NoiseKey k;
+    k.seed_lo = a.seed_lo; k.seed_hi = a.seed_hi; k.sidx = (uint32_t)s;
+    k.cidx = (uint64_t)(c + a.c_offset); k.bidx = (uint64_t)(b + a.b_offset);
+    return k;
+}
+
 // Philox mode: this lane writes the standard normals of its evaluation into its own staged row, in
 // reference draw order (the discarded site-0 coupling slots are left untouched and never read).
-// The pair loop is deliberately NOT unrolled: one copy of Philox + log + sqrt + sincospi in the
-// instruction stream (code size matters more than the loop overhead, see rc_ql.cuh).
+// `kw` = the CTA's shared-memory copy of the ziggurat fast-path table.
 template <int N, int MODEL>
-__device__ __forceinline__ void philox_fill_row(const FidArgs& a, long long s, long long c, long long b, double* row) {
+__device__ __forceinline__ void philox_fill_row(const FidArgs& a, long long s, long long c, long long b, double* row,
+                                                const ZigEntry* kw) {
     constexpr int P = draws_per_site(MODEL);
     constexpr int NC = P * N - (P - 1);  // compact count: reference order minus discarded draws
-    const uint64_t cg = (uint64_t)(c + a.c_offset), bg = (uint64_t)(b + a.b_offset);
-#pragma unroll 1
-    for (int p = 0; p < (NC + 1) / 2; ++p) {
-        double z0, z1;
-        normal_pair(a.seed_lo, a.seed_hi, (uint32_t)s, cg, bg, (uint32_t)p, z0, z1);
-        const int jc = 2 * p;
-        row[jc == 0 ? 0 : jc + (P - 1)] = z0;
-        if (jc + 1 < NC) row[jc + 1 + (P - 1)] = z1;
-    }
+    ZigTables t;
+    t.kw = kw; t.y = a.zig.y;
+    normals_fill(noise_key(a, s, c, b), NC, t, [&](int jc) -> double& { return row[jc == 0 ? 0 : jc + (P - 1)]; });
+}
+
+// Cooperative copy of the 16 KB fast-path table into shared memory (once per persistent CTA).
+__device__ __forceinline__ void load_zig_table(const ZigEntry* __restrict__ g, ZigEntry* s) {
+    const double2* src = reinterpret_cast<const double2*>(g);
+    double2* dst = reinterpret_cast<double2*>(s);
+    for (int i = threadIdx.x; i < ZIG_LAYERS; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
 }
 
 // Coalesced staging of `nvalid` consecutive replay rows (K doubles each) into padded shared rows.
@@ -105,13 +115,14 @@ __device__ __forceinline__ void stage_replay_rows(const double* __restrict__ src
 // holds the standard normals on entry (staged replay or Philox) and is reused as the eigenvalue /
 // weight scratch of the eigensolver (2N <= K doubles).
 template <int N, int MODEL, bool REPLAY>
-__device__ __forceinline__ double eval_reg(const FidArgs& a, long long s, long long c, long long b, double* row) {
+__device__ __forceinline__ double eval_reg(const FidArgs& a, long long s, long long c, long long b, double* row,
+                                           const ZigEntry* kw) {
     const double* x = a.ctrl + c * (N + 1);
     double xr[N + 1];
 #pragma unroll
     for (int i = 0; i <= N; ++i) xr[i] = __ldg(x + i);
     const double sigma = __ldg(a.sigma + s);
-    if (!REPLAY) philox_fill_row<N, MODEL>(a, s, c, b, row);
+    if (!REPLAY) philox_fill_row<N, MODEL>(a, s, c, b, row, kw);
     double d[N], ee[N];
     build_tridiagonal<N, MODEL>(xr, sigma, a.zz, [&](int j) { return row[j]; }, d, ee);
     int fail = 0;
@@ -120,14 +131,39 @@ __device__ __forceinline__ double eval_reg(const FidArgs& a, long long s, long l
     return f;
 }
 
+// CTA shape of the register-resident kernels, measured on B200 at N = 4..8 (profiles/README.md, r01h):
+// Philox mode runs fastest as ONE 24-warp CTA per SM with the compiler held to 80 registers (a few
+// spilled doubles): 3.58e9 evaluations/s at N=7 against 3.1e9 for four 4-warp CTAs at 126 registers;
+// warp counts that are not a multiple of the four schedulers lose 5-10 %.  Replay mode stages its
+// rows behind CTA barriers and prefers three 8-warp CTAs.  N > 8 (non-default, RC_REG_MAX_N) keeps
+// 4-warp CTAs: the eigensolver state alone needs more than 80 registers there.
+// RC_REG_THREADS / RC_REG_MIN_BLOCKS (compile time) and RC_FID_THREADS (environment) are tuning overrides.
 #ifndef RC_REG_MIN_BLOCKS
-#define RC_REG_MIN_BLOCKS 1
+#define RC_REG_MIN_BLOCKS 0
 #endif
+#ifndef RC_REG_THREADS
+#define RC_REG_THREADS 0
+#endif
+#ifndef RC_TILE_SYNC
+#define RC_TILE_SYNC 0
+#endif
+__host__ __device__ constexpr int reg_cta_threads(int n, bool replay) {
+    return RC_REG_THREADS ? RC_REG_THREADS : (n > 8 ? 128 : (replay ? 256 : 768));
+}
+__host__ __device__ constexpr int reg_cta_min_blocks(int n, bool replay) {
+    return RC_REG_MIN_BLOCKS ? RC_REG_MIN_BLOCKS : (n > 8 ? 1 : (replay ? 3 : 1));
+}
+constexpr int MAX_CTA_WARPS = 32;
+
 template <int N, int MODEL, bool REPLAY>
-__global__ void __launch_bounds__(128, RC_REG_MIN_BLOCKS) fidelity_reg_kernel(FidArgs a) {
+__global__ void __launch_bounds__(reg_cta_threads(N, REPLAY), reg_cta_min_blocks(N, REPLAY)) fidelity_reg_kernel(FidArgs a) {
     constexpr int K = draws_per_site(MODEL) * N;
     constexpr int KP = K | 1;
-    extern __shared__ double stage[];
+    extern __shared__ __align__(16) double smem_raw[];
+    // Philox mode: [ziggurat table 16 KB][one row per lane]; replay mode: rows only
+    const ZigEntry* kw = reinterpret_cast<const ZigEntry*>(smem_raw);
+    double* stage = smem_raw + (REPLAY ? 0 : 2 * ZIG_LAYERS);
+    if (!REPLAY) load_zig_table(a.zig.kw, reinterpret_cast<ZigEntry*>(smem_raw));
     const long long total = (long long)a.S * a.C * a.B;
     const long long ntiles = (total + blockDim.x - 1) / blockDim.x;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -137,9 +173,12 @@ __global__ void __launch_bounds__(128, RC_REG_MIN_BLOCKS) fidelity_reg_kernel(Fi
             long long nvalid = total - e0 < (long long)blockDim.x ? total - e0 : (long long)blockDim.x;
             stage_replay_rows<K>(a.replay + e0 * K, (int)nvalid, stage);
         }
+#if RC_TILE_SYNC
+        if (!REPLAY) __syncthreads();   // keeps the CTA's warps in the same phase of the code
+#endif
         if (e >= total) continue;
         EvalIndex ix = decode_eval(e, a.C, a.B);
-        a.fids[e] = eval_reg<N, MODEL, REPLAY>(a, ix.s, ix.c, ix.b, stage + threadIdx.x * KP);
+        a.fids[e] = eval_reg<N, MODEL, REPLAY>(a, ix.s, ix.c, ix.b, stage + threadIdx.x * KP, kw);
     }
 }
 
@@ -230,12 +269,15 @@ __device__ __forceinline__ void moments_block_merge(Moments& m, double* scratch 
 }
 
 template <int N, int MODEL, bool REPLAY>
-__global__ void __launch_bounds__(128) fidelity_stats_reg_kernel(FusedArgs g) {
+__global__ void __launch_bounds__(reg_cta_threads(N, REPLAY), reg_cta_min_blocks(N, REPLAY)) fidelity_stats_reg_kernel(FusedArgs g) {
     constexpr int K = draws_per_site(MODEL) * N;
     constexpr int KP = K | 1;
-    extern __shared__ double stage[];
-    __shared__ double scratch[4 * PART_DOUBLES];
+    extern __shared__ __align__(16) double smem_raw[];
+    __shared__ double scratch[MAX_CTA_WARPS * PART_DOUBLES];
     const FidArgs& a = g.f;
+    const ZigEntry* kw = reinterpret_cast<const ZigEntry*>(smem_raw);
+    double* stage = smem_raw + (REPLAY ? 0 : 2 * ZIG_LAYERS);
+    if (!REPLAY) load_zig_table(a.zig.kw, reinterpret_cast<ZigEntry*>(smem_raw));
     const long long nseg = (long long)a.S * a.C;
     const long long nitems = nseg * g.nchunks;
     for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -253,7 +295,7 @@ __global__ void __launch_bounds__(128) fidelity_stats_reg_kernel(FusedArgs g) {
                 stage_replay_rows<K>(a.replay + (seg * a.B + bt) * K, (int)nvalid, stage);
             }
             if (b < b1) {
-                double f = eval_reg<N, MODEL, REPLAY>(a, s, c, b, stage + threadIdx.x * KP);
+                double f = eval_reg<N, MODEL, REPLAY>(a, s, c, b, stage + threadIdx.x * KP, kw);
                 moments_add(m, f, g.eps, shift, m.n == 0.0);
             }
         }
@@ -289,22 +331,11 @@ __device__ __forceinline__ double eval_smem(const FidArgs& a, long long s, long 
             }
         }
     } else {
-        const uint64_t cg = (uint64_t)(c + a.c_offset), bg = (uint64_t)(b + a.b_offset);
-        const int nc = P * n - (P - 1);  // compact draw count
-#pragma unroll 1
-        for (int p = 0; p < (nc + 1) / 2; ++p) {
-            double z[2];
-            normal_pair(a.seed_lo, a.seed_hi, (uint32_t)s, cg, bg, (uint32_t)p, z[0], z[1]);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int jc = 2 * p + h;  // compact index: 0 -> z_00, then (z_ii, nn_i[, nn2_i]) for i >= 1
-                if (jc < nc) {
-                    const int site = jc == 0 ? 0 : 1 + (jc - 1) / P, kind = jc == 0 ? 0 : (jc - 1) % P;
-                    double* dst = kind == 0 ? d + (size_t)site * ld : (kind == 1 ? e + (size_t)(site - 1) * ld : zi + (size_t)site * ld);
-                    *dst = z[h];
-                }
-            }
-        }
+        // compact index: 0 -> z_00, then (z_ii, nn_i[, nn2_i]) for i >= 1; fast-path table read through L1
+        normals_fill(noise_key(a, s, c, b), P * n - (P - 1), a.zig, [&](int jc) -> double& {
+            const int site = jc == 0 ? 0 : 1 + (jc - 1) / P, kind = jc == 0 ? 0 : (jc - 1) % P;
+            return *(kind == 0 ? d + (size_t)site * ld : (kind == 1 ? e + (size_t)(site - 1) * ld : zi + (size_t)site * ld));
+        });
     }
     for (int i = 0; i < n; ++i) {
         const double base = a.zz ? zz_diag(i, n) : 0.0;
@@ -344,7 +375,7 @@ __global__ void __launch_bounds__(128) fidelity_smem_kernel(FidArgs a) {
 template <int MODEL, bool REPLAY>
 __global__ void __launch_bounds__(128) fidelity_stats_smem_kernel(FusedArgs g) {
     extern __shared__ double sm[];
-    __shared__ double scratch[4 * PART_DOUBLES];
+    __shared__ double scratch[MAX_CTA_WARPS * PART_DOUBLES];
     const FidArgs& a = g.f;
     const long long K = (long long)draws_per_site(MODEL) * a.N;
     const long long nseg = (long long)a.S * a.C;
@@ -370,6 +401,12 @@ __global__ void __launch_bounds__(128) fidelity_stats_smem_kernel(FusedArgs g) {
 
 // launchers implemented in rc_fidelity_n.cu (one translation unit per N) / rc_fidelity.cu
 typedef cudaError_t (*fid_launch_fn)(const FidArgs&, int sm_count, cudaStream_t);
-typedef cudaError_t (*fused_launch_fn)(const FusedArgs&, int sm_count, cudaStream_t);
+typedef cudaError_t (*fused_launch_fn)(const FusedArgs&, int threads, int sm_count, cudaStream_t);
+
+// CTA size of the register-resident kernels at run time: the compiled shape unless RC_FID_THREADS asks for less.
+int reg_threads_runtime(int n, bool replay);
+// CTA size of the fused (streaming statistics) register kernels for segments of B draws: the largest
+// of {compiled, 384, 256, 128} that keeps the last pass over a chunk reasonably full.
+int fused_reg_threads(int n, bool replay, long long B);
 
 }  // namespace rc

@@ -11,23 +11,13 @@
 
 namespace rc {
 
-// CTA size of the register-resident kernels (RC_FID_THREADS overrides for tuning: 32..128).
-static int reg_threads() {
-    static int v = 0;
-    if (!v) {
-        const char* e = getenv("RC_FID_THREADS");
-        v = e ? atoi(e) : 128;
-        if (v < 32 || v > 128 || (v % 32)) v = 128;
-    }
-    return v;
-}
-
 template <int MODEL, bool REPLAY>
 static cudaError_t launch_reg(const FidArgs& a, int sm_count, cudaStream_t st) {
     constexpr int N = RC_NSPIN;
     constexpr int K = draws_per_site(MODEL) * N;
-    const int threads = reg_threads();
-    size_t smem = (size_t)threads * (K | 1) * sizeof(double);  // one private row per lane
+    const int threads = reg_threads_runtime(N, REPLAY);
+    // one private row per lane (+ the ziggurat fast-path table in Philox mode)
+    size_t smem = (size_t)threads * (K | 1) * sizeof(double) + (REPLAY ? 0 : sizeof(ZigEntry) * ZIG_LAYERS);
     auto kern = fidelity_reg_kernel<N, MODEL, REPLAY>;
     if (const char* e = getenv("RC_FID_SMEM_PAD")) smem += (size_t)atoi(e) * 1024;  // tuning: limits CTAs/SM
     cudaError_t err;
@@ -49,11 +39,10 @@ static cudaError_t launch_reg(const FidArgs& a, int sm_count, cudaStream_t st) {
 }
 
 template <int MODEL, bool REPLAY>
-static cudaError_t launch_fused_reg(const FusedArgs& g, int sm_count, cudaStream_t st) {
+static cudaError_t launch_fused_reg(const FusedArgs& g, int threads, int sm_count, cudaStream_t st) {
     constexpr int N = RC_NSPIN;
     constexpr int K = draws_per_site(MODEL) * N;
-    const int threads = reg_threads();
-    size_t smem = (size_t)threads * (K | 1) * sizeof(double);  // one private row per lane
+    size_t smem = (size_t)threads * (K | 1) * sizeof(double) + (REPLAY ? 0 : sizeof(ZigEntry) * ZIG_LAYERS);
     auto kern = fidelity_stats_reg_kernel<N, MODEL, REPLAY>;
     cudaError_t err;
     if (smem > 40 * 1024) {
@@ -72,11 +61,13 @@ static cudaError_t launch_fused_reg(const FusedArgs& g, int sm_count, cudaStream
     return cudaGetLastError();
 }
 
-cudaError_t RC_CAT(launch_fused_reg_, RC_NSPIN)(const FusedArgs& g, int sm_count, cudaStream_t st) {
+cudaError_t RC_CAT(launch_fused_reg_, RC_NSPIN)(const FusedArgs& g, int threads, int sm_count, cudaStream_t st) {
     const bool replay = g.f.replay != nullptr;
     if (g.f.model == MODEL_COMPLEX3)
-        return replay ? launch_fused_reg<MODEL_COMPLEX3, true>(g, sm_count, st) : launch_fused_reg<MODEL_COMPLEX3, false>(g, sm_count, st);
-    return replay ? launch_fused_reg<MODEL_REAL2, true>(g, sm_count, st) : launch_fused_reg<MODEL_REAL2, false>(g, sm_count, st);
+        return replay ? launch_fused_reg<MODEL_COMPLEX3, true>(g, threads, sm_count, st)
+                      : launch_fused_reg<MODEL_COMPLEX3, false>(g, threads, sm_count, st);
+    return replay ? launch_fused_reg<MODEL_REAL2, true>(g, threads, sm_count, st)
+                  : launch_fused_reg<MODEL_REAL2, false>(g, threads, sm_count, st);
 }
 
 cudaError_t RC_CAT(launch_fid_reg_, RC_NSPIN)(const FidArgs& a, int sm_count, cudaStream_t st) {

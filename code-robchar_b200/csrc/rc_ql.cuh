@@ -16,6 +16,9 @@
 // evaluates 32 noise draws of the SAME controller, so sweep counts are strongly correlated
 // across lanes and divergence stays low.
 #pragma once
+#ifndef RC_QL_RMIN
+#define RC_QL_RMIN 1
+#endif
 #include <math.h>
 #include <float.h>
 #include <string.h>
@@ -65,7 +68,7 @@ RC_HD double wilkinson_g(double dl, double dl1, double el, double dm) {
 template <int N, int L>
 struct QlSweep {
     static RC_HD void run(double (&d)[N], double (&e)[N], double (&zi)[N], double (&zo)[N], int m, double dm,
-                          int mend = -1, double tiny = 1e-280) {
+                          int mend, double tiny, int& rmin) {
         // Wilkinson shift from the leading 2x2 of the block, single-division form:
         // mu = d[L] - e^2 / (delta + sign(delta) sqrt(delta^2 + e^2)),  g = d[m] - mu
         double g = wilkinson_g(d[L], d[L + 1], e[L], dm);
@@ -82,6 +85,7 @@ struct QlSweep {
                 double rinv = rc_rsqrt(h);
                 r = h * rinv;
                 e[i + 1] = r;
+                rmin = hi_word(r) < rmin ? hi_word(r) : rmin;   // smallest new coupling of this sweep (r >= 0)
                 s = f * rinv;
                 c = g * rinv;
                 g = d[i + 1] - p;
@@ -129,7 +133,8 @@ struct QlLevel {
                 }
                 if (m == L) break;
                 if (++it > QL_MAX_SWEEPS) { fail = 1; break; }
-                QlSweep<N, L>::run(d, e, zi, zo, m, dm);
+                int rmin_unused = 0x7fffffff;
+                QlSweep<N, L>::run(d, e, zi, zo, m, dm, -1, 1e-280, rmin_unused);
                 RC_STAT(st->sweeps_per_l[L]++; st->total_sweeps++; st->rotations += m - L;)
             }
             fail |= QlLevel<N, L + 1>::run(d, e, zi, zo, tol
@@ -227,6 +232,47 @@ RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int ou
     const double tol = DBL_EPSILON * anorm;
     const int tolhi = threshold_hi(tol);
     const double tiny = fmin(tol, 1e-280);  // == 1e-280, kept in a register instead of re-materialised per rotation
+#if RC_QL_RMIN
+    // rmin = smallest high word among the couplings the last sweep produced (a full-block sweep rewrites
+    // every interior coupling of the active block), so "no interior split" is ONE integer compare per
+    // trip; the descending scan for the split position only runs when that compare fails (first trip,
+    // and in the rare genuine split).  The block handed to the sweep must be unreduced: a zero interior
+    // coupling would drive g to exactly 0 and break the next rotation.
+    int nact = N, ndone = 0, it = 0, bad = 0, rmin = 0;
+    while (nact > 1) {
+        if (negligible_hi(e[0], tolhi)) {
+            // deflate: eigenvalue d[0] with weight V[in,k] V[out,k]
+            scratch[(size_t)ndone * sstride] = d[0];
+            scratch[(size_t)(N + ndone) * sstride] = zi[0] * zo[0];
+            ++ndone; --nact; it = 0;
+#pragma unroll
+            for (int i = 0; i < N - 1; ++i) { d[i] = d[i + 1]; e[i] = e[i + 1]; zi[i] = zi[i + 1]; zo[i] = zo[i + 1]; }
+        }
+        // sweep in the same trip (lanes that deflated stay converged with the lanes that did not)
+        // unless the new leading off-diagonal is negligible as well
+        if (nact > 1 && !negligible_hi(e[0], tolhi)) {
+            int m = nact - 1;
+            bool split = false;
+            if (rmin < tolhi) {
+                // first negligible off-diagonal inside the active block (descending scan: smallest wins);
+                // compares the high words as integers (ALU pipe) instead of fp64 compares
+#pragma unroll
+                for (int i = N - 2; i >= 1; --i)
+                    if (i < nact - 1 && negligible_hi(e[i], tolhi)) m = i;
+                split = m != nact - 1;
+            }
+            double dm = d[N - 1];
+#pragma unroll
+            for (int i = N - 2; i >= 1; --i)
+                if (i == m) dm = d[i];
+            if (++it > QL_MAX_SWEEPS) { bad = 1; break; }
+            rmin = 0x7fffffff;
+            QlSweep<N, 0>::run(d, e, zi, zo, m, dm, nact - 1, tiny, rmin);
+            if (split) rmin = 0;   // e[m] = 0 stays inside the block until [0, m] is deflated: keep scanning
+            RC_STAT(st->total_sweeps++; st->rotations += m;)
+        }
+    }
+#else
     int nact = N, ndone = 0, it = 0, bad = 0;
     while (nact > 1) {
         if (negligible_hi(e[0], tolhi)) {
@@ -252,10 +298,12 @@ RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int ou
             for (int i = N - 2; i >= 1; --i)
                 if (i == m) dm = d[i];
             if (++it > QL_MAX_SWEEPS) { bad = 1; break; }
-            QlSweep<N, 0>::run(d, e, zi, zo, m, dm, nact - 1, tiny);
+            int rmin_unused = 0x7fffffff;
+            QlSweep<N, 0>::run(d, e, zi, zo, m, dm, nact - 1, tiny, rmin_unused);
             RC_STAT(st->total_sweeps++; st->rotations += m;)
         }
     }
+#endif
     if (bad) { *fail = 1; return NAN; }
     scratch[(size_t)ndone * sstride] = d[0];
     scratch[(size_t)(N + ndone) * sstride] = zi[0] * zo[0];

@@ -54,7 +54,8 @@ int rc_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * noise_model_base.evaluate_noisy_fidelity(x, ham_noisy=True) (noise_model.py:98-109), and
  * LBFGS.fidelity_ss(x, ham_noisy=True) (qnewton.py:383-400) for RC_MODEL_REAL2 / zz.
  * replay_dev == NULL: noise from in-kernel Philox4x32-10 keyed by `seed`, counters from the
- * GLOBAL indices (sigma idx, c_offset + c, b_offset + b) — sharding invariant.
+ * GLOBAL indices (sigma idx, c_offset + c, b_offset + b) — sharding invariant; the 64 bits of each
+ * draw feed a 1024-layer ziggurat (exact N(0,1); csrc/rc_philox.cuh).
  * NaN controller rows give NaN fidelities (mcsim.py:369-374, 443).
  * nonconv_dev: optional device counter (uint64) incremented per non-converged evaluation. */
 int rc_fidelity_mc(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
