@@ -93,8 +93,27 @@ int fused_reg_threads(int n, bool replay, long long B) {
     return top < 128 ? top : 128;
 }
 
-// CTA size of the shared-memory kernels: 128 lanes while four [N][128] arrays leave room for >= 4 CTAs/SM
-static int smem_threads(int n) { return (size_t)4 * n * 128 * sizeof(double) <= 56 * 1024 ? 128 : 64; }
+// CTA size of the shared-memory kernels (each lane owns four [N] double arrays = 32 N bytes): ONE CTA per
+// SM holding as many lanes as fit into the 227 KB of shared memory, rounded down to a multiple of 128
+// (equal warp counts on the four schedulers; measured 5-14 % over several small CTAs, r01h), or to a
+// multiple of 32 when fewer than 256 lanes fit (N >= 29: warp count matters more than balance).
+// RC_SMEM_THREADS (environment) overrides for tuning.
+constexpr size_t SMEM_BYTES_MAX = 227 * 1024;
+constexpr size_t FUSED_STATIC_SMEM = (SMEM_FUSED_MAX_THREADS / 32) * PART_DOUBLES * sizeof(double);   // merge scratch
+static int smem_threads(int n, int cap = SMEM_MAX_THREADS, size_t static_bytes = 0) {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("RC_SMEM_THREADS");
+        env = e ? atoi(e) : 0;
+        if (env < 32 || env > SMEM_MAX_THREADS || (env % 32)) env = 0;
+    }
+    int t = env;
+    if (!t) {
+        const int lanes = (int)((SMEM_BYTES_MAX - static_bytes) / ((size_t)32 * n));
+        t = lanes >= 256 ? lanes / 128 * 128 : lanes / 32 * 32;
+    }
+    return t > cap ? cap : t;
+}
 
 template <int MODEL, bool REPLAY>
 static cudaError_t launch_smem(const FidArgs& a, int sm_count, cudaStream_t st) {
@@ -139,7 +158,7 @@ cudaError_t launch_fidelity(const FidArgs& a, cudaStream_t st) {
 
 template <int MODEL, bool REPLAY>
 static cudaError_t launch_fused_smem(const FusedArgs& g, int sm_count, cudaStream_t st) {
-    const int threads = smem_threads(g.f.N);
+    const int threads = smem_threads(g.f.N, SMEM_FUSED_MAX_THREADS, FUSED_STATIC_SMEM);
     size_t smem = (size_t)4 * g.f.N * threads * sizeof(double);
     auto kern = fidelity_stats_smem_kernel<MODEL, REPLAY>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -178,7 +197,8 @@ static void fused_chunking_threads(long long threads, long long B, long long* ch
     if (*nchunks < 1) *nchunks = 1;
 }
 static void fused_chunking(int nspin, bool replay, long long B, long long* chunk, long long* nchunks) {
-    const long long threads = nspin <= reg_crossover() ? fused_reg_threads(nspin, replay, B) : smem_threads(nspin);
+    const long long threads = nspin <= reg_crossover() ? fused_reg_threads(nspin, replay, B)
+                                                       : smem_threads(nspin, SMEM_FUSED_MAX_THREADS, FUSED_STATIC_SMEM);
     fused_chunking_threads(threads, B, chunk, nchunks);
 }
 
@@ -290,10 +310,9 @@ extern "C" size_t rc_fidelity_stats_workspace_bytes(int64_t nseg, int64_t B) {
     if (nseg <= 0 || B <= 0) return 256;
     // upper bound over every CTA size any path may pick
     long long nmax = 1;
-    const long long sizes[6] = {64, 128, 256, 384, 768, RC_REG_THREADS ? RC_REG_THREADS : 768};
-    for (int k = 0; k < 6; ++k) {
+    for (long long t = 32; t <= 1024; t += 32) {
         long long chunk, nchunks;
-        fused_chunking_threads(sizes[k], B, &chunk, &nchunks);
+        fused_chunking_threads(t, B, &chunk, &nchunks);
         if (nchunks > nmax) nmax = nchunks;
     }
     return (size_t)nseg * nmax * PART_DOUBLES * sizeof(double) + 256;

@@ -154,6 +154,8 @@ __host__ __device__ constexpr int reg_cta_min_blocks(int n, bool replay) {
     return RC_REG_MIN_BLOCKS ? RC_REG_MIN_BLOCKS : (n > 8 ? 1 : (replay ? 3 : 1));
 }
 constexpr int MAX_CTA_WARPS = 32;
+constexpr int SMEM_MAX_THREADS = 768;         // launch bound of the shared-memory evolution kernel
+constexpr int SMEM_FUSED_MAX_THREADS = 512;   // ... and of its fused-statistics variant (more live registers)
 
 template <int N, int MODEL, bool REPLAY>
 __global__ void __launch_bounds__(reg_cta_threads(N, REPLAY), reg_cta_min_blocks(N, REPLAY)) fidelity_reg_kernel(FidArgs a) {
@@ -361,7 +363,7 @@ __device__ __forceinline__ double eval_smem(const FidArgs& a, long long s, long 
 }
 
 template <int MODEL, bool REPLAY>
-__global__ void __launch_bounds__(128) fidelity_smem_kernel(FidArgs a) {
+__global__ void __launch_bounds__(SMEM_MAX_THREADS) fidelity_smem_kernel(FidArgs a) {
     extern __shared__ double sm[];
     const long long K = (long long)draws_per_site(MODEL) * a.N;
     const long long total = (long long)a.S * a.C * a.B;
@@ -373,9 +375,9 @@ __global__ void __launch_bounds__(128) fidelity_smem_kernel(FidArgs a) {
 }
 
 template <int MODEL, bool REPLAY>
-__global__ void __launch_bounds__(128) fidelity_stats_smem_kernel(FusedArgs g) {
+__global__ void __launch_bounds__(SMEM_FUSED_MAX_THREADS) fidelity_stats_smem_kernel(FusedArgs g) {
     extern __shared__ double sm[];
-    __shared__ double scratch[MAX_CTA_WARPS * PART_DOUBLES];
+    __shared__ double scratch[(SMEM_FUSED_MAX_THREADS / 32) * PART_DOUBLES];
     const FidArgs& a = g.f;
     const long long K = (long long)draws_per_site(MODEL) * a.N;
     const long long nseg = (long long)a.S * a.C;

@@ -202,6 +202,44 @@ def test_philox_normals_distribution_and_sharding(rb):
     assert not torch.equal(whole, other)
 
 
+def test_philox_ziggurat_tails_and_bins(rb):
+    """The in-kernel ziggurat is exact in the wedges and the tail, not only in the bulk: equiprobable-bin
+    chi-square and tail counts over 2.3e7 draws (same check as tools/zig_check.cpp on the host build)."""
+    n = 16                                                    # 46 draws per evaluation
+    z = rb.engine.philox_normals(500, n, 2, 500, seed=2024).cpu().numpy()
+    used = np.ones(3 * n, bool); used[[1, 2]] = False
+    v = z[..., used].reshape(-1)
+    N = v.size
+    assert np.isfinite(v).all() and np.abs(v).max() < 7.0
+    nb = 256
+    counts = np.bincount(np.minimum((scipy.stats.norm.cdf(v) * nb).astype(np.int64), nb - 1), minlength=nb)
+    chi2 = ((counts - N / nb) ** 2 / (N / nb)).sum()
+    assert chi2 < scipy.stats.chi2.ppf(1 - 1e-6, nb - 1), chi2
+    for thr in (3.0, 4.0, 4.5):                               # the tail sampler starts at R = 4.0388
+        expect = N * 2 * scipy.stats.norm.sf(thr)
+        got = float((np.abs(v) > thr).sum())
+        assert abs(got - expect) < 5.5 * np.sqrt(expect), (thr, got, expect)
+    assert abs(v.mean()) < 5.5 / np.sqrt(N) and abs(v.var() - 1) < 5.5 * np.sqrt(2.0 / N)
+    assert abs((v ** 4).mean() - 3) < 5.5 * np.sqrt(96.0 / N)
+
+
+@pytest.mark.parametrize("n,B", [(4, 100), (7, 1000), (8, 5000), (9, 300), (12, 700), (16, 5000), (24, 129), (29, 64), (32, 257)])
+def test_fused_statistics_every_kernel_family(rb, n, B):
+    """Streaming (fused) statistics == statistics of the materialised fidelities, in Philox mode, for every
+    kernel family / CTA shape (register kernels N <= 8, shared-memory kernels above, ragged B)."""
+    ctrl = orc.synthetic_controllers(5, n, seed=n)
+    sig = np.array([0.0, 0.04, 0.1])
+    eps = float(orc.compute_dkw_error(0.05, B))
+    kw = dict(seed=77, c_offset=3, b_offset=9, zz=bool(n % 2))
+    f = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, n - 1, **kw)
+    a = rb.engine.stats(f, eps).cpu().numpy()
+    b = rb.engine.fidelity_stats(ctrl, sig, B, n, 0, n - 1, dkw_eps=eps, **kw).cpu().numpy()
+    assert np.abs(a - b).max() < 1e-12
+    m = orc.metrics(f.cpu().numpy(), 0.05)
+    for k, key in enumerate(rb.engine.STAT_KEYS):
+        assert np.abs(b[k] - m[key]).max() < 1e-12, key
+
+
 @pytest.mark.parametrize("B", [1, 2, 31, 100, 1000, 4096, 5000])
 def test_stats_vs_oracle(rb, B):
     rs = np.random.RandomState(B)
