@@ -6,7 +6,7 @@
         --master-port P bench.py --gpus N --steps K --warmup W
 
 One step = one pass of the hot path over one synthetic batch: Philox noise -> perturbed
-Hamiltonians -> fidelities [S][C][B] -> segmented sort + 15 statistics -> per-group top-k ->
+Hamiltonians -> fidelities [S][C][B] -> 15 statistics (sort-free streaming pass) -> per-group top-k ->
 clustered/ordinal ranks -> Kendall tau matrices (+ one all-gather of the statistics for N > 1).
 Default workload `paper_n7` = BASELINE.json configs[2]: nspin=7 0->6, 19 controller groups x 1000
 controllers (the paper's fig-5 sweep size per problem), S=11 sigma_sim levels, B=100 draws.
@@ -209,7 +209,7 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     fids = torch.empty((S, C_local, B), dtype=torch.float64, device=dev)
     topk = min(100, cg)
-    fused = B > 512   # long segments: streaming statistics (no fidelity tensor); short ones: materialise + warp sort
+    fused = B > 512   # long segments: streaming statistics (no fidelity tensor); short ones: materialise + sort-free statistics pass
     fid_events = []
 
     def step(seed, timed=False):
@@ -224,7 +224,7 @@ def run_ours(args):
                             check_convergence=False)
             if timed:
                 e1.record(); fid_events.append((e0, e1))
-            st = eng.stats(fids, eps, check_legal=False)
+            st = eng.stats_unsorted(fids, eps, check_legal=False)   # sort-free streaming pass (rc_stats_unsorted)
         tau, sel, wsel = eng.grouped_rank_consistency(st[0], groups, topk=topk)
         arim, arim_std = eng.arim_bootstrap_device(wsel, 100, seed=seed)     # fig-5 ARIM + bootstrap error bar
         if world > 1:

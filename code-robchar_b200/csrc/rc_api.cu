@@ -1,5 +1,6 @@
 // Host-buffer pipeline entry point (what MCDataSim.get_metrics_dict computes from scratch,
 // mcsim.py:463-510) and the FP64 roofline micro-benchmark.
+#include <stdlib.h>
 #include "rc_common.cuh"
 
 using namespace rc;
@@ -31,6 +32,34 @@ static cudaError_t keep_pool_memory() {
     e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     if (e == cudaSuccess) done[dev] = true;
     return e;
+}
+
+// Second stream + events of the host sweep's copy pipeline, created once per (host thread, device).
+struct SweepAsync {
+    static constexpr int MAX_CHUNKS = 16;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev[MAX_CHUNKS] = {};
+    cudaEvent_t done = nullptr;
+};
+static cudaError_t sweep_async(SweepAsync** out) {
+    static thread_local SweepAsync cache[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    SweepAsync& a = cache[dev];
+    if (!a.copy) {
+        e = cudaStreamCreateWithFlags(&a.copy, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+        for (int k = 0; k < SweepAsync::MAX_CHUNKS; ++k) {
+            e = cudaEventCreateWithFlags(&a.ev[k], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        e = cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    *out = &a;
+    return cudaSuccess;
 }
 
 // 8 independent dependent-FMA chains per thread; 2 flops per DFMA.
@@ -106,6 +135,9 @@ static int sweep_host_impl(const double* ctrl_host, int64_t C, int nspin, int in
     unsigned long long* illegal = nonconv + 1;
     if (stats_host || want_rank) RC_CUDA_TRY(stats.alloc((size_t)RC_NUM_STATS * nseg * 8));
     int rcode;
+    SweepAsync* async = nullptr;
+    cudaStream_t copy = nullptr;
+    bool stats_copied = false;
     if (fused) {
         size_t wb = rc_fidelity_stats_workspace_bytes(nseg, B);
         RC_CUDA_TRY(ws.alloc(wb));
@@ -114,21 +146,52 @@ static int sweep_host_impl(const double* ctrl_host, int64_t C, int nspin, int in
                                   stats.as<double>(), nonconv, ws.p, wb, st);
         if (rcode) return rcode;
     } else {
+        // Materialising path: evolution, then the sort-free statistics pass over the fresh fidelities (mostly
+        // still in L2).  Large sweeps are cut into a few sigma chunks so that the D2H copies of chunk k (its
+        // columns of the statistics tensor, its slab of the fidelity tensor) run on a second stream underneath
+        // the evolution of chunk k+1; results do not depend on the chunking (global sigma indices feed the
+        // Philox counters).
+        const bool want_stats = stats_host || want_rank;
         RC_CUDA_TRY(fids.alloc((size_t)total * 8));
-        rcode = rc_fidelity_mc(ctrl.as<double>(), C, nspin, inspin, outspin, sigma.as<double>(), S, B, model, zz, seed,
-                               c_offset, b_offset, replay_host ? replay.as<double>() : nullptr, fids.as<double>(), nonconv, st);
-        if (rcode) return rcode;
-        // the reference dumps the UNSORTED tensor to .mc before any metric sorts it (mcsim.py:457-459)
-        if (fids_host) RC_CUDA_TRY(cudaMemcpyAsync(fids_host, fids.p, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
-        if (stats_host || want_rank) {
-            size_t wb = rc_stats_workspace_bytes(nseg, B);
-            if (wb == 0) return set_error(RC_ERR_BAD_ARG, "sweep: B too large for the sort path (use fused)");
-            RC_CUDA_TRY(ws.alloc(wb));
-            rcode = rc_stats(fids.as<double>(), nseg, B, dkw_eps, stats.as<double>(), nullptr, illegal, ws.p, wb, st);
-            if (rcode) return rcode;
+        int nch = 1;
+        if (S >= 2 && total >= 2000000) {
+            nch = S < 4 ? S : 4;
+            if (const char* e = getenv("RC_SWEEP_CHUNKS")) { int v = atoi(e); if (v >= 1) nch = v < S ? v : S; }
+            if (nch > SweepAsync::MAX_CHUNKS) nch = SweepAsync::MAX_CHUNKS;
         }
+        if (nch > 1) {
+            RC_CUDA_TRY(sweep_async(&async));
+            copy = async->copy;
+        }
+        for (int k = 0; k < nch; ++k) {
+            const long long s0 = (long long)S * k / nch, s1 = (long long)S * (k + 1) / nch, Sk = s1 - s0;
+            const long long e0 = s0 * C * B;
+            rcode = fidelity_mc_impl("sweep", ctrl.as<double>(), C, nspin, inspin, outspin, sigma.as<double>() + s0, (int)Sk,
+                                     B, model, zz, seed, c_offset, b_offset,
+                                     replay_host ? replay.as<double>() + e0 * K : nullptr, fids.as<double>() + e0, nonconv,
+                                     (int)s0, st);
+            if (rcode) return rcode;
+            if (want_stats) {
+                rcode = stats_unsorted_impl(fids.as<double>() + e0, Sk * C, B, dkw_eps, stats.as<double>() + s0 * C, nseg,
+                                            illegal, st);
+                if (rcode) return rcode;
+            }
+            cudaStream_t cs = st;
+            if (nch > 1) {
+                RC_CUDA_TRY(cudaEventRecord(async->ev[k], st));
+                RC_CUDA_TRY(cudaStreamWaitEvent(copy, async->ev[k], 0));
+                cs = copy;
+            }
+            // the reference dumps the UNSORTED tensor to .mc before any metric sorts it (mcsim.py:457-459)
+            if (fids_host)
+                RC_CUDA_TRY(cudaMemcpyAsync(fids_host + e0, fids.as<double>() + e0, (size_t)Sk * C * B * 8, cudaMemcpyDeviceToHost, cs));
+            if (stats_host)
+                RC_CUDA_TRY(cudaMemcpy2DAsync(stats_host + s0 * C, (size_t)nseg * 8, stats.as<double>() + s0 * C, (size_t)nseg * 8,
+                                              (size_t)Sk * C * 8, RC_NUM_STATS, cudaMemcpyDeviceToHost, cs));
+        }
+        stats_copied = true;
     }
-    if (stats_host)
+    if (stats_host && !stats_copied)
         RC_CUDA_TRY(cudaMemcpyAsync(stats_host, stats.p, (size_t)RC_NUM_STATS * nseg * 8, cudaMemcpyDeviceToHost, st));
     if (want_rank) {
         const int64_t Cg = C / G, k = topk < Cg ? topk : Cg;
@@ -154,6 +217,10 @@ static int sweep_host_impl(const double* ctrl_host, int64_t C, int nspin, int in
     }
     unsigned long long hc[2] = {0, 0};
     RC_CUDA_TRY(cudaMemcpyAsync(hc, counters.p, 16, cudaMemcpyDeviceToHost, st));
+    if (copy) {   // the stream-ordered frees of the scratch buffers (on st) must follow the copies that read them
+        RC_CUDA_TRY(cudaEventRecord(async->done, copy));
+        RC_CUDA_TRY(cudaStreamWaitEvent(st, async->done, 0));
+    }
     RC_CUDA_TRY(cudaStreamSynchronize(st));
     if (hc[0]) return set_error(RC_ERR_NONCONV, "eigensolver did not converge for %llu evaluations (NaN written)", hc[0]);
     if (hc[1]) return set_error(RC_ERR_ILLEGAL_FIDS, "illegal fids values - must be in [0,1] (%llu samples)", hc[1]);

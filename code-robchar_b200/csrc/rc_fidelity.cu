@@ -270,22 +270,48 @@ extern "C" int rc_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     return RC_OK;
 }
 
+namespace rc {
+// Shared implementation of rc_fidelity_mc.  The host sweep (rc_api.cu) also calls it once per sigma chunk:
+// sigma_dev / fids_dev / replay_dev then point at the chunk, S is the chunk's level count and s_offset its
+// first level (the Philox counters use the global level index, so chunking does not change the draws).
+int fidelity_mc_impl(const char* who, const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
+                     const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed, int64_t c_offset,
+                     int64_t b_offset, const double* replay_dev, double* fids_dev, unsigned long long* nonconv_dev,
+                     int s_offset, cudaStream_t st) {
+    int rcode = check_model_args(C, nspin, inspin, outspin, S, B, model);
+    if (rcode) return rcode;
+    if ((long long)S * C * B == 0) return RC_OK;
+    if (!ctrl_dev || !sigma_dev || !fids_dev) return set_error(RC_ERR_NULL, "%s: null ctrl/sigma/fids pointer", who);
+    if (s_offset < 0 || s_offset + S > 65535) return set_error(RC_ERR_BAD_ARG, "%s: sigma level range exceeds 65535", who);
+    FidArgs a = {};
+    a.ctrl = ctrl_dev; a.sigma = sigma_dev; a.replay = replay_dev; a.fids = fids_dev; a.nonconv = nonconv_dev;
+    a.C = C; a.B = B; a.S = S; a.N = nspin; a.in = inspin; a.out = outspin; a.model = model; a.zz = zz;
+    a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+    a.c_offset = c_offset; a.b_offset = b_offset; a.s_offset = s_offset;
+    RC_CUDA_TRY(zig_tables_device(&a.zig));
+    RC_CUDA_TRY(launch_fidelity(a, st));
+    return RC_OK;
+}
+}  // namespace rc
+
 extern "C" int rc_fidelity_mc(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
                               const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed,
                               int64_t c_offset, int64_t b_offset, const double* replay_dev, double* fids_dev,
                               unsigned long long* nonconv_dev, void* stream) {
-    int rcode = check_model_args(C, nspin, inspin, outspin, S, B, model);
-    if (rcode) return rcode;
-    if ((long long)S * C * B == 0) return RC_OK;
-    if (!ctrl_dev || !sigma_dev || !fids_dev) return set_error(RC_ERR_NULL, "rc_fidelity_mc: null ctrl/sigma/fids pointer");
-    FidArgs a;
-    a.ctrl = ctrl_dev; a.sigma = sigma_dev; a.replay = replay_dev; a.fids = fids_dev; a.nonconv = nonconv_dev;
-    a.C = C; a.B = B; a.S = S; a.N = nspin; a.in = inspin; a.out = outspin; a.model = model; a.zz = zz;
-    a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
-    a.c_offset = c_offset; a.b_offset = b_offset;
-    RC_CUDA_TRY(zig_tables_device(&a.zig));
-    RC_CUDA_TRY(launch_fidelity(a, (cudaStream_t)stream));
-    return RC_OK;
+    return fidelity_mc_impl("rc_fidelity_mc", ctrl_dev, C, nspin, inspin, outspin, sigma_dev, S, B, model, zz, seed,
+                            c_offset, b_offset, replay_dev, fids_dev, nonconv_dev, 0, (cudaStream_t)stream);
+}
+
+extern "C" int rc_fidelity_mc_stats(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
+                                    const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed,
+                                    int64_t c_offset, int64_t b_offset, const double* replay_dev, double dkw_eps,
+                                    double* fids_dev, double* stats_dev, unsigned long long* nonconv_dev,
+                                    unsigned long long* illegal_dev, void* stream) {
+    if ((long long)S * C * B > 0 && !stats_dev) return set_error(RC_ERR_NULL, "rc_fidelity_mc_stats: null stats pointer");
+    int rcode = fidelity_mc_impl("rc_fidelity_mc_stats", ctrl_dev, C, nspin, inspin, outspin, sigma_dev, S, B, model, zz,
+                                 seed, c_offset, b_offset, replay_dev, fids_dev, nonconv_dev, 0, (cudaStream_t)stream);
+    if (rcode || (long long)S * C * B == 0) return rcode;
+    return rc_stats_unsorted(fids_dev, (int64_t)S * C, B, dkw_eps, stats_dev, illegal_dev, stream);
 }
 
 extern "C" int rc_philox_normals(int64_t C, int nspin, int S, int64_t B, int model, uint64_t seed, int64_t c_offset,
@@ -329,7 +355,7 @@ extern "C" int rc_fidelity_stats(const double* ctrl_dev, int64_t C, int nspin, i
     if (nseg == 0) return RC_OK;
     if (B < 1) return set_error(RC_ERR_BAD_ARG, "rc_fidelity_stats: B must be >= 1");
     if (!ctrl_dev || !sigma_dev || !stats_dev) return set_error(RC_ERR_NULL, "rc_fidelity_stats: null ctrl/sigma/stats pointer");
-    FusedArgs g;
+    FusedArgs g = {};
     FidArgs& a = g.f;
     a.ctrl = ctrl_dev; a.sigma = sigma_dev; a.replay = replay_dev; a.fids = nullptr; a.nonconv = nonconv_dev;
     a.C = C; a.B = B; a.S = S; a.N = nspin; a.in = inspin; a.out = outspin; a.model = model; a.zz = zz;

@@ -29,6 +29,7 @@ struct FidArgs {
     uint32_t seed_lo, seed_hi;
     long long c_offset, b_offset;  // global index of this shard's first controller / draw (Philox counters)
     ZigTables zig;                 // ziggurat tables in global memory (Philox mode), see zig_tables_device()
+    int s_offset;                  // global index of this launch's first sigma level (sigma-chunked host sweep)
 };
 
 __host__ __device__ constexpr int draws_per_site(int model) { return model == MODEL_COMPLEX3 ? 3 : 2; }
@@ -73,7 +74,7 @@ __device__ __forceinline__ void build_tridiagonal(const double* __restrict__ x, 
 
 RC_HD NoiseKey noise_key(const FidArgs& a, long long s, long long c, long long b) {
     NoiseKey k;
-    k.seed_lo = a.seed_lo; k.seed_hi = a.seed_hi; k.sidx = (uint32_t)s;
+    k.seed_lo = a.seed_lo; k.seed_hi = a.seed_hi; k.sidx = (uint32_t)(s + a.s_offset);
     k.cidx = (uint64_t)(c + a.c_offset); k.bidx = (uint64_t)(b + a.b_offset);
     return k;
 }

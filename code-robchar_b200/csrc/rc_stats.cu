@@ -247,6 +247,208 @@ __global__ void __launch_bounds__(128) sort_stats_warp_kernel(const double* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sort-free statistics (rc_stats_unsorted): the sweep only needs the VALUES of the 15 metrics, and none of
+// them depends on the order of the samples once W is written as mean(1 - v) — the value of wd_from_ideal's
+// sorted telescoping sum (wd_sortof_fast_implementation.py:105-114) up to rounding (<= B ulp).  Without the
+// bitonic network the per-segment work drops from ~2900 to ~300 warp instructions and the kernel becomes a
+// single streaming pass over the fidelity tensor (8 B/sample, HBM/L2 bound).
+//   B <= 32*E (E <= 16): one warp per segment, samples in registers, two passes from registers
+//   longer segments    : one CTA per segment, second pass re-reads (L2)
+// Q = -(#v >= thr)/B (mcsim.py:144-146), std = two-pass population std (np.std, mcsim.py:147), worst case
+// = -min (mcsim.py:148), each for v = f, clip(f - eps), clip(f + eps) (mcsim.py:483-485); NaN samples give
+// NaN W/std/worst case and count as below threshold, as in numpy.  Fixed reduction trees: deterministic.
+// ---------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(256, E <= 4 ? 4 : (E <= 8 ? 3 : 2)) stats_unsorted_warp_kernel(const double* __restrict__ fids, long long nseg, int B,
+                                                                  double eps, long long stat_stride,
+                                                                  double* __restrict__ stats, unsigned long long* illegal) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const double nB = (double)B;
+    // software pipeline: the samples of the warp's NEXT segment are requested before the current one is
+    // reduced, so the HBM/L2 round trip hides behind the dependent shuffle/divide chain of the reduction
+    double fn[E];
+    if (warp0 < nseg) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) fn[j] = (j * 32 + lane < B) ? __ldcs(fids + warp0 * (long long)B + j * 32 + lane) : 1.0;
+    }
+    for (long long seg = warp0; seg < nseg; seg += nwarps) {
+        double f[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) f[j] = fn[j];
+        if (seg + nwarps < nseg) {
+            const double* nsrc = fids + (seg + nwarps) * (long long)B;
+#pragma unroll
+            for (int j = 0; j < E; ++j) fn[j] = (j * 32 + lane < B) ? __ldcs(nsrc + j * 32 + lane) : 1.0;
+        }
+        double s1[3] = {0.0, 0.0, 0.0}, sv[3] = {0.0, 0.0, 0.0};
+        int c95[3] = {0, 0, 0}, c98[3] = {0, 0, 0};
+        double mn = INFINITY;
+        unsigned flags = 0;   // bit 0: NaN seen; bits 1..: illegal samples
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            if (j * 32 + lane < B) {
+                const double v[3] = {f[j], clip01(f[j] - eps), clip01(f[j] + eps)};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    s1[k] += 1.0 - v[k];
+                    sv[k] += v[k];
+                    c95[k] += v[k] >= 0.95;
+                    c98[k] += v[k] >= 0.98;
+                }
+                mn = fmin(mn, f[j]);
+                flags |= (f[j] != f[j]) ? 1u : 0u;
+                flags += fabs(f[j] - 1e-8) > 1.0 ? 2u : 0u;   // check_fidtype (wd_sortof_fast_implementation.py:23)
+            }
+        }
+        double mean[3], m2[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) mean[k] = warp_sum(sv[k]) / nB;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            if (j * 32 + lane < B) {
+                const double v[3] = {f[j], clip01(f[j] - eps), clip01(f[j] + eps)};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double dlt = v[k] - mean[k];
+                    m2[k] = fma(dlt, dlt, m2[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            s1[k] = warp_sum(s1[k]);
+            m2[k] = warp_sum(m2[k]);
+            c95[k] = __reduce_add_sync(0xffffffffu, c95[k]);
+            c98[k] = __reduce_add_sync(0xffffffffu, c98[k]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if (__reduce_or_sync(0xffffffffu, flags & 1u)) mn = NAN;
+        const unsigned bad = __reduce_add_sync(0xffffffffu, flags >> 1);
+        if (bad && illegal && lane == 0) atomicAdd(illegal, (unsigned long long)bad);
+        if (lane < 3) {
+            const int k = lane;
+            const double mk = k == 0 ? mn : clip01(mn + (k == 1 ? -eps : eps));
+            const double w = k == 0 ? s1[0] : (k == 1 ? s1[1] : s1[2]);
+            const double a95 = (double)(k == 0 ? c95[0] : (k == 1 ? c95[1] : c95[2]));
+            const double a98 = (double)(k == 0 ? c98[0] : (k == 1 ? c98[1] : c98[2]));
+            const double mm = k == 0 ? m2[0] : (k == 1 ? m2[1] : m2[2]);
+            double* out = stats + seg;
+            out[(ST_W + k) * stat_stride] = w / nB;
+            out[(ST_Q95 + k) * stat_stride] = -1.0 * (a95 / nB);
+            out[(ST_Q98 + k) * stat_stride] = -1.0 * (a98 / nB);
+            out[(ST_STD + k) * stat_stride] = sqrt(mm / nB);
+            out[(ST_WC + k) * stat_stride] = -mk;
+        }
+    }
+}
+
+// One CTA per (long) segment.
+__global__ void __launch_bounds__(256) stats_unsorted_block_kernel(const double* __restrict__ fids, long long nseg, long long B,
+                                                                   double eps, long long stat_stride,
+                                                                   double* __restrict__ stats, unsigned long long* illegal) {
+    __shared__ double scratch[32 * 12];
+    __shared__ double smn[8];
+    __shared__ unsigned sflags[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const double nB = (double)B;
+    for (long long seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+        const double* src = fids + seg * B;
+        double acc[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+        double mn = INFINITY;
+        unsigned nan = 0;
+        unsigned long long bad = 0;
+        for (long long i = threadIdx.x; i < B; i += blockDim.x) {
+            const double f = __ldg(src + i);
+            const double v[3] = {f, clip01(f - eps), clip01(f + eps)};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                acc[k] += 1.0 - v[k];
+                acc[3 + k] += v[k];
+                acc[6 + k] += (v[k] >= 0.95) ? 1.0 : 0.0;
+                acc[9 + k] += (v[k] >= 0.98) ? 1.0 : 0.0;
+            }
+            mn = fmin(mn, f);
+            nan |= (f != f) ? 1u : 0u;
+            if (fabs(f - 1e-8) > 1.0) ++bad;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        nan = __reduce_or_sync(0xffffffffu, nan);
+        __syncthreads();
+        if (lane == 0) { smn[warp] = mn; sflags[warp] = nan; }
+        block_sum<12>(acc, scratch);   // contains the barriers that publish smn / sflags
+        if (bad && illegal) atomicAdd(illegal, bad);
+        double m2[3] = {0.0, 0.0, 0.0};
+        const double mean[3] = {acc[3] / nB, acc[4] / nB, acc[5] / nB};
+        for (long long i = threadIdx.x; i < B; i += blockDim.x) {
+            const double f = __ldg(src + i);
+            const double v[3] = {f, clip01(f - eps), clip01(f + eps)};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double dlt = v[k] - mean[k];
+                m2[k] = fma(dlt, dlt, m2[k]);
+            }
+        }
+        block_sum<3>(m2, scratch);
+        if (threadIdx.x < 3) {
+            const int k = threadIdx.x;
+            double mnb = smn[0];
+            unsigned anynan = sflags[0];
+            for (int w = 1; w < nwarp; ++w) { mnb = fmin(mnb, smn[w]); anynan |= sflags[w]; }
+            if (anynan) mnb = NAN;
+            const double mk = k == 0 ? mnb : clip01(mnb + (k == 1 ? -eps : eps));
+            double* out = stats + seg;
+            out[(ST_W + k) * stat_stride] = acc[k] / nB;
+            out[(ST_Q95 + k) * stat_stride] = -1.0 * (acc[6 + k] / nB);
+            out[(ST_Q98 + k) * stat_stride] = -1.0 * (acc[9 + k] / nB);
+            out[(ST_STD + k) * stat_stride] = sqrt(m2[k] / nB);
+            out[(ST_WC + k) * stat_stride] = -mk;
+        }
+        __syncthreads();
+    }
+}
+
+template <int E>
+static cudaError_t launch_stats_unsorted_warp(const double* fids, long long nseg, int B, double eps, long long stride,
+                                              double* stats, unsigned long long* illegal, int sm, cudaStream_t st) {
+    int occ = 0;
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stats_unsorted_warp_kernel<E>, 256, 0);
+    if (err != cudaSuccess) return err;
+    if (occ < 1) occ = 1;
+    long long grid = (long long)sm * occ;
+    const long long need = (nseg + 7) / 8;
+    if (grid > need) grid = need;
+    stats_unsorted_warp_kernel<E><<<(unsigned)grid, 256, 0, st>>>(fids, nseg, B, eps, stride, stats, illegal);
+    return cudaGetLastError();
+}
+
+int stats_unsorted_impl(const double* fids_dev, int64_t nseg, int64_t B, double dkw_eps, double* stats_dev,
+                        int64_t stat_stride, unsigned long long* illegal_dev, cudaStream_t st) {
+    if (nseg < 0 || B < 1) return set_error(RC_ERR_BAD_ARG, "rc_stats_unsorted: nseg=%lld B=%lld", (long long)nseg, (long long)B);
+    if (nseg == 0) return RC_OK;
+    if (!fids_dev || !stats_dev) return set_error(RC_ERR_NULL, "rc_stats_unsorted: null fids/stats pointer");
+    const int sm = device_sm_count();
+    cudaError_t err;
+    const int b = (int)(B <= 512 ? B : 0);
+    if (B > 512) {
+        long long grid = nseg < (long long)sm * 8 ? nseg : (long long)sm * 8;
+        stats_unsorted_block_kernel<<<(unsigned)grid, 256, 0, st>>>(fids_dev, nseg, B, dkw_eps, stat_stride, stats_dev, illegal_dev);
+        err = cudaGetLastError();
+    } else if (b <= 32) err = launch_stats_unsorted_warp<1>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);
+    else if (b <= 64) err = launch_stats_unsorted_warp<2>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);
+    else if (b <= 128) err = launch_stats_unsorted_warp<4>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);
+    else if (b <= 256) err = launch_stats_unsorted_warp<8>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);
+    else err = launch_stats_unsorted_warp<16>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);
+    RC_CUDA_TRY(err);
+    return RC_OK;
+}
+
 template <int E>
 static cudaError_t launch_sort_stats_warp(const double* fids, long long nseg, int B, double eps, double* stats,
                                           double* sorted_out, unsigned long long* illegal, int sm, cudaStream_t st) {
@@ -328,6 +530,11 @@ static size_t cub_temp_bytes(long long chunk_segs, long long B) {
 }  // namespace rc
 
 using namespace rc;
+
+extern "C" int rc_stats_unsorted(const double* fids_dev, int64_t nseg, int64_t B, double dkw_eps, double* stats_dev,
+                                 unsigned long long* illegal_dev, void* stream) {
+    return stats_unsorted_impl(fids_dev, nseg, B, dkw_eps, stats_dev, nseg, illegal_dev, (cudaStream_t)stream);
+}
 
 extern "C" size_t rc_stats_workspace_bytes(int64_t nseg, int64_t B) {
     if (nseg <= 0 || B <= SMEM_SORT_MAX) return 256;

@@ -109,6 +109,55 @@ def fidelity_mc(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, *, 
     return out
 
 
+def fidelity_mc_stats(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, *, dkw_eps: float = 0.0,
+                      model: int = MODEL_COMPLEX3, zz: bool = False, seed: int = 0, c_offset: int = 0, b_offset: int = 0,
+                      replay=None, out=None, counters: Counters | None = None, check: bool = True):
+    """Fidelity tensor [S][C][B] (mcsim.py:422-456) AND its [15][S][C] statistics (mcsim.py:463-510) in one C
+    call (rc_fidelity_mc_stats: evolution kernel + the sort-free statistics pass).  Returns (fids, stats)."""
+    dev = require_cuda()
+    ctrl = _f64(ctrl, dev)
+    sigmas = _f64(sigmas, dev).reshape(-1)
+    if ctrl.dim() != 2 or ctrl.shape[1] != nspin + 1:
+        raise ValueError(f"ctrl must be [C][{nspin + 1}], got {tuple(ctrl.shape)}")
+    Cn, S = ctrl.shape[0], sigmas.shape[0]
+    if replay is not None:
+        replay = _f64(replay, dev)
+        K = draws_per_eval(nspin, model)
+        if replay.numel() != S * Cn * B * K:
+            raise ValueError(f"replay must hold S*C*B*{K} standard normals")
+    if out is None:
+        out = torch.empty((S, Cn, B), dtype=torch.float64, device=dev)
+    st = torch.empty((NUM_STATS, S, Cn), dtype=torch.float64, device=dev)
+    own = counters is None
+    if own:
+        counters = Counters(dev)
+    _lib.check(lib().rc_fidelity_mc_stats(_ptr(ctrl), Cn, nspin, inspin, outspin, _ptr(sigmas), S, B, model,
+                                          int(bool(zz)), C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, _ptr(replay),
+                                          float(dkw_eps), _ptr(out), _ptr(st), counters.nonconv_ptr, counters.illegal_ptr,
+                                          _stream()))
+    _count(2)
+    if own and check:
+        counters.raise_if_set()
+    return out, st
+
+
+def stats_unsorted(fids: torch.Tensor, dkw_eps: float = 0.0, *, check_legal: bool = True) -> torch.Tensor:
+    """[15, *lead] statistics of fids[*lead, B] without sorting (rc_stats_unsorted): same values as stats()
+    up to rounding of W and std; counts and minimum identical.  fids is left untouched."""
+    dev = require_cuda()
+    fids = _f64(fids, dev) if not (isinstance(fids, torch.Tensor) and fids.is_cuda and fids.dtype == torch.float64
+                                   and fids.is_contiguous()) else fids
+    lead, B = tuple(fids.shape[:-1]), fids.shape[-1]
+    nseg = int(np.prod(lead)) if lead else 1
+    out = torch.empty((NUM_STATS,) + lead, dtype=torch.float64, device=dev)
+    cnt = Counters(dev)
+    _lib.check(lib().rc_stats_unsorted(_ptr(fids), nseg, B, float(dkw_eps), _ptr(out), cnt.illegal_ptr, _stream()))
+    _count(1)
+    if check_legal:
+        cnt.raise_if_set()
+    return out
+
+
 def philox_normals(C_: int, nspin: int, S: int, B: int, *, model: int = MODEL_COMPLEX3, seed: int = 0,
                    c_offset: int = 0, b_offset: int = 0) -> torch.Tensor:
     dev = require_cuda()
@@ -329,7 +378,7 @@ def robustness_sweep_host(ctrl: np.ndarray, sigmas: np.ndarray, B: int, nspin: i
                                          C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, float(dkw_eps),
                                          int(bool(fused)), groups, topk, float(alpha_cluster), vp(st), vp(tau), vp(sel),
                                          int(nboot), vp(ar), vp(ars), _stream()))
-    _count(12)  # evolution + sort/stats + the 9 ranking kernels + ARIM bootstrap
+    _count(12)  # evolution + (finalize when fused | sort-free statistics otherwise) + 9 ranking kernels + ARIM bootstrap (per sigma chunk: +2)
     return st, tau, sel, ar, ars
 
 

@@ -63,6 +63,15 @@ int rc_fidelity_mc(const double* ctrl_dev, int64_t C, int nspin, int inspin, int
                    int64_t c_offset, int64_t b_offset, const double* replay_dev, double* fids_dev,
                    unsigned long long* nonconv_dev, void* stream);
 
+/* rc_fidelity_mc followed by rc_stats_unsorted on the same stream: the fidelity tensor
+ * (get_algo_fid_dist, mcsim.py:422-460) and the 15 metric tensors get_metrics_dict derives from it
+ * (mcsim.py:463-510).  fids_dev [S][C][B] (the unsorted `.mc` tensor), stats_dev [15][S][C]. */
+int rc_fidelity_mc_stats(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
+                         const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed,
+                         int64_t c_offset, int64_t b_offset, const double* replay_dev, double dkw_eps,
+                         double* fids_dev, double* stats_dev, unsigned long long* nonconv_dev,
+                         unsigned long long* illegal_dev, void* stream);
+
 /* The standard normals rc_fidelity_mc's Philox mode uses, written in replay layout [S][C][B][K]
  * (discarded site-0 coupling slots are zero).  Lets callers replay a GPU sweep through the
  * reference CPU path. */
@@ -81,6 +90,14 @@ size_t rc_stats_workspace_bytes(int64_t nseg, int64_t B);
 int rc_stats(const double* fids_dev, int64_t nseg, int64_t B, double dkw_eps, double* stats_dev,
              double* sorted_dev, unsigned long long* illegal_dev, void* workspace_dev, size_t workspace_bytes,
              void* stream);
+
+/* The same 15 statistics WITHOUT sorting: none of them depends on the order of the samples once W is
+ * written as mean(1 - f), the value of wd_from_ideal's sorted telescoping sum
+ * (wd_sortof_fast_implementation.py:105-114) up to rounding; two-pass population std, exact threshold
+ * counts and minimum.  One streaming pass over fids_dev (8 B/sample, HBM bound) instead of a sort:
+ * what the sweep entry points use.  fids_dev is not modified.  stats_dev: [15][nseg]. */
+int rc_stats_unsorted(const double* fids_dev, int64_t nseg, int64_t B, double dkw_eps, double* stats_dev,
+                      unsigned long long* illegal_dev, void* stream);
 
 /* Fused evolution + statistics that never materialises the fidelity tensor (streaming moments;
  * W = mean(1 - f), identical to the sorted formula up to rounding).  Same arguments as

@@ -266,6 +266,85 @@ def test_stats_vs_oracle(rb, B):
     assert np.array_equal(t.cpu().numpy(), np.sort(f[:2], axis=-1))
 
 
+@pytest.mark.parametrize("n,B,C", [(4, 1, 70), (5, 2, 45), (7, 31, 9), (7, 32, 9), (6, 33, 9), (7, 100, 40), (8, 257, 7),
+                                   (3, 1000, 5), (7, 5000, 3), (9, 100, 12), (16, 300, 5), (32, 65, 5)])
+@pytest.mark.parametrize("replay", [False, True])
+def test_fidelity_mc_stats_vs_oracle(rb, n, B, C, replay):
+    """rc_fidelity_mc_stats (evolution + sort-free statistics): the fidelity tensor is bit-identical to
+    rc_fidelity_mc's and the statistics match the oracle's metrics of that tensor (sorted W1 formula, np.std,
+    counts, minimum) — for segments shorter than, equal to and longer than a warp, both statistics kernels
+    (warp per segment <= 512, CTA per segment above), both evolution kernel families, NaN controllers included."""
+    ctrl = orc.synthetic_controllers(C, n, seed=n + B)
+    if C > 4:
+        ctrl[3] = np.nan                                       # missing controller (mcsim.py:369-374)
+    sig = np.array([0.0, 0.03, 0.1])
+    eps = float(orc.compute_dkw_error(0.05, B))
+    kw = dict(seed=11, c_offset=2, b_offset=5, zz=bool(n % 2), model=n % 2)
+    if replay:
+        K = rb.engine.draws_per_eval(n, kw["model"])
+        kw["replay"] = np.random.RandomState(B).standard_normal((3, C, B, K))
+    f0 = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, n - 1, **kw)
+    f1, st = rb.engine.fidelity_mc_stats(ctrl, sig, B, n, 0, n - 1, dkw_eps=eps, **kw)
+    f2, st2 = rb.engine.fidelity_mc_stats(ctrl, sig, B, n, 0, n - 1, dkw_eps=eps, **kw)
+    assert torch.equal(f0.nan_to_num(nan=-7.0), f1.nan_to_num(nan=-7.0))
+    assert torch.equal(st.nan_to_num(nan=-7.0), st2.nan_to_num(nan=-7.0))      # deterministic
+    st = st.cpu().numpy()
+    m = orc.metrics(f0.cpu().numpy(), 0.05)
+    for k, key in enumerate(rb.engine.STAT_KEYS):
+        a, b = st[k], m[key]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), key
+        ok = ~np.isnan(b)
+        if key.startswith("Q th.") or key.startswith("worst"):
+            assert np.array_equal(a[ok], b[ok]), key
+        else:
+            assert np.abs(a[ok] - b[ok]).max() < 1e-12, key
+    if C > 4:
+        assert np.isnan(st[0][:, 3]).all() and np.isnan(st[9][:, 3]).all() and np.isnan(st[12][:, 3]).all()
+
+
+def test_fidelity_mc_stats_errors_and_empty(rb):
+    n = 4
+    ctrl = orc.synthetic_controllers(3, n)
+    with pytest.raises(ValueError):
+        rb.engine.fidelity_mc_stats(ctrl[:, :3], np.zeros(1), 4, n, 0, 2)
+    f, st = rb.engine.fidelity_mc_stats(ctrl[:0], np.zeros(2), 4, n, 0, 2)        # empty sweep
+    assert f.shape == (2, 0, 4) and st.shape == (15, 2, 0)
+
+
+@pytest.mark.parametrize("B", [1, 2, 31, 33, 100, 128, 129, 500, 512, 513, 1000, 5000])
+def test_stats_unsorted_vs_oracle(rb, B):
+    """rc_stats_unsorted on arbitrary samples (exact 0 / 1 rows, a NaN row, values on the thresholds) == the
+    oracle's metrics (which sort, as the reference does) to 1e-12; counts and minimum exactly; input untouched."""
+    rs = np.random.RandomState(B)
+    S, C = 3, 17
+    f = np.clip(rs.normal(0.93, 0.05, (S, C, B)), 0, 1)
+    f[0, 3] = 1.0
+    f[1, 5] = 0.0
+    f[2, 7] = np.nan
+    f[1, 9] = 0.95
+    f[2, 11, 0] = np.nan                                    # a single NaN sample poisons W/std/worst case only
+    eps = float(orc.compute_dkw_error(0.05, B))
+    t = torch.as_tensor(f).cuda()
+    st = rb.engine.stats_unsorted(t, eps).cpu().numpy()
+    assert np.array_equal(t.cpu().numpy(), f, equal_nan=True)
+    m = orc.metrics(f.copy(), 0.05)
+    for k, key in enumerate(rb.engine.STAT_KEYS):
+        a, b = st[k], m[key]
+        if key.startswith("worst"):                          # python min() vs NaN: compare where the row has no NaN
+            ok = ~np.isnan(f).any(axis=2)
+            assert np.array_equal(a[ok], b[ok]), key
+            assert np.isnan(a[~ok]).all(), key
+            continue
+        assert np.array_equal(np.isnan(a), np.isnan(b)), key
+        ok = ~np.isnan(b)
+        if key.startswith("Q th."):
+            assert np.array_equal(a[ok], b[ok]), key
+        else:
+            assert np.abs(a[ok] - b[ok]).max() < 1e-12, key
+    with pytest.raises(AssertionError):
+        rb.engine.stats_unsorted(torch.tensor([[0.5, 2.5, 0.1]], dtype=torch.float64).cuda())
+
+
 def test_stats_illegal_fids_raise(rb):
     with pytest.raises(AssertionError):
         rb.engine.stats(torch.tensor([[0.5, 2.5, 0.1]], dtype=torch.float64).cuda())
@@ -327,7 +406,11 @@ def test_host_buffer_sweep_equals_device_path(rb):
     st_h, f_h = rb.engine.mc_sweep_host(ctrl, sig, B, n, 0, 3, dkw_eps=eps, seed=5, want_fids=True)
     f_d = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, 3, seed=5)
     assert np.array_equal(f_h, f_d.cpu().numpy())
-    assert np.array_equal(st_h, rb.engine.stats(f_d, eps).cpu().numpy())
+    # the host sweep uses the sort-free statistics pass: W/std agree with the sorted path to rounding, counts
+    # and the minimum exactly
+    st_s = rb.engine.stats(f_d, eps).cpu().numpy()
+    assert np.abs(st_h - st_s).max() < 1e-13
+    assert np.array_equal(st_h[3:9], st_s[3:9]) and np.array_equal(st_h[12:], st_s[12:])
     st_f, _ = rb.engine.mc_sweep_host(ctrl, sig, B, n, 0, 3, dkw_eps=eps, seed=5, fused=True)
     assert np.abs(st_f - st_h).max() < 1e-12
 
@@ -425,6 +508,9 @@ def test_full_size_properties_nspin7(rb):
     sub = np.arange(0, C, 997)
     assert np.abs(f[0, sub, 0].cpu().numpy() - orc.fidelity_batch(ctrl[sub], n, 0, 6)).max() < FID_TOL
     st = rb.engine.stats(f, eps)
+    fe, ste = rb.engine.fidelity_mc_stats(ctrl, sig, B, n, 0, 6, dkw_eps=eps, seed=1)   # sort-free statistics
+    assert torch.equal(fe, f)
+    assert float((ste - st).abs().max()) < 1e-13 and torch.equal(ste[3:9], st[3:9]) and torch.equal(ste[12:], st[12:])
     W = st[0]
     assert torch.allclose(W, 1 - f.mean(dim=2), atol=1e-12, rtol=0)      # W1 to delta(1) == mean infidelity
     assert bool((st[1] >= st[0] - 1e-15).all()) and bool((st[2] <= st[0] + 1e-15).all())   # upper/lower bracket
@@ -457,9 +543,12 @@ def test_rank_consistency_single_call(rb):
     sig = np.linspace(0, 0.1, S)
     eps = float(orc.compute_dkw_error(0.05, 50))
     out = rb.rim_analysis.robustness_sweep(ctrl, sig, 50, n, 0, 5, groups=G, topk=k, seed=4)
-    f = rb.engine.fidelity_mc(ctrl, sig, 50, n, 0, 5, seed=4)
-    st = rb.engine.stats(f, eps).cpu().numpy()
+    # the sweep call uses the sort-free statistics pass: same W as rc_fidelity_mc_stats bit for bit, and as the
+    # sort-based rc_stats to rounding
+    f, ste = rb.engine.fidelity_mc_stats(ctrl, sig, 50, n, 0, 5, dkw_eps=eps, seed=4)
+    st = ste.cpu().numpy()
     assert np.array_equal(out["stats"][orc.METRIC_W], st[0])
+    assert np.abs(st - rb.engine.stats(f, eps).cpu().numpy()).max() < 1e-13
     t2, s2, _ = rb.engine.grouped_rank_consistency(st[0], G, topk=k)
     assert np.array_equal(out["tau"], t2.cpu().numpy(), equal_nan=True) and np.array_equal(out["topk_idx"], s2.cpu().numpy())
 

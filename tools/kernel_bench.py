@@ -29,6 +29,11 @@ for n in [int(v) for v in a.ns.split(",")]:
         if a.fused:
             rb.engine.fidelity_stats(ctrl, sig, a.B, n, 0, n - 1, dkw_eps=0.01, seed=r, check_convergence=False)
         else:
+            if a.stats == 2:     # evolution + sort-free statistics pass
+                rb.engine.fidelity_mc_stats(ctrl, sig, a.B, n, 0, n - 1, dkw_eps=0.01, seed=r, out=out, check=False)
+                e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+                continue
             rb.engine.fidelity_mc(ctrl, sig, a.B, n, 0, n - 1, seed=r, out=out, check_convergence=False)
             if a.stats:
                 rb.engine.stats(out, 0.01, check_legal=False)
