@@ -259,8 +259,11 @@ __global__ void __launch_bounds__(128) sort_stats_warp_kernel(const double* __re
 // = -min (mcsim.py:148), each for v = f, clip(f - eps), clip(f + eps) (mcsim.py:483-485); NaN samples give
 // NaN W/std/worst case and count as below threshold, as in numpy.  Fixed reduction trees: deterministic.
 // ---------------------------------------------------------------------------------------------
+#ifndef RC_STATS_MINB
+#define RC_STATS_MINB 3
+#endif
 template <int E>
-__global__ void __launch_bounds__(256, E <= 4 ? 4 : (E <= 8 ? 3 : 2)) stats_unsorted_warp_kernel(const double* __restrict__ fids, long long nseg, int B,
+__global__ void __launch_bounds__(256, E <= 4 ? RC_STATS_MINB : (E <= 8 ? 3 : 2)) stats_unsorted_warp_kernel(const double* __restrict__ fids, long long nseg, int B,
                                                                   double eps, long long stat_stride,
                                                                   double* __restrict__ stats, unsigned long long* illegal) {
     const int lane = threadIdx.x & 31;
@@ -283,17 +286,22 @@ __global__ void __launch_bounds__(256, E <= 4 ? 4 : (E <= 8 ? 3 : 2)) stats_unso
 #pragma unroll
             for (int j = 0; j < E; ++j) fn[j] = (j * 32 + lane < B) ? __ldcs(nsrc + j * 32 + lane) : 1.0;
         }
-        double s1[3] = {0.0, 0.0, 0.0}, sv[3] = {0.0, 0.0, 0.0};
+        // NaN samples: flagged here and turned into NaN W / std / worst case at the end, so the hot loop can use
+        // the plain min/max clip (fmax(NaN, 0) = 0 keeps a NaN sample out of the threshold counts, as numpy does)
+        double sv[3] = {0.0, 0.0, 0.0};
+        constexpr bool KEEP = E <= 4;          // keep the clipped variants in registers for the second pass
+        double vu[KEEP ? E : 1], vl[KEEP ? E : 1];
         int c95[3] = {0, 0, 0}, c98[3] = {0, 0, 0};
         double mn = INFINITY;
         unsigned flags = 0;   // bit 0: NaN seen; bits 1..: illegal samples
 #pragma unroll
         for (int j = 0; j < E; ++j) {
+            const double u = fmin(fmax(f[j] - eps, 0.0), 1.0), l = fmin(fmax(f[j] + eps, 0.0), 1.0);
+            if (KEEP) { vu[j] = u; vl[j] = l; }
             if (j * 32 + lane < B) {
-                const double v[3] = {f[j], clip01(f[j] - eps), clip01(f[j] + eps)};
+                const double v[3] = {f[j], u, l};
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    s1[k] += 1.0 - v[k];
                     sv[k] += v[k];
                     c95[k] += v[k] >= 0.95;
                     c98[k] += v[k] >= 0.98;
@@ -305,11 +313,12 @@ __global__ void __launch_bounds__(256, E <= 4 ? 4 : (E <= 8 ? 3 : 2)) stats_unso
         }
         double mean[3], m2[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-        for (int k = 0; k < 3; ++k) mean[k] = warp_sum(sv[k]) / nB;
+        for (int k = 0; k < 3; ++k) { sv[k] = warp_sum(sv[k]); mean[k] = sv[k] / nB; }
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             if (j * 32 + lane < B) {
-                const double v[3] = {f[j], clip01(f[j] - eps), clip01(f[j] + eps)};
+                const double v[3] = {f[j], KEEP ? vu[j] : fmin(fmax(f[j] - eps, 0.0), 1.0),
+                                     KEEP ? vl[j] : fmin(fmax(f[j] + eps, 0.0), 1.0)};
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const double dlt = v[k] - mean[k];
@@ -319,29 +328,29 @@ __global__ void __launch_bounds__(256, E <= 4 ? 4 : (E <= 8 ? 3 : 2)) stats_unso
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            s1[k] = warp_sum(s1[k]);
             m2[k] = warp_sum(m2[k]);
             c95[k] = __reduce_add_sync(0xffffffffu, c95[k]);
             c98[k] = __reduce_add_sync(0xffffffffu, c98[k]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        if (__reduce_or_sync(0xffffffffu, flags & 1u)) mn = NAN;
+        const bool anynan = __reduce_or_sync(0xffffffffu, flags & 1u) != 0;
         const unsigned bad = __reduce_add_sync(0xffffffffu, flags >> 1);
         if (bad && illegal && lane == 0) atomicAdd(illegal, (unsigned long long)bad);
         if (lane < 3) {
             const int k = lane;
-            const double mk = k == 0 ? mn : clip01(mn + (k == 1 ? -eps : eps));
-            const double w = k == 0 ? s1[0] : (k == 1 ? s1[1] : s1[2]);
+            const double mk = k == 0 ? mn : fmin(fmax(mn + (k == 1 ? -eps : eps), 0.0), 1.0);
+            const double svk = k == 0 ? sv[0] : (k == 1 ? sv[1] : sv[2]);
             const double a95 = (double)(k == 0 ? c95[0] : (k == 1 ? c95[1] : c95[2]));
             const double a98 = (double)(k == 0 ? c98[0] : (k == 1 ? c98[1] : c98[2]));
             const double mm = k == 0 ? m2[0] : (k == 1 ? m2[1] : m2[2]);
             double* out = stats + seg;
-            out[(ST_W + k) * stat_stride] = w / nB;
+            // W = mean(1 - v) = (B - sum v) / B: the subtraction is exact for sum v in [B/2, 2B] (Sterbenz)
+            out[(ST_W + k) * stat_stride] = anynan ? NAN : (nB - svk) / nB;
             out[(ST_Q95 + k) * stat_stride] = -1.0 * (a95 / nB);
             out[(ST_Q98 + k) * stat_stride] = -1.0 * (a98 / nB);
-            out[(ST_STD + k) * stat_stride] = sqrt(mm / nB);
-            out[(ST_WC + k) * stat_stride] = -mk;
+            out[(ST_STD + k) * stat_stride] = anynan ? NAN : sqrt(mm / nB);
+            out[(ST_WC + k) * stat_stride] = anynan ? NAN : -mk;
         }
     }
 }
