@@ -342,63 +342,63 @@ RC_HD double fidelity_strided(double* d, double* e, double* zi, double* zo, int 
     // rmin: smallest high word among the couplings the last sweep wrote (see fidelity_reg_compact) — the
     // scan for an interior split (a dependent chain of shared-memory loads) only runs when it says so.
     int rmin = 0;
-    for (int l = 0; l < n - 1; ++l) {
-        int it = 0;
-        while (true) {
-            if (negligible_hi(AT(e, l), tolhi)) break;
-            int m = n - 1;
-            if (rmin < tolhi) {
-                m = l + 1;
-                while (m < n - 1 && !negligible_hi(AT(e, m), tolhi)) ++m;
-            }
-            const bool split = m != n - 1;
-            if (++it > QL_MAX_SWEEPS) { bad = 1; break; }
-            double g = wilkinson_g(AT(d, l), AT(d, l + 1), AT(e, l), AT(d, m));
-            double r;
-            double s = 1.0, c = 1.0, p = 0.0;
-            double d_up = AT(d, m), zi_up = AT(zi, m), zo_up = AT(zo, m);  // values at i+1
-            // running pointers to position i of each array (one subtraction per array per rotation
-            // instead of an index multiply per access); the operands of rotation i-1 are loaded while
-            // rotation i computes (they do not depend on the chase), so the shared-memory latency stays
-            // off the dependent chain
-            double* pe = e + (size_t)(m - 1) * ld;
-            double* pd = d + (size_t)(m - 1) * ld;
-            double* pzi = zi + (size_t)(m - 1) * ld;
-            double* pzo = zo + (size_t)(m - 1) * ld;
-            double ei = *pe, di = *pd, zii = *pzi, zoi = *pzo;
-            rmin = 0x7fffffff;
-            for (int i = m - 1; i >= l; --i) {
-                const int back = i > l ? ld : 0;   // clamp: the last prefetch re-reads position l
-                const double ein = *(pe - back), din = *(pd - back), ziin = *(pzi - back), zoin = *(pzo - back);
-                double f = s * ei, b = c * ei;
-                double h = fma(f, f, fma(g, g, tiny));
-                double rinv = rc_rsqrt(h);
-                r = h * rinv;
-                pe[ld] = r;
-                rmin = hi_word(r) < rmin ? hi_word(r) : rmin;
-                s = f * rinv;
-                c = g * rinv;
-                g = d_up - p;
-                r = (di - g) * s + 2.0 * c * b;
-                p = s * r;
-                pd[ld] = g + p;
-                g = c * r - b;
-                pzi[ld] = s * zii + c * zi_up;
-                zi_up = c * zii - s * zi_up;
-                pzo[ld] = s * zoi + c * zo_up;
-                zo_up = c * zoi - s * zo_up;
-                d_up = di;
-                ei = ein; di = din; zii = ziin; zoi = zoin;
-                pe -= ld; pd -= ld; pzi -= ld; pzo -= ld;
-            }
-            AT(zi, l) = zi_up;
-            AT(zo, l) = zo_up;
-            AT(d, l) = d_up - p;
-            AT(e, l) = g;
-            AT(e, m) = 0.0;
-            if (split) rmin = 0;   // the zero stays inside [l, n-1] until [l, m] is deflated: keep scanning
+    // One flat loop: every lane walks its own sequence (deflate while e[l] is negligible, else sweep), so a
+    // warp runs max-over-lanes(total sweeps) trips instead of the sum over l of max-over-lanes(sweeps at l).
+    int l = 0, it = 0;
+    while (true) {
+        while (l < n - 1 && negligible_hi(AT(e, l), tolhi)) { ++l; it = 0; }
+        if (l >= n - 1) break;
+        int m = n - 1;
+        if (rmin < tolhi) {
+            m = l + 1;
+            while (m < n - 1 && !negligible_hi(AT(e, m), tolhi)) ++m;
         }
-        if (bad) break;
+        const bool split = m != n - 1;
+        if (++it > QL_MAX_SWEEPS) { bad = 1; break; }
+        double g = wilkinson_g(AT(d, l), AT(d, l + 1), AT(e, l), AT(d, m));
+        double r;
+        double s = 1.0, c = 1.0, p = 0.0;
+        double d_up = AT(d, m), zi_up = AT(zi, m), zo_up = AT(zo, m);  // values at i+1
+        // running pointers to position i of each array (one subtraction per array per rotation
+        // instead of an index multiply per access); the operands of rotation i-1 are loaded while
+        // rotation i computes (they do not depend on the chase), so the shared-memory latency stays
+        // off the dependent chain
+        double* pe = e + (size_t)(m - 1) * ld;
+        double* pd = d + (size_t)(m - 1) * ld;
+        double* pzi = zi + (size_t)(m - 1) * ld;
+        double* pzo = zo + (size_t)(m - 1) * ld;
+        double ei = *pe, di = *pd, zii = *pzi, zoi = *pzo;
+        rmin = 0x7fffffff;
+        for (int i = m - 1; i >= l; --i) {
+            const int back = i > l ? ld : 0;   // clamp: the last prefetch re-reads position l
+            const double ein = *(pe - back), din = *(pd - back), ziin = *(pzi - back), zoin = *(pzo - back);
+            double f = s * ei, b = c * ei;
+            double h = fma(f, f, fma(g, g, tiny));
+            double rinv = rc_rsqrt(h);
+            r = h * rinv;
+            pe[ld] = r;
+            rmin = hi_word(r) < rmin ? hi_word(r) : rmin;
+            s = f * rinv;
+            c = g * rinv;
+            g = d_up - p;
+            r = (di - g) * s + 2.0 * c * b;
+            p = s * r;
+            pd[ld] = g + p;
+            g = c * r - b;
+            pzi[ld] = s * zii + c * zi_up;
+            zi_up = c * zii - s * zi_up;
+            pzo[ld] = s * zoi + c * zo_up;
+            zo_up = c * zoi - s * zo_up;
+            d_up = di;
+            ei = ein; di = din; zii = ziin; zoi = zoin;
+            pe -= ld; pd -= ld; pzi -= ld; pzo -= ld;
+        }
+        AT(zi, l) = zi_up;
+        AT(zo, l) = zo_up;
+        AT(d, l) = d_up - p;
+        AT(e, l) = g;
+        AT(e, m) = 0.0;
+        if (split) rmin = 0;   // the zero stays inside [l, n-1] until [l, m] is deflated: keep scanning
     }
     *fail = bad;
     if (bad) return NAN;
