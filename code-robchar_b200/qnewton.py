@@ -104,8 +104,13 @@ class LBFGS(object):
         rows[:, 3::2] = lo - 1.0
         return rows
 
-    def _eval_rows(self, x, rows: np.ndarray) -> torch.Tensor:
+    def _eval_rows(self, x, rows: np.ndarray | None) -> np.ndarray:
+        """Fidelities of x under the perturbation rows (None: nominal) as a host array."""
+        if self.topo != "ring":   # tridiagonal: the low-latency objective entry point (one C call, host in/out)
+            return engine.objective_host(x, rows, self.Nspin, self.In, self.Out, model=MODEL_REAL2, zz=self.heisenberg_int)
         xa = np.asarray(x, dtype=np.float64).reshape(1, self.Nspin + 1)
+        if rows is None:
+            rows = np.zeros((1, 2 * self.Nspin))
         m = rows.shape[0]
         if self.topo == "ring":  # not tridiagonal: dense expm path on explicit Hamiltonians
             n = self.Nspin
@@ -115,9 +120,8 @@ class LBFGS(object):
             lo = np.arange(1, n)
             H[:, lo, lo - 1] += rows[:, 3::2]
             H[:, lo - 1, lo] += rows[:, 3::2]
-            return engine.dense_fidelity(H, np.full(m, abs(xa[0, n])), self.In, self.Out)
-        return engine.fidelity_mc(xa, np.ones(1), m, self.Nspin, self.In, self.Out, model=MODEL_REAL2,
-                                  zz=self.heisenberg_int, replay=rows.reshape(1, 1, m, 2 * self.Nspin)).reshape(-1)
+            return engine.dense_fidelity(H, np.full(m, abs(xa[0, n])), self.In, self.Out).cpu().numpy()
+        raise AssertionError("unreachable")
 
     def eval_static_fidelity_gradient(self, x):
         """qnewton.py:162-212: infidelity and its gradient w.r.t. biases and time.  Same construction as
@@ -175,10 +179,10 @@ class LBFGS(object):
                 raise AssertionError(f"H cannot be {type(rH)}")
             rows = self._rows_from_hamiltonians(np.asarray(rH)[None])
         else:
-            rows = np.zeros((1, 2 * n))
+            rows = None
             if ham_noisy:
                 rows = self._rows_from_hamiltonians((self.HH + self.structured_perturabation())[None])
-        fid = float(self._eval_rows(x, rows)[0].item())
+        fid = float(self._eval_rows(x, rows)[0])
         return self._shot_noise(fid) if noisy else fid
 
     def fidelity_ss_av(self, x, noisy=False, ham_noisy=False, reps=10, test=False):
@@ -187,17 +191,23 @@ class LBFGS(object):
             self._rows_train = self._rows_from_hamiltonians(self.randH)
             self._rows_test = self._rows_from_hamiltonians(self.randH_test)
         rows = self._rows_test if test else self._rows_train[:reps]
-        f = self._eval_rows(x, rows)
-        if noisy:
-            f = torch.as_tensor(np.array([self._shot_noise(v) for v in f.cpu().numpy()]))
-        return float(f.mean().item())
+        if noisy:   # per-Hamiltonian shot noise is a host binomial draw (qnewton.py:407): needs the individual values
+            return float(np.mean([self._shot_noise(v) for v in self._eval_rows(x, rows)]))
+        if self.topo == "ring":
+            return float(np.mean(self._eval_rows(x, rows)))
+        _, st = engine.objective_host(x, rows, self.Nspin, self.In, self.Out, model=MODEL_REAL2, zz=self.heisenberg_int,
+                                      want_fids=False, want_stats=True)
+        return float(1.0 - st[0])                                  # mean fidelity = 1 - W1 (device reduction)
 
     def wass_cost(self, x, bootstrap_reps=5):
         """qnewton.py:447-455: W1 to delta(1) of `bootstrap_reps` noisy fidelities (host draws in upstream order)."""
         rows = np.stack([self._rows_from_hamiltonians((self.HH + self.structured_perturabation())[None])[0]
                          for _ in range(bootstrap_reps)])
-        f = self._eval_rows(x, rows)
-        return float(engine.stats(f.reshape(1, -1), 0.0)[0, 0].item())
+        if self.topo == "ring":
+            return float(engine.stats(torch.as_tensor(self._eval_rows(x, rows)).reshape(1, -1), 0.0)[0, 0].item())
+        _, st = engine.objective_host(x, rows, self.Nspin, self.In, self.Out, model=MODEL_REAL2, zz=self.heisenberg_int,
+                                      want_fids=False, want_stats=True)
+        return float(st[0])                                        # W1 to the ideal distribution (wd_from_ideal)
 
     def infidelity(self, x):
         return 1 - self.fidelity_ss(x, noisy=self.fid_noisy, ham_noisy=self.ham_noisy)

@@ -175,6 +175,18 @@ int rc_robustness_sweep_host(const double* ctrl_host, int64_t C, int nspin, int 
                              int64_t topk, double alpha_cluster, double* stats_host, double* tau_host,
                              int64_t* sel_host, int nboot, double* arim_host, double* arim_std_host, void* stream);
 
+/* Low-latency objective evaluation for optimiser loops: ONE controller x_host [N+1] against m explicit
+ * perturbations, host buffers in and out, one H2D + one launch + one D2H through cached pinned staging (no
+ * allocation in steady state).  rows_host [m][K]: the perturbation of each evaluation in replay layout with
+ * sigma = 1 (K = 3N or 2N, reference draw order) — what LBFGS.fidelity_ss(x, use_fixed_ham=True, rH=...) /
+ * fidelity_ss_av / wass_cost evaluate (qnewton.py:383-455) and Environment.step's fidelity (RL...py:260);
+ * rows_host == NULL with m = 1: the nominal fidelity of x (fidelity_ss(x), qnewton.py:383-400).
+ * fids_host [m] and/or stats_host [15]: the statistics of the m fidelities taken as one segment (rc_stats_unsorted
+ * order; row 0 = W1 to the ideal distribution = wass_cost's value, 1 - row 0 = their mean = fidelity_ss_av's value).
+ * Returns RC_ERR_NONCONV after completing if an evaluation did not converge. */
+int rc_objective_host(const double* x_host, int nspin, int inspin, int outspin, const double* rows_host, int64_t m,
+                      int model, int zz, double dkw_eps, double* fids_host, double* stats_host, void* stream);
+
 /* Dense complex matrix exponential of `batch` M x M matrices (M <= 32), interleaved (re, im) float64,
  * row-major: out = expm(A).  The generality path behind the reference's scipy.linalg.expm calls whose
  * argument is not Hermitian tridiagonal: topo="ring" (noise_model.py:83-85), the complex diagonal

@@ -415,6 +415,28 @@ def test_host_buffer_sweep_equals_device_path(rb):
     assert np.abs(st_f - st_h).max() < 1e-12
 
 
+def test_host_sweep_sigma_chunking_is_invisible(rb, monkeypatch):
+    """Large host sweeps are cut into sigma chunks (D2H of chunk k overlaps the evolution of chunk k+1 on a second
+    stream): statistics, fidelities, Kendall matrices and top-k selections are bit-identical for 1, 4 and S chunks
+    (the Philox counters use the global sigma index)."""
+    n, C, B = 4, 2000, 100
+    ctrl = orc.synthetic_controllers(C, n)
+    sig = np.linspace(0, 0.1, 11)                      # 2.2e6 evaluations: above the chunking threshold
+    eps = float(orc.compute_dkw_error(0.05, B))
+    res = {}
+    for ch in ("1", "4", "11"):
+        monkeypatch.setenv("RC_SWEEP_CHUNKS", ch)
+        st, f = rb.engine.mc_sweep_host(ctrl, sig, B, n, 0, 2, dkw_eps=eps, seed=9, want_fids=True)
+        out = rb.rim_analysis.robustness_sweep(ctrl, sig, B, n, 0, 2, groups=4, topk=50, seed=9)
+        res[ch] = (st.copy(), f.copy(), out["tau"].copy(), out["topk_idx"].copy(), out["stats"][orc.METRIC_W].copy())
+    for ch in ("4", "11"):
+        for a, b in zip(res["1"], res[ch]):
+            assert np.array_equal(a, b, equal_nan=True)
+    f_d = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, 2, seed=9)
+    assert np.array_equal(res["4"][1], f_d.cpu().numpy())
+    assert np.array_equal(res["4"][0], rb.engine.stats_unsorted(f_d, eps).cpu().numpy())
+
+
 def test_fused_equals_materialised_large_B(rb):
     n = 7
     ctrl = orc.synthetic_controllers(6, n)
@@ -579,6 +601,36 @@ def test_optimiser_objectives_match_reference(rb):
     assert abs(hz.fidelity_ss(x) - orc.evaluate_fidelity(x, 6, 0, 3, zz=True)) < FID_TOL
     with pytest.raises(NotImplementedError):
         env.run()
+
+
+@pytest.mark.parametrize("n,model,zz", [(4, 0, False), (7, 0, False), (6, 1, True), (12, 1, False), (32, 0, False)])
+def test_objective_host_entry_point(rb, n, model, zz):
+    """rc_objective_host (optimiser-loop entry point: one controller, explicit perturbation rows, host in/out) ==
+    the sweep kernels on the same rows == the oracle; nominal call; statistics of the returned fidelities."""
+    rs = np.random.RandomState(n)
+    x = orc.synthetic_controllers(1, n, seed=3 + n)[0]
+    K = rb.engine.draws_per_eval(n, model)
+    for m in (1, 5, 100, 700):
+        rows = 0.05 * rs.standard_normal((m, K))
+        f = rb.engine.objective_host(x, rows, n, 0, n - 1, model=model, zz=zz)
+        f_dev = rb.engine.fidelity_mc(x[None], np.ones(1), m, n, 0, n - 1, model=model, zz=zz,
+                                      replay=rows.reshape(1, 1, m, K)).cpu().numpy().reshape(-1)
+        assert np.array_equal(f, f_dev)
+        f_or = orc.fidelity_mc_replay(x[None], np.ones(1), rows.reshape(1, 1, m, K), n, 0, n - 1, model=model, zz=zz).reshape(-1)
+        assert np.abs(f - f_or).max() < FID_TOL
+        f2, st = rb.engine.objective_host(x, rows, n, 0, n - 1, model=model, zz=zz, want_stats=True, dkw_eps=0.02)
+        assert np.array_equal(f2, f)
+        ref = rb.engine.stats_unsorted(torch.as_tensor(f).cuda().reshape(1, -1), 0.02).cpu().numpy().reshape(-1)
+        assert np.array_equal(st, ref)
+        assert abs((1.0 - st[0]) - f.mean()) < 1e-14 and abs(st[0] - orc.wd_from_ideal(f.copy())) < 1e-13
+    f0 = rb.engine.objective_host(x, None, n, 0, n - 1, model=model, zz=zz)
+    assert f0.shape == (1,) and abs(f0[0] - orc.evaluate_fidelity(x, n, 0, n - 1, zz=zz)) < FID_TOL
+    xn = x.copy(); xn[1] = np.nan
+    assert np.isnan(rb.engine.objective_host(xn, None, n, 0, n - 1, model=model, zz=zz)[0])
+    with pytest.raises(ValueError):
+        rb.engine.objective_host(x[:-1], None, n, 0, n - 1)
+    with pytest.raises(ValueError):
+        rb.engine.objective_host(x, np.zeros((3, K + 1)), n, 0, n - 1, model=model)
 
 
 def test_arim_and_bootstrap_match_reference(rb):
