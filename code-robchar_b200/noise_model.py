@@ -65,11 +65,9 @@ class noise_model_base:
         n = self.Nspin
         z = np.asarray(self.perturbation()) if ham_noisy else None
         if self.topo == "chain" and (z is None or self._is_hermitian_tridiagonal(z)):
-            row = self._replay_row_from_matrix(z) if z is not None else np.zeros(3 * n)
-            xa = np.asarray(x, dtype=np.float64).reshape(1, n + 1)
-            f = engine.fidelity_mc(xa, np.ones(1), 1, n, self.inspin, self.outspin, model=MODEL_COMPLEX3, zz=self.zz,
-                                   replay=row.reshape(1, 1, 1, 3 * n))
-            return float(f.reshape(-1)[0].item())
+            # low-latency entry point (rc_objective_host): one C call, host in/out
+            rows = self._replay_row_from_matrix(z).reshape(1, 3 * n) if z is not None else None
+            return float(engine.objective_host(x, rows, n, self.inspin, self.outspin, model=MODEL_COMPLEX3, zz=self.zz)[0])
         # generality path (ring topology, non-tridiagonal or non-Hermitian perturbations such as
         # directional_perturbation's complex diagonal entries): dense expm on the device
         H = self.HH.copy()
