@@ -156,6 +156,27 @@ cudaError_t launch_fidelity(const FidArgs& a, cudaStream_t st) {
     return replay ? launch_smem<MODEL_REAL2, true>(a, sm, st) : launch_smem<MODEL_REAL2, false>(a, sm, st);
 }
 
+template <int MODEL>
+static cudaError_t launch_fused_smem_warp(const FusedArgs& g, int sm_count, cudaStream_t st) {
+    const int threads = smem_threads(g.f.N, SMEM_MAX_THREADS, (SMEM_MAX_THREADS / 32) * WACC_DOUBLES * sizeof(double));
+    size_t smem = (size_t)4 * g.f.N * threads * sizeof(double);
+    auto kern = fidelity_stats_smem_warp_kernel<MODEL>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    int occ = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    if (err != cudaSuccess) return err;
+    if (occ < 1) occ = 1;
+    const long long wpc = threads / 32;
+    const long long nitems = (long long)g.f.S * g.f.C * g.nchunks;
+    long long grid = (long long)sm_count * occ;
+    const long long need = (nitems + wpc - 1) / wpc;
+    if (grid > need) grid = need;
+    if (grid < 1) return cudaSuccess;
+    kern<<<(unsigned)grid, threads, smem, st>>>(g);
+    return cudaGetLastError();
+}
+
 template <int MODEL, bool REPLAY>
 static cudaError_t launch_fused_smem(const FusedArgs& g, int sm_count, cudaStream_t st) {
     const int threads = smem_threads(g.f.N, SMEM_FUSED_MAX_THREADS, FUSED_STATIC_SMEM);
@@ -180,9 +201,11 @@ cudaError_t launch_fused(const FusedArgs& g, cudaStream_t st) {
     if (g.f.N <= reg_crossover())
         return fused_table[g.f.N](g, fused_reg_threads(g.f.N, g.f.replay != nullptr, g.f.B), sm, st);
     const bool replay = g.f.replay != nullptr;
-    if (g.f.model == MODEL_COMPLEX3)
-        return replay ? launch_fused_smem<MODEL_COMPLEX3, true>(g, sm, st) : launch_fused_smem<MODEL_COMPLEX3, false>(g, sm, st);
-    return replay ? launch_fused_smem<MODEL_REAL2, true>(g, sm, st) : launch_fused_smem<MODEL_REAL2, false>(g, sm, st);
+    if (!replay)
+        return g.f.model == MODEL_COMPLEX3 ? launch_fused_smem_warp<MODEL_COMPLEX3>(g, sm, st)
+                                           : launch_fused_smem_warp<MODEL_REAL2>(g, sm, st);
+    return g.f.model == MODEL_COMPLEX3 ? launch_fused_smem<MODEL_COMPLEX3, true>(g, sm, st)
+                                       : launch_fused_smem<MODEL_REAL2, true>(g, sm, st);
 }
 
 // chunking of the draw axis for the fused path: a multiple of the CTA size close to 4096 draws per item
@@ -196,31 +219,55 @@ static void fused_chunking_threads(long long threads, long long B, long long* ch
     *nchunks = (B + ch - 1) / ch;
     if (*nchunks < 1) *nchunks = 1;
 }
-static void fused_chunking(int nspin, bool replay, long long B, long long* chunk, long long* nchunks) {
+// Draws per warp item of the warp-autonomous (Philox mode) fused kernels: the largest of 4096 .. 128 that still
+// gives every resident warp >= 32 items (static round-robin distribution: <= 3 % tail), else 128; the whole
+// segment (rounded up to 32) when it is shorter than that.
+static long long warp_chunk_for(long long nseg, long long B) {
+    const long long warps = (long long)device_sm_count() * MAX_CTA_WARPS;
+    long long chunk = 4096;
+    while (chunk > 128 && nseg * ((B + chunk - 1) / chunk) < 32 * warps) chunk >>= 1;
+    if (B < chunk) chunk = (B + 31) / 32 * 32;
+    return chunk;
+}
+
+static void fused_chunking(int nspin, bool replay, long long nseg, long long B, long long* chunk, long long* nchunks) {
+    if (!replay) {
+        *chunk = warp_chunk_for(nseg, B);
+        *nchunks = (B + *chunk - 1) / *chunk;
+        return;
+    }
     const long long threads = nspin <= reg_crossover() ? fused_reg_threads(nspin, replay, B)
                                                        : smem_threads(nspin, SMEM_FUSED_MAX_THREADS, FUSED_STATIC_SMEM);
     fused_chunking_threads(threads, B, chunk, nchunks);
 }
 
-// One thread per segment merges its chunk partials in order and emits the 15 statistics.
-__global__ void fused_finalize_kernel(const double* __restrict__ partials, long long nseg, long long nchunks,
-                                      long long B, double eps, double* __restrict__ stats) {
-    for (long long seg = (long long)blockIdx.x * blockDim.x + threadIdx.x; seg < nseg;
-         seg += (long long)gridDim.x * blockDim.x) {
+// One WARP per segment merges its chunk partials (lane L takes chunks L, L+32, ... in order, then a fixed
+// shuffle tree: deterministic) and lane 0 emits the 15 statistics.  The warp-autonomous fused kernels write up
+// to B/128 partials per segment, so a single thread per segment would serialise hundreds of dependent L2 reads.
+__global__ void __launch_bounds__(256) fused_finalize_kernel(const double* __restrict__ partials, long long nseg,
+                                                             long long nchunks, long long B, double eps,
+                                                             double* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long seg = warp0; seg < nseg; seg += nwarps) {
         Moments m;
-        moments_load(m, partials + seg * nchunks * PART_DOUBLES);
-        for (long long ch = 1; ch < nchunks; ++ch) {
+        moments_init(m);
+        for (long long ch = lane; ch < nchunks; ch += 32) {
             Moments o;
             moments_load(o, partials + (seg * nchunks + ch) * PART_DOUBLES);
             moments_merge(m, o);
         }
-        const double mn[3] = {m.mn, clip01(m.mn - eps), clip01(m.mn + eps)};
-        for (int k = 0; k < 3; ++k) {
-            stats[(ST_W + k) * nseg + seg] = m.s1[k] / (double)B;       // mean(1 - f) == sorted W1 formula
-            stats[(ST_Q95 + k) * nseg + seg] = -1.0 * (m.c95[k] / (double)B);
-            stats[(ST_Q98 + k) * nseg + seg] = -1.0 * (m.c98[k] / (double)B);
-            stats[(ST_STD + k) * nseg + seg] = sqrt(m.m2[k] / (double)B);
-            stats[(ST_WC + k) * nseg + seg] = -mn[k];
+        moments_warp_merge(m);
+        if (lane == 0) {
+            const double mn[3] = {m.mn, clip01(m.mn - eps), clip01(m.mn + eps)};
+            for (int k = 0; k < 3; ++k) {
+                stats[(ST_W + k) * nseg + seg] = m.s1[k] / (double)B;       // mean(1 - f) == sorted W1 formula
+                stats[(ST_Q95 + k) * nseg + seg] = -1.0 * (m.c95[k] / (double)B);
+                stats[(ST_Q98 + k) * nseg + seg] = -1.0 * (m.c98[k] / (double)B);
+                stats[(ST_STD + k) * nseg + seg] = sqrt(m.m2[k] / (double)B);
+                stats[(ST_WC + k) * nseg + seg] = -mn[k];
+            }
         }
     }
 }
@@ -341,6 +388,9 @@ extern "C" size_t rc_fidelity_stats_workspace_bytes(int64_t nseg, int64_t B) {
         fused_chunking_threads(t, B, &chunk, &nchunks);
         if (nchunks > nmax) nmax = nchunks;
     }
+    const long long wc = warp_chunk_for(nseg, B);                      // Philox mode
+    const long long warp_items = (B + wc - 1) / wc;
+    if (warp_items > nmax) nmax = warp_items;
     return (size_t)nseg * nmax * PART_DOUBLES * sizeof(double) + 256;
 }
 
@@ -363,16 +413,16 @@ extern "C" int rc_fidelity_stats(const double* ctrl_dev, int64_t C, int nspin, i
     a.c_offset = c_offset; a.b_offset = b_offset;
     RC_CUDA_TRY(zig_tables_device(&a.zig));
     g.eps = dkw_eps;
-    fused_chunking(nspin, replay_dev != nullptr, B, &g.chunk, &g.nchunks);
+    fused_chunking(nspin, replay_dev != nullptr, nseg, B, &g.chunk, &g.nchunks);
     const size_t need = (size_t)nseg * g.nchunks * PART_DOUBLES * sizeof(double);
     if (!workspace_dev || workspace_bytes < need)
         return set_error(RC_ERR_WORKSPACE, "rc_fidelity_stats: workspace %zu < required %zu bytes", workspace_bytes, need);
     g.partials = (double*)workspace_dev;
     cudaStream_t st = (cudaStream_t)stream;
     RC_CUDA_TRY(launch_fused(g, st));
-    long long blocks = (nseg + 127) / 128;
+    long long blocks = (nseg + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    fused_finalize_kernel<<<(unsigned)blocks, 128, 0, st>>>(g.partials, nseg, g.nchunks, B, dkw_eps, stats_dev);
+    fused_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(g.partials, nseg, g.nchunks, B, dkw_eps, stats_dev);
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }

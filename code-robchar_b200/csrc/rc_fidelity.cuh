@@ -251,6 +251,16 @@ __device__ __forceinline__ void moments_load(Moments& m, const double* p) {
     for (int k = 0; k < 3; ++k) { m.mean[k] = p[1 + k]; m.m2[k] = p[4 + k]; m.s1[k] = p[7 + k]; m.c95[k] = p[10 + k]; m.c98[k] = p[13 + k]; }
 }
 
+// Fixed shuffle tree over the warp; result valid in lane 0.
+__device__ __forceinline__ void moments_warp_merge(Moments& m) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        Moments other = moments_shfl_down(m, o);
+        if (lane + o < 32) moments_merge(m, other);
+    }
+}
+
 // CTA-wide deterministic merge of per-thread Moments; result valid in thread 0.
 __device__ __forceinline__ void moments_block_merge(Moments& m, double* scratch /* [nwarp][PART_DOUBLES] */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
@@ -271,6 +281,120 @@ __device__ __forceinline__ void moments_block_merge(Moments& m, double* scratch 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-autonomous fused path (Philox mode).  Work item = (segment, chunk of 128..4096 draws) processed by ONE warp in
+// chunk / 32 passes: no CTA barrier anywhere (a barrier per item keeps re-aligning the 24 warps of the CTA
+// to the slowest one).  Nothing statistical stays live in registers across an evaluation (the eigensolver
+// already fills the register budget; 20 extra live registers cost more in spills than the statistics cost in
+// instructions): after every pass the warp reduces its 32 fidelities by shuffles / ballots and lane 0 adds the
+// pass totals to the warp's 16-double accumulator in shared memory.  Sums are taken about a shift (the item's
+// first sample) so the variance does not cancel; at the end of the item the accumulator becomes a Moments
+// partial; fused_finalize_kernel merges the partials of a segment in chunk order as before.  Fixed order
+// everywhere => deterministic.
+// ---------------------------------------------------------------------------------------------
+constexpr int WACC_DOUBLES = 16;   // sy[3] syy[3] c95[3] c98[3] | mn shift n nan
+enum WaccSlot { WA_SY = 0, WA_SYY = 3, WA_C95 = 6, WA_C98 = 9, WA_MN = 12, WA_SHIFT = 13, WA_N = 14, WA_NAN = 15 };
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// All 32 lanes call, converged; `valid` lanes hold a fidelity.  `first`: first pass of the item (lane 0 is valid).
+__device__ __forceinline__ void warp_acc_pass(double* __restrict__ wacc, bool first, bool valid, double f, double eps) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    if (first) {
+        const double f0 = __shfl_sync(0xffffffffu, f, 0);
+        if (lane < WACC_DOUBLES) wacc[lane] = lane == WA_MN ? INFINITY : (lane == WA_SHIFT ? f0 : 0.0);
+        __syncwarp();
+    }
+    const double shift = wacc[WA_SHIFT];
+    const double v[3] = {f, clip01(f - eps), clip01(f + eps)};
+    const double sh[3] = {shift, clip01(shift - eps), clip01(shift + eps)};
+    double tot[12];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double y = valid ? v[k] - sh[k] : 0.0;
+        tot[WA_SY + k] = warp_sum_f64(y);
+        tot[WA_SYY + k] = warp_sum_f64(y * y);
+        tot[WA_C95 + k] = (double)__popc(__ballot_sync(0xffffffffu, valid && v[k] >= 0.95));
+        tot[WA_C98 + k] = (double)__popc(__ballot_sync(0xffffffffu, valid && v[k] >= 0.98));
+    }
+    double mn = valid ? f : INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const unsigned nanmask = __ballot_sync(0xffffffffu, valid && f != f);
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) wacc[j] += tot[j];
+        wacc[WA_MN] = fmin(wacc[WA_MN], mn);
+        wacc[WA_N] += (double)__popc(vmask);
+        wacc[WA_NAN] += (double)__popc(nanmask);
+    }
+}
+
+// Lane 0: the warp accumulator of a finished item as a Moments partial.
+__device__ __forceinline__ void warp_acc_finish(const double* __restrict__ wacc, double eps, Moments& m) {
+    moments_init(m);
+    const double n = wacc[WA_N];
+    if (n == 0.0) return;
+    const double shift = wacc[WA_SHIFT];
+    const double sh[3] = {shift, clip01(shift - eps), clip01(shift + eps)};
+    const bool nan = wacc[WA_NAN] != 0.0;
+    m.n = n;
+    m.mn = nan ? NAN : wacc[WA_MN];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double sy = wacc[WA_SY + k], syy = wacc[WA_SYY + k];
+        m.mean[k] = sh[k] + sy / n;
+        m.m2[k] = fmax(syy - sy * sy / n, 0.0);
+        if (nan || sy != sy || syy != syy) { m.mean[k] = NAN; m.m2[k] = NAN; }
+        m.s1[k] = nan ? NAN : n * (1.0 - sh[k]) - sy;     // sum(1 - v) = n (1 - shift) - sum(v - shift)
+        m.c95[k] = wacc[WA_C95 + k];
+        m.c98[k] = wacc[WA_C98 + k];
+    }
+}
+
+template <int N, int MODEL>
+__global__ void __launch_bounds__(reg_cta_threads(N, false), reg_cta_min_blocks(N, false)) fidelity_stats_reg_warp_kernel(FusedArgs g) {
+    constexpr int K = draws_per_site(MODEL) * N;
+    constexpr int KP = K | 1;
+    extern __shared__ __align__(16) double smem_raw[];
+    const FidArgs& a = g.f;
+    const ZigEntry* kw = reinterpret_cast<const ZigEntry*>(smem_raw);
+    double* row = smem_raw + 2 * ZIG_LAYERS + threadIdx.x * KP;
+    load_zig_table(a.zig.kw, reinterpret_cast<ZigEntry*>(smem_raw));
+    __shared__ double wacc_all[MAX_CTA_WARPS * WACC_DOUBLES];
+    double* wacc = wacc_all + (threadIdx.x >> 5) * WACC_DOUBLES;
+    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const long long nitems = (long long)a.S * a.C * g.nchunks;
+    const long long stride = (long long)gridDim.x * wpc;
+    for (long long item = (long long)blockIdx.x * wpc + (threadIdx.x >> 5); item < nitems; item += stride) {
+        const long long seg = item / g.nchunks, ch = item - seg * g.nchunks;
+        const long long s = seg / a.C, c = seg - s * a.C;
+        const long long b0 = ch * g.chunk;
+        const long long b1 = b0 + g.chunk < a.B ? b0 + g.chunk : a.B;
+        for (long long bt = b0; bt < b1; bt += 32) {
+            const long long b = bt + lane;
+            const bool valid = b < b1;
+            double f = 0.0;
+            if (valid) f = eval_reg<N, MODEL, false>(a, s, c, b, row, kw);
+            warp_acc_pass(wacc, bt == b0, valid, f, g.eps);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            Moments m;
+            warp_acc_finish(wacc, g.eps, m);
+            moments_store(m, g.partials + item * PART_DOUBLES);
+        }
+        __syncwarp();
+    }
+}
+
+// CTA-per-item variant, kept for replay mode (the replay rows of a tile are staged behind CTA barriers).
 template <int N, int MODEL, bool REPLAY>
 __global__ void __launch_bounds__(reg_cta_threads(N, REPLAY), reg_cta_min_blocks(N, REPLAY)) fidelity_stats_reg_kernel(FusedArgs g) {
     constexpr int K = draws_per_site(MODEL) * N;
@@ -372,6 +496,38 @@ __global__ void __launch_bounds__(SMEM_MAX_THREADS) fidelity_smem_kernel(FidArgs
          ev += (long long)gridDim.x * blockDim.x) {
         EvalIndex ix = decode_eval(ev, a.C, a.B);
         a.fids[ev] = eval_smem<MODEL, REPLAY>(a, ix.s, ix.c, ix.b, REPLAY ? a.replay + ev * K : nullptr, sm);
+    }
+}
+
+// Warp-autonomous fused variant of the shared-memory kernel (Philox mode): see fidelity_stats_reg_warp_kernel.
+template <int MODEL>
+__global__ void __launch_bounds__(SMEM_MAX_THREADS) fidelity_stats_smem_warp_kernel(FusedArgs g) {
+    extern __shared__ double sm[];
+    __shared__ double wacc_all[(SMEM_MAX_THREADS / 32) * WACC_DOUBLES];
+    double* wacc = wacc_all + (threadIdx.x >> 5) * WACC_DOUBLES;
+    const FidArgs& a = g.f;
+    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const long long nitems = (long long)a.S * a.C * g.nchunks;
+    const long long stride = (long long)gridDim.x * wpc;
+    for (long long item = (long long)blockIdx.x * wpc + (threadIdx.x >> 5); item < nitems; item += stride) {
+        const long long seg = item / g.nchunks, ch = item - seg * g.nchunks;
+        const long long s = seg / a.C, c = seg - s * a.C;
+        const long long b0 = ch * g.chunk;
+        const long long b1 = b0 + g.chunk < a.B ? b0 + g.chunk : a.B;
+        for (long long bt = b0; bt < b1; bt += 32) {
+            const long long b = bt + lane;
+            const bool valid = b < b1;
+            double f = 0.0;
+            if (valid) f = eval_smem<MODEL, false>(a, s, c, b, nullptr, sm);
+            warp_acc_pass(wacc, bt == b0, valid, f, g.eps);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            Moments m;
+            warp_acc_finish(wacc, g.eps, m);
+            moments_store(m, g.partials + item * PART_DOUBLES);
+        }
+        __syncwarp();
     }
 }
 

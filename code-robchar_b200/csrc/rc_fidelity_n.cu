@@ -38,6 +38,33 @@ static cudaError_t launch_reg(const FidArgs& a, int sm_count, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// Philox mode: warp-autonomous items (no CTA barriers), same CTA shape and shared-memory layout as the plain kernel.
+template <int MODEL>
+static cudaError_t launch_fused_reg_warp(const FusedArgs& g, int sm_count, cudaStream_t st) {
+    constexpr int N = RC_NSPIN;
+    constexpr int K = draws_per_site(MODEL) * N;
+    const int threads = reg_threads_runtime(N, false);
+    size_t smem = (size_t)threads * (K | 1) * sizeof(double) + sizeof(ZigEntry) * ZIG_LAYERS;
+    auto kern = fidelity_stats_reg_warp_kernel<N, MODEL>;
+    cudaError_t err;
+    if (smem > 40 * 1024) {
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+    }
+    int occ = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    if (err != cudaSuccess) return err;
+    if (occ < 1) occ = 1;
+    const long long wpc = threads / 32;
+    const long long nitems = (long long)g.f.S * g.f.C * g.nchunks;
+    long long grid = (long long)sm_count * occ;
+    const long long need = (nitems + wpc - 1) / wpc;
+    if (grid > need) grid = need;
+    if (grid < 1) return cudaSuccess;
+    kern<<<(unsigned)grid, threads, smem, st>>>(g);
+    return cudaGetLastError();
+}
+
 template <int MODEL, bool REPLAY>
 static cudaError_t launch_fused_reg(const FusedArgs& g, int threads, int sm_count, cudaStream_t st) {
     constexpr int N = RC_NSPIN;
@@ -63,11 +90,11 @@ static cudaError_t launch_fused_reg(const FusedArgs& g, int threads, int sm_coun
 
 cudaError_t RC_CAT(launch_fused_reg_, RC_NSPIN)(const FusedArgs& g, int threads, int sm_count, cudaStream_t st) {
     const bool replay = g.f.replay != nullptr;
-    if (g.f.model == MODEL_COMPLEX3)
-        return replay ? launch_fused_reg<MODEL_COMPLEX3, true>(g, threads, sm_count, st)
-                      : launch_fused_reg<MODEL_COMPLEX3, false>(g, threads, sm_count, st);
-    return replay ? launch_fused_reg<MODEL_REAL2, true>(g, threads, sm_count, st)
-                  : launch_fused_reg<MODEL_REAL2, false>(g, threads, sm_count, st);
+    if (!replay)
+        return g.f.model == MODEL_COMPLEX3 ? launch_fused_reg_warp<MODEL_COMPLEX3>(g, sm_count, st)
+                                           : launch_fused_reg_warp<MODEL_REAL2>(g, sm_count, st);
+    return g.f.model == MODEL_COMPLEX3 ? launch_fused_reg<MODEL_COMPLEX3, true>(g, threads, sm_count, st)
+                                       : launch_fused_reg<MODEL_REAL2, true>(g, threads, sm_count, st);
 }
 
 cudaError_t RC_CAT(launch_fid_reg_, RC_NSPIN)(const FidArgs& a, int sm_count, cudaStream_t st) {
