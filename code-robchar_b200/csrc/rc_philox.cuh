@@ -196,12 +196,12 @@ RC_HD void normals_fill(const NoiseKey& key, int nc, const ZigTables& t, Slot&& 
     const int np = (nc + 1) / 2;
     uint32_t pend = 0;      // up to four parked draw indices (jc + 1), 8 bits each
     int p = 0;
-    while (true) {
+    // structured loops only (conditions instead of `break`): the warp reconverges after the drain of every trip
+    do {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-        for (; p < np; ++p) {
-            if (pend >> 16) break;   // fewer than two free entries: drain first (rare)
+        for (; p < np && !(pend >> 16); ++p) {   // fewer than two free entries: drain first (rare)
             const Philox4 r = philox_block(key, (uint32_t)p);
             bool miss;
             const int j0 = 2 * p;
@@ -217,8 +217,7 @@ RC_HD void normals_fill(const NoiseKey& key, int nc, const ZigTables& t, Slot&& 
             pend >>= 8;
             slot((int)jc) = zig_complete(key, jc, slot((int)jc), t);
         }
-        if (p >= np) break;
-    }
+    } while (p < np);
 #endif
 }
 
