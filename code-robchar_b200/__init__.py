@@ -7,6 +7,7 @@ point without the built library or without a CUDA device raises (no CPU fallback
 """
 from . import _lib, engine  # noqa: F401
 from . import noise_model, wd_sortof_fast_implementation, rim_analysis, noise_analysis, mcsim, kendall, dist, arim, qnewton  # noqa: F401
+from . import RLreinforceXXchain_actionedtime  # noqa: F401
 from .mcsim import MCDataSim  # noqa: F401
 from .noise_model import noise_function, structured_perturbation, directional_perturbation  # noqa: F401
 from .wd_sortof_fast_implementation import wd_from_ideal, wd_from_ideal_zero, RIM_p, compute_dkw_error  # noqa: F401
@@ -16,10 +17,12 @@ __version__ = "0.1.0"
 
 def install_reference_module_aliases():
     """Register this package's modules under the reference's flat module names (``mcsim``,
-    ``noise_model``, ``wd_sortof_fast_implementation``, ``noise_analysis``) so unmodified analysis
-    scripts that do ``from mcsim import MCDataSim`` pick up the GPU path."""
+    ``noise_model``, ``wd_sortof_fast_implementation``, ``noise_analysis``,
+    ``RLreinforceXXchain_actionedtime``) so unmodified scripts that do ``from mcsim import MCDataSim`` or
+    ``from RLreinforceXXchain_actionedtime import Environment`` (ppo.py:16) pick up the GPU path."""
     import sys
     for name, mod in (("mcsim", mcsim), ("noise_model", noise_model),
                       ("wd_sortof_fast_implementation", wd_sortof_fast_implementation),
-                      ("noise_analysis", noise_analysis)):
+                      ("noise_analysis", noise_analysis),
+                      ("RLreinforceXXchain_actionedtime", RLreinforceXXchain_actionedtime)):
         sys.modules[name] = mod

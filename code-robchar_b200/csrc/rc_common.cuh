@@ -14,7 +14,7 @@ int device_sm_count();                // SMs of the current device (cached per d
 int fidelity_mc_impl(const char* who, const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
                      const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed, int64_t c_offset,
                      int64_t b_offset, const double* replay_dev, double* fids_dev, unsigned long long* nonconv_dev,
-                     int s_offset, cudaStream_t st);
+                     int s_offset, cudaStream_t st, double* amps_dev = nullptr);
 // rc_stats.cu: sort-free statistics of segments [0, nseg_chunk) of fids_dev, written to columns
 // stats_dev[row * stat_stride + seg] (rc_stats_unsorted; per sigma chunk in the host sweep)
 int stats_unsorted_impl(const double* fids_dev, int64_t nseg_chunk, int64_t B, double dkw_eps, double* stats_dev,

@@ -115,11 +115,11 @@ static int smem_threads(int n, int cap = SMEM_MAX_THREADS, size_t static_bytes =
     return t > cap ? cap : t;
 }
 
-template <int MODEL, bool REPLAY>
+template <int MODEL, bool REPLAY, bool AMPS = false>
 static cudaError_t launch_smem(const FidArgs& a, int sm_count, cudaStream_t st) {
     const int threads = smem_threads(a.N);
     size_t smem = (size_t)4 * a.N * threads * sizeof(double);
-    auto kern = fidelity_smem_kernel<MODEL, REPLAY>;
+    auto kern = fidelity_smem_kernel<MODEL, REPLAY, AMPS>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int occ = 0;
@@ -149,6 +149,8 @@ static int reg_crossover() {
 
 cudaError_t launch_fidelity(const FidArgs& a, cudaStream_t st) {
     int sm = device_sm_count();
+    if (a.amps)   // complex amplitudes (real symmetric model only): the general-N kernel, any chain length
+        return a.replay ? launch_smem<MODEL_REAL2, true, true>(a, sm, st) : launch_smem<MODEL_REAL2, false, true>(a, sm, st);
     if (a.N <= reg_crossover()) return reg_table[a.N](a, sm, st);
     const bool replay = a.replay != nullptr;
     if (a.model == MODEL_COMPLEX3)
@@ -324,7 +326,7 @@ namespace rc {
 int fidelity_mc_impl(const char* who, const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
                      const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed, int64_t c_offset,
                      int64_t b_offset, const double* replay_dev, double* fids_dev, unsigned long long* nonconv_dev,
-                     int s_offset, cudaStream_t st) {
+                     int s_offset, cudaStream_t st, double* amps_dev) {
     int rcode = check_model_args(C, nspin, inspin, outspin, S, B, model);
     if (rcode) return rcode;
     if ((long long)S * C * B == 0) return RC_OK;
@@ -335,6 +337,9 @@ int fidelity_mc_impl(const char* who, const double* ctrl_dev, int64_t C, int nsp
     a.C = C; a.B = B; a.S = S; a.N = nspin; a.in = inspin; a.out = outspin; a.model = model; a.zz = zz;
     a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
     a.c_offset = c_offset; a.b_offset = b_offset; a.s_offset = s_offset;
+    a.amps = amps_dev;
+    if (amps_dev && model != MODEL_REAL2)
+        return set_error(RC_ERR_BAD_ARG, "%s: complex amplitudes need the real symmetric model (RC_MODEL_REAL2)", who);
     RC_CUDA_TRY(zig_tables_device(&a.zig));
     RC_CUDA_TRY(launch_fidelity(a, st));
     return RC_OK;

@@ -30,6 +30,10 @@ struct FidArgs {
     long long c_offset, b_offset;  // global index of this shard's first controller / draw (Philox counters)
     ZigTables zig;                 // ziggurat tables in global memory (Philox mode), see zig_tables_device()
     int s_offset;                  // global index of this launch's first sigma level (sigma-chunked host sweep)
+    double* amps;                  // optional [S][C][B][2]: complex transfer amplitude (re, im) per evaluation (served by
+                                   // the shared-memory kernel's AMPS instantiation for every N; small batches only).
+                                   // The Hamiltonian must be real symmetric (RC_MODEL_REAL2): the complex model's
+                                   // phase gauge leaves |amp|^2 invariant but not amp
 };
 
 __host__ __device__ constexpr int draws_per_site(int model) { return model == MODEL_COMPLEX3 ? 3 : 2; }
@@ -438,7 +442,7 @@ __global__ void __launch_bounds__(reg_cta_threads(N, REPLAY), reg_cta_min_blocks
 // One evaluation with the four [N] arrays in shared memory (column = this lane, stride blockDim).
 // Raw standard normals are first parked in the arrays themselves (d <- z_ii, e <- nn, zi <- nn2) by a
 // non-unrolled Philox pair loop (or read from the replay row), then transformed in place.
-template <int MODEL, bool REPLAY>
+template <int MODEL, bool REPLAY, bool AMPS = false>
 __device__ __forceinline__ double eval_smem(const FidArgs& a, long long s, long long c, long long b,
                                             const double* row /* global replay row */, double* sm) {
     const int n = a.N, ld = blockDim.x;
@@ -482,12 +486,18 @@ __device__ __forceinline__ double eval_smem(const FidArgs& a, long long s, long 
         zo[(size_t)i * ld] = (i == a.out) ? 1.0 : 0.0;
     }
     int fail = 0;
-    double f = fidelity_strided(d, e, zi, zo, ld, n, fabs(__ldg(x + n)), &fail);
+    double re, im;
+    amplitude_strided(d, e, zi, zo, ld, n, fabs(__ldg(x + n)), &fail, re, im);
     if (fail && a.nonconv) atomicAdd(a.nonconv, 1ull);
-    return f;
+    if (AMPS) {   // two 8-byte stores: the caller's buffer is only guaranteed to be 8-byte aligned
+        double* dst = a.amps + 2 * ((s * a.C + c) * a.B + b);
+        dst[0] = re;
+        dst[1] = im;
+    }
+    return re * re + im * im;
 }
 
-template <int MODEL, bool REPLAY>
+template <int MODEL, bool REPLAY, bool AMPS = false>
 __global__ void __launch_bounds__(SMEM_MAX_THREADS) fidelity_smem_kernel(FidArgs a) {
     extern __shared__ double sm[];
     const long long K = (long long)draws_per_site(MODEL) * a.N;
@@ -495,7 +505,7 @@ __global__ void __launch_bounds__(SMEM_MAX_THREADS) fidelity_smem_kernel(FidArgs
     for (long long ev = (long long)blockIdx.x * blockDim.x + threadIdx.x; ev < total;
          ev += (long long)gridDim.x * blockDim.x) {
         EvalIndex ix = decode_eval(ev, a.C, a.B);
-        a.fids[ev] = eval_smem<MODEL, REPLAY>(a, ix.s, ix.c, ix.b, REPLAY ? a.replay + ev * K : nullptr, sm);
+        a.fids[ev] = eval_smem<MODEL, REPLAY, AMPS>(a, ix.s, ix.c, ix.b, REPLAY ? a.replay + ev * K : nullptr, sm);
     }
 }
 

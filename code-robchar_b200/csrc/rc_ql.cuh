@@ -330,7 +330,8 @@ RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int ou
 // `ld` between consecutive matrix positions (column = this lane), dynamic loop bounds.
 // Holds the "i+1" elements in registers while chasing upwards to halve the memory traffic.
 // ---------------------------------------------------------------------------------------------
-RC_HD double fidelity_strided(double* d, double* e, double* zi, double* zo, int ld, int n, double T, int* fail) {
+RC_HD void amplitude_strided(double* d, double* e, double* zi, double* zo, int ld, int n, double T, int* fail,
+                             double& re_out, double& im_out) {
 #define AT(a, i) a[(size_t)(i) * ld]
     double anorm = 0.0, chk = T;
     AT(e, n - 1) = 0.0;
@@ -338,7 +339,8 @@ RC_HD double fidelity_strided(double* d, double* e, double* zi, double* zo, int 
         anorm = fmax(anorm, fabs(AT(d, k)) + fabs(AT(e, k)));
         chk += AT(d, k) + AT(e, k);
     }
-    if (!(fabs(chk) <= DBL_MAX)) { *fail = 0; return NAN; }
+    re_out = NAN; im_out = NAN;
+    if (!(fabs(chk) <= DBL_MAX)) { *fail = 0; return; }
     const double tol = DBL_EPSILON * anorm;
     const int tolhi = threshold_hi(tol);
     const double tiny = fmin(tol, 1e-280);
@@ -410,7 +412,7 @@ RC_HD double fidelity_strided(double* d, double* e, double* zi, double* zo, int 
     }
     bad = l < n - 1;
     *fail = bad;
-    if (bad) return NAN;
+    if (bad) return;
     double re = 0.0, im = 0.0;
     for (int k = 0; k < n; ++k) {
         double sn, cs;
@@ -420,6 +422,12 @@ RC_HD double fidelity_strided(double* d, double* e, double* zi, double* zo, int 
         im = fma(-w, sn, im);
     }
 #undef AT
+    re_out = re; im_out = im;
+}
+
+RC_HD double fidelity_strided(double* d, double* e, double* zi, double* zo, int ld, int n, double T, int* fail) {
+    double re, im;
+    amplitude_strided(d, e, zi, zo, ld, n, T, fail, re, im);
     return re * re + im * im;
 }
 

@@ -383,11 +383,12 @@ def robustness_sweep_host(ctrl: np.ndarray, sigmas: np.ndarray, B: int, nspin: i
 
 
 def objective_host(x, rows, nspin: int, inspin: int, outspin: int, *, model: int = MODEL_COMPLEX3, zz: bool = False,
-                   want_fids: bool = True, want_stats: bool = False, dkw_eps: float = 0.0):
+                   want_fids: bool = True, want_stats: bool = False, dkw_eps: float = 0.0, want_amps: bool = False):
     """Fidelities of ONE controller x [N+1] under m explicit perturbation rows [m][K] (replay layout, sigma 1), or
     its nominal fidelity when rows is None: the optimiser-loop entry point (rc_objective_host), host numpy in and
     out, one H2D + one launch (+ one for the statistics) + one D2H, no allocations in steady state.
-    Returns fids [m], or (fids, stats [15]) with want_stats (fids is None without want_fids)."""
+    Returns fids [m], or (fids, stats [15]) with want_stats (fids is None without want_fids); with want_amps the
+    complex amplitudes U_k[out, in] as a complex128 array [m] are appended (real symmetric model only)."""
     require_cuda()
     x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
     if x.shape[0] != nspin + 1:
@@ -402,11 +403,16 @@ def objective_host(x, rows, nspin: int, inspin: int, outspin: int, *, model: int
         m, rp = rows.shape[0], C.c_void_p(rows.ctypes.data)
     out = np.empty(m) if want_fids else None
     st = np.empty(NUM_STATS) if want_stats else None
+    amps = np.empty(m, dtype=np.complex128) if want_amps else None
     check(lib().rc_objective_host(C.c_void_p(x.ctypes.data), nspin, inspin, outspin, rp, m, model, int(bool(zz)),
                                   float(dkw_eps), C.c_void_p(out.ctypes.data if want_fids else 0),
-                                  C.c_void_p(st.ctypes.data if want_stats else 0), _stream()))
+                                  C.c_void_p(st.ctypes.data if want_stats else 0),
+                                  C.c_void_p(amps.ctypes.data if want_amps else 0), _stream()))
     _count(2 if want_stats else 1)
-    return (out, st) if want_stats else out
+    res = (out, st) if want_stats else (out,)
+    if want_amps:
+        res = res + (amps,)
+    return res if len(res) > 1 else res[0]
 
 
 def arim_bootstrap_device(rims, nboot: int = 100, seed: int = 0):

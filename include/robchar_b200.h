@@ -183,9 +183,12 @@ int rc_robustness_sweep_host(const double* ctrl_host, int64_t C, int nspin, int 
  * rows_host == NULL with m = 1: the nominal fidelity of x (fidelity_ss(x), qnewton.py:383-400).
  * fids_host [m] and/or stats_host [15]: the statistics of the m fidelities taken as one segment (rc_stats_unsorted
  * order; row 0 = W1 to the ideal distribution = wass_cost's value, 1 - row 0 = their mean = fidelity_ss_av's value).
- * Returns RC_ERR_NONCONV after completing if an evaluation did not converge. */
+ * amps_host [m][2] (optional, RC_MODEL_REAL2 only): the complex transfer amplitudes U_k[out,in] = (re, im) — what
+ * Environment.state's fixed-Hamiltonian mode averages before squaring (RL...py:147-160: mean propagator, then
+ * |<out|mean_k U_k|in>|^2).  Returns RC_ERR_NONCONV after completing if an evaluation did not converge. */
 int rc_objective_host(const double* x_host, int nspin, int inspin, int outspin, const double* rows_host, int64_t m,
-                      int model, int zz, double dkw_eps, double* fids_host, double* stats_host, void* stream);
+                      int model, int zz, double dkw_eps, double* fids_host, double* stats_host, double* amps_host,
+                      void* stream);
 
 /* Dense complex matrix exponential of `batch` M x M matrices (M <= 32), interleaved (re, im) float64,
  * row-major: out = expm(A).  The generality path behind the reference's scipy.linalg.expm calls whose

@@ -334,6 +334,52 @@ def make_dense_path():
     print("dense_path done")
 
 
+def make_rl_env():
+    """Rewards / noise-free fidelities of the UNMODIFIED RL environment (RLreinforceXXchain_actionedtime.py:260-279)
+    driven the way ppo.py:338-363 drives it: reset, advance timestep, step(diag(bias increments))."""
+    import warnings
+    from RLreinforceXXchain_actionedtime import Environment
+    warnings.simplefilter("ignore")
+    out = {}
+    rs = np.random.RandomState(123)
+    n, i, o = 5, 0, 4
+    acts = rs.uniform(-9, 9, (6, n)); acts[3] += 14 * np.sign(acts[3])      # step 4 leaves the +-20 bounds: wrap
+    times = np.array([2.5, 7.25, 11.0, 19.5, 28.0, 33.5])                    # last one exceeds max_time: wrap
+    good = np.array(load_json(f"{REF}/noisy_analysis/lbfgs_spin_5_0-4_in")["lbfgs"]["5"]["controller"][0], dtype=float)
+    acts[0], times[0] = good[:n], good[n]                                   # a real optimised controller (fidelity ~ 1)
+    out["env_acts"], out["env_times"], out["env_meta"] = acts, times, np.array([n, i, o])
+
+    def drive(env, seed):
+        np.random.seed(seed)
+        env.reset()
+        rew, tf, done, act = [], [], [], []
+        for a, t in zip(acts, times):
+            env.timestep = t
+            ao, r, d = env.step(np.diag(a))
+            rew.append(np.real(r)); tf.append(np.real(env.tf)); done.append(d); act.append(np.diag(ao).copy())
+        return np.array(rew), np.array(tf), np.array(done), np.array(act)
+
+    for name, kw in (("plain", {}), ("hamnoisy", dict(ham_noisy=True)), ("shot", dict(fid_noisy=True, draws=20)),
+                     ("adaptive", dict(fid_noisy=True, adaptive=True, draws=20)), ("heis", dict(heisenberg_int=True)),
+                     ("fixed", dict(use_fixed_ham=True)), ("ring", dict(topo="ring"))):
+        env = Environment(n, i, o, noise=0.05, opt_train_size=12, **kw)
+        r, tf, d, a = drive(env, 17)
+        out[f"env_{name}_reward"], out[f"env_{name}_tf"], out[f"env_{name}_done"], out[f"env_{name}_action"] = r, tf, d, a
+        if name == "fixed":
+            out["env_fixed_truefid"] = np.array([np.real(env.true_fid(np.diag(acts[0]), timestep_n=times[0]))])
+        if name == "adaptive":
+            out["env_adaptive_calls"] = np.array([env.adp_func_calls_increment])
+    np.random.seed(5)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        env = Environment(n, i, o, noise=0.05, opt_train_size=4, transfer_learning=True)
+    out["env_tl_sys"] = env.sys
+    r, tf, d, a = drive(env, 18)
+    out["env_tl_reward"], out["env_tl_tf"] = r, tf
+    np.savez_compressed(f"{OUT}/rl_env.npz", **out)
+    print("rl_env done")
+
+
 if __name__ == "__main__":
     make_kat_bestfid()
     make_kat_mc_zero()
@@ -344,3 +390,4 @@ if __name__ == "__main__":
     make_large_n()
     make_objective_and_arim()
     make_dense_path()
+    make_rl_env()

@@ -633,6 +633,63 @@ def test_objective_host_entry_point(rb, n, model, zz):
         rb.engine.objective_host(x, np.zeros((3, K + 1)), n, 0, n - 1, model=model)
 
 
+def test_rl_environment_matches_reference(rb, capsys):
+    """Environment (RLreinforceXXchain_actionedtime.py) driven like ppo.py:338-363 — reset, advance timestep,
+    step(diag(bias increments)) — against rewards / noise-free fidelities / wrapped actions recorded from the
+    UNMODIFIED reference under the same numpy seeds: plain, noisy Hamiltonian, binomial and adaptive shot noise,
+    Heisenberg term, fixed-Hamiltonian mode (mean PROPAGATOR element, then squared modulus), ring topology and
+    transfer-learning couplings."""
+    g = load_golden("rl_env.npz")
+    acts, times = g["env_acts"], g["env_times"]
+    n, i, o = (int(v) for v in g["env_meta"])
+    Env = rb.RLreinforceXXchain_actionedtime.Environment
+
+    def drive(env, seed):
+        np.random.seed(seed)
+        o0 = env.reset()
+        assert o0.shape == (n, n) and not o0.any()
+        rew, tf, done, act = [], [], [], []
+        for a, t in zip(acts, times):
+            env.timestep = t
+            ao, r, d = env.step(np.diag(a))
+            rew.append(np.real(r)); tf.append(np.real(env.tf)); done.append(d); act.append(np.diag(ao).copy())
+        return np.array(rew), np.array(tf), np.array(done), np.array(act)
+
+    for name, kw in (("plain", {}), ("hamnoisy", dict(ham_noisy=True)), ("shot", dict(fid_noisy=True, draws=20)),
+                     ("adaptive", dict(fid_noisy=True, adaptive=True, draws=20)), ("heis", dict(heisenberg_int=True)),
+                     ("fixed", dict(use_fixed_ham=True)), ("ring", dict(topo="ring"))):
+        env = Env(n, i, o, noise=0.05, opt_train_size=12, **kw)
+        r, tf, d, a = drive(env, 17)
+        tol = 1e-12 if name in ("shot", "adaptive") else FID_TOL          # shot-noise rewards are ratios of counts
+        assert np.abs(r - g[f"env_{name}_reward"]).max() < tol, name
+        assert np.abs(tf - g[f"env_{name}_tf"]).max() < FID_TOL, name
+        assert np.array_equal(d, g[f"env_{name}_done"]) and np.abs(a - g[f"env_{name}_action"]).max() < 1e-12, name
+        if name == "fixed":
+            assert abs(env.true_fid(np.diag(acts[0]), timestep_n=times[0]) - g["env_fixed_truefid"][0]) < FID_TOL
+        if name == "adaptive":
+            assert env.adp_func_calls_increment == int(g["env_adaptive_calls"][0])
+    np.random.seed(5)
+    env = Env(n, i, o, noise=0.05, opt_train_size=4, transfer_learning=True)
+    assert np.array_equal(env.sys, g["env_tl_sys"])
+    r, tf, _, _ = drive(env, 18)
+    assert np.abs(r - g["env_tl_reward"]).max() < FID_TOL and np.abs(tf - g["env_tl_tf"]).max() < FID_TOL
+    # state() / fidelity() used directly (non-basis in_state after two applications): dense device exponential
+    env = Env(n, i, o)
+    env.reset(); env.timestep = 1.7
+    amat = np.diag(acts[1])
+    U = env.state(amat); env.state(amat)
+    Uref = __import__("scipy.linalg").linalg.expm(-1j * 1.7 * (env.sys + amat))
+    assert np.abs(U - Uref).max() < 1e-11
+    assert abs(env.fidelity() - abs((Uref @ Uref)[o, i]) ** 2) < FID_TOL
+    # amplitudes straight from the entry point
+    x = np.concatenate([acts[0], [times[0]]])
+    f, amps = rb.engine.objective_host(x, env._rows(env.randH[:7]), n, i, o, model=1, want_amps=True)
+    ref = np.array([__import__("scipy.linalg").linalg.expm(-1j * times[0] * (H + np.diag(acts[0])))[o, i] for H in env.randH[:7]])
+    assert np.abs(amps - ref).max() < FID_TOL and np.abs(f - np.abs(ref) ** 2).max() < FID_TOL
+    with pytest.raises(ValueError):
+        rb.engine.objective_host(x, np.zeros((2, 3 * n)), n, i, o, model=0, want_amps=True)   # complex model: gauge
+
+
 def test_arim_and_bootstrap_match_reference(rb):
     g = load_golden("objective_arim.npz")
     rims = g["arim_rims"]
