@@ -194,3 +194,66 @@ def test_reference_module_aliases():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def _oracle_objective_host(x, rows, nspin, inspin, outspin, *, model=0, zz=False, want_fids=True, want_stats=False,
+                           dkw_eps=0.0, want_amps=False):
+    """Stand-in for engine.objective_host built on the CPU oracle's Hamiltonian + scipy expm (test infrastructure):
+    lets the HOST logic of the optimiser-facing mirrors (draw order, action wrapping, shot noise, propagator
+    averaging) be checked against the reference goldens without a GPU."""
+    import scipy.linalg
+    x = np.asarray(x, dtype=float)
+    m = 1 if rows is None else rows.shape[0]
+    amps = np.zeros(m, dtype=complex)
+    for k in range(m):
+        H = orc.base_hamiltonian(nspin, "chain", zz)
+        if rows is not None:
+            H = H + orc.perturbation_from_draws(rows[k], nspin, model)
+        H = H + np.diag(x[:nspin])
+        amps[k] = scipy.linalg.expm(-1j * abs(x[nspin]) * H)[outspin, inspin]
+    f = np.abs(amps) ** 2
+    st = None
+    if want_stats:
+        st = np.full(15, np.nan)
+        st[0] = orc.wd_from_ideal(f.copy())
+    res = (f if want_fids else None,) + ((st,) if want_stats else ()) + ((amps,) if want_amps else ())
+    return res if len(res) > 1 else res[0]
+
+
+def test_rl_environment_host_logic_matches_reference(monkeypatch):
+    """The Environment mirror's host side (RNG draw order incl. reset's hidden draws, bias accumulation and
+    wrapping into the bounds, time wrapping, binomial / adaptive shot noise, mean-propagator reward, transfer-
+    learning couplings) against the goldens recorded from the unmodified reference; the device evaluation is
+    replaced by the oracle stand-in above (the GPU version of this test is test_rl_environment_matches_reference)."""
+    import scipy.linalg
+    import torch
+    monkeypatch.setattr(rb.engine, "objective_host", _oracle_objective_host)
+    monkeypatch.setattr(rb.engine, "expm_batch", lambda A: torch.as_tensor(np.array([scipy.linalg.expm(a) for a in np.asarray(A)])))
+    g = load_golden("rl_env.npz")
+    acts, times = g["env_acts"], g["env_times"]
+    n, i, o = (int(v) for v in g["env_meta"])
+    Env = rb.RLreinforceXXchain_actionedtime.Environment
+
+    def drive(env, seed):
+        np.random.seed(seed)
+        env.reset()
+        rew, tf, act = [], [], []
+        for a, t in zip(acts, times):
+            env.timestep = t
+            ao, r, d = env.step(np.diag(a))
+            rew.append(np.real(r)); tf.append(np.real(env.tf)); act.append(np.diag(ao).copy())
+        return np.array(rew), np.array(tf), np.array(act)
+
+    for name, kw in (("plain", {}), ("hamnoisy", dict(ham_noisy=True)), ("shot", dict(fid_noisy=True, draws=20)),
+                     ("adaptive", dict(fid_noisy=True, adaptive=True, draws=20)), ("heis", dict(heisenberg_int=True)),
+                     ("fixed", dict(use_fixed_ham=True)), ("ring", dict(topo="ring"))):
+        env = Env(n, i, o, noise=0.05, opt_train_size=12, opt_test_size=50, **kw)
+        r, tf, a = drive(env, 17)
+        assert np.abs(r - g[f"env_{name}_reward"]).max() < 1e-12, name
+        assert np.abs(tf - g[f"env_{name}_tf"]).max() < 1e-12, name
+        assert np.abs(a - g[f"env_{name}_action"]).max() < 1e-12, name
+    np.random.seed(5)
+    env = Env(n, i, o, noise=0.05, opt_train_size=4, opt_test_size=10, transfer_learning=True)
+    assert np.array_equal(env.sys, g["env_tl_sys"])
+    r, tf, _ = drive(env, 18)
+    assert np.abs(r - g["env_tl_reward"]).max() < 1e-12 and np.abs(tf - g["env_tl_tf"]).max() < 1e-12
