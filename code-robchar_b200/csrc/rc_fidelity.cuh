@@ -139,7 +139,8 @@ __device__ __forceinline__ double eval_reg(const FidArgs& a, long long s, long l
 // CTA shape of the register-resident kernels, measured on B200 at N = 4..8 (profiles/README.md, r01h):
 // Philox mode runs fastest as ONE 24-warp CTA per SM with the compiler held to 80 registers (a few
 // spilled doubles): 3.58e9 evaluations/s at N=7 against 3.1e9 for four 4-warp CTAs at 126 registers;
-// warp counts that are not a multiple of the four schedulers lose 5-10 %.  Replay mode stages its
+// warp counts that are not a multiple of the four schedulers lose 5-10 %; the short chains have registers to
+// spare and run 2 % faster with 32 (N <= 4) / 28 (N = 5) warps (r01k).  Replay mode stages its
 // rows behind CTA barriers and prefers three 8-warp CTAs.  N > 8 (non-default, RC_REG_MAX_N) keeps
 // 4-warp CTAs: the eigensolver state alone needs more than 80 registers there.
 // RC_REG_THREADS / RC_REG_MIN_BLOCKS (compile time) and RC_FID_THREADS (environment) are tuning overrides.
@@ -153,7 +154,7 @@ __device__ __forceinline__ double eval_reg(const FidArgs& a, long long s, long l
 #define RC_TILE_SYNC 0
 #endif
 __host__ __device__ constexpr int reg_cta_threads(int n, bool replay) {
-    return RC_REG_THREADS ? RC_REG_THREADS : (n > 8 ? 128 : (replay ? 256 : 768));
+    return RC_REG_THREADS ? RC_REG_THREADS : (n > 8 ? 128 : (replay ? 256 : (n <= 4 ? 1024 : (n == 5 ? 896 : 768))));
 }
 __host__ __device__ constexpr int reg_cta_min_blocks(int n, bool replay) {
     return RC_REG_MIN_BLOCKS ? RC_REG_MIN_BLOCKS : (n > 8 ? 1 : (replay ? 3 : 1));
