@@ -240,6 +240,21 @@ def test_fused_statistics_every_kernel_family(rb, n, B):
         assert np.abs(b[k] - m[key]).max() < 1e-12, key
 
 
+@pytest.mark.parametrize("n,B", [(6, 300), (8, 1000), (12, 520), (20, 100)])
+def test_fused_statistics_replay_mode(rb, n, B):
+    """Replay mode keeps the CTA-per-item fused kernels (rows staged behind CTA barriers): same statistics as the
+    materialised path on the same replayed normals, register and shared-memory families."""
+    ctrl = orc.synthetic_controllers(4, n, seed=50 + n)
+    sig = np.array([0.0, 0.07])
+    eps = float(orc.compute_dkw_error(0.05, B))
+    normals = np.random.RandomState(n).standard_normal((2, 4, B, 3 * n))
+    f = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, n - 1, replay=normals)
+    a = rb.engine.stats_unsorted(f, eps).cpu().numpy()
+    b = rb.engine.fidelity_stats(ctrl, sig, B, n, 0, n - 1, dkw_eps=eps, replay=normals).cpu().numpy()
+    assert np.abs(a - b).max() < 1e-12
+    assert np.array_equal(a[3:9], b[3:9])          # threshold counts exactly
+
+
 @pytest.mark.parametrize("B", [1, 2, 31, 100, 1000, 4096, 5000])
 def test_stats_vs_oracle(rb, B):
     rs = np.random.RandomState(B)
