@@ -221,20 +221,18 @@ static void fused_chunking_threads(long long threads, long long B, long long* ch
     *nchunks = (B + ch - 1) / ch;
     if (*nchunks < 1) *nchunks = 1;
 }
-// Draws per warp item of the warp-autonomous (Philox mode) fused kernels: the largest of 4096 .. 128 that still
-// gives every resident warp >= 32 items (static round-robin distribution: <= 3 % tail), else 128; the whole
-// segment (rounded up to 32) when it is shorter than that.
-static long long warp_chunk_for(long long nseg, long long B) {
-    const long long warps = (long long)device_sm_count() * MAX_CTA_WARPS;
-    long long chunk = 4096;
-    while (chunk > 128 && nseg * ((B + chunk - 1) / chunk) < 32 * warps) chunk >>= 1;
-    if (B < chunk) chunk = (B + 31) / 32 * 32;
-    return chunk;
-}
+// Draws per warp item of the warp-autonomous (Philox mode) fused kernels: 512 (16 passes), or the whole segment
+// rounded up to 32 when it is shorter.  A function of B ONLY: the grouping of draws into partials fixes the
+// order of the floating-point merges, so it must not depend on how many controllers this launch (this GPU's
+// shard) holds — the statistics are bit-identical for any controller sharding.  512 keeps the tail of the static
+// round-robin distribution small already for modest sweeps (>= 30 items per warp from 5e7 evaluations on) at
+// 0.27 B of partials per draw.
+constexpr long long WARP_CHUNK = 512;
+static long long warp_chunk_for(long long B) { return B < WARP_CHUNK ? (B + 31) / 32 * 32 : WARP_CHUNK; }
 
 static void fused_chunking(int nspin, bool replay, long long nseg, long long B, long long* chunk, long long* nchunks) {
     if (!replay) {
-        *chunk = warp_chunk_for(nseg, B);
+        *chunk = warp_chunk_for(B);
         *nchunks = (B + *chunk - 1) / *chunk;
         return;
     }
@@ -393,7 +391,7 @@ extern "C" size_t rc_fidelity_stats_workspace_bytes(int64_t nseg, int64_t B) {
         fused_chunking_threads(t, B, &chunk, &nchunks);
         if (nchunks > nmax) nmax = nchunks;
     }
-    const long long wc = warp_chunk_for(nseg, B);                      // Philox mode
+    const long long wc = warp_chunk_for(B);                            // Philox mode
     const long long warp_items = (B + wc - 1) / wc;
     if (warp_items > nmax) nmax = warp_items;
     return (size_t)nseg * nmax * PART_DOUBLES * sizeof(double) + 256;

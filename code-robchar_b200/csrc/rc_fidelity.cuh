@@ -287,8 +287,7 @@ __device__ __forceinline__ void moments_block_merge(Moments& m, double* scratch 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warp-autonomous fused path (Philox mode).  Work item = (segment, chunk of 128..4096 draws) processed by ONE warp in
-// chunk / 32 passes: no CTA barrier anywhere (a barrier per item keeps re-aligning the 24 warps of the CTA
+// Warp-autonomous fused path (Philox mode).  Work item = (segment, 512 draws) processed by ONE warp in 16 passes: no CTA barrier anywhere (a barrier per item keeps re-aligning the 24 warps of the CTA
 // to the slowest one).  Nothing statistical stays live in registers across an evaluation (the eigensolver
 // already fills the register budget; 20 extra live registers cost more in spills than the statistics cost in
 // instructions): after every pass the warp reduces its 32 fidelities by shuffles / ballots and lane 0 adds the

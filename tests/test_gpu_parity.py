@@ -560,6 +560,44 @@ def test_full_size_properties_nspin7(rb):
     assert tau[0, 0] > 0.5 and np.all(np.diag(tau) > 0.3)
 
 
+@pytest.mark.parametrize("n,C,B,S,zz", [(16, 1250, 200000, 1, True), (32, 40, 100000, 3, False)])
+def test_scaled_config_slices_size_independent_properties(rb, n, C, B, S, zz):
+    """BASELINE configs[3] / configs[4] at (a slice of) one GPU's share, fused streaming statistics (no fidelity
+    tensor): determinism, invariance under controller sharding (c_offset) and linearity under draw sharding
+    (b_offset), the sigma = 0 row against the oracle, bracket ordering of the DKW variants, and a spot check of the
+    in-kernel Philox draws against the oracle on a replayed slice."""
+    ctrl = orc.synthetic_controllers(C, n, seed=n)
+    sig = np.array([0.05]) if S == 1 else np.array([0.0, 0.05, 0.1])
+    eps = float(orc.compute_dkw_error(0.05, B))
+    kw = dict(dkw_eps=eps, seed=2024, zz=zz)
+    st = rb.engine.fidelity_stats(ctrl, sig, B, n, 0, n - 1, **kw)
+    assert torch.equal(st, rb.engine.fidelity_stats(ctrl, sig, B, n, 0, n - 1, **kw))            # deterministic
+    assert bool(torch.isfinite(st).all())
+    lo, hi = C // 3, C // 3 + max(1, C // 5)
+    part = rb.engine.fidelity_stats(ctrl[lo:hi], sig, B, n, 0, n - 1, c_offset=lo, **kw)
+    assert torch.equal(part, st[:, :, lo:hi])                                                    # controller sharding
+    h = B // 2
+    a = rb.engine.fidelity_stats(ctrl[:8], sig, h, n, 0, n - 1, b_offset=0, **{**kw, "dkw_eps": eps})
+    b = rb.engine.fidelity_stats(ctrl[:8], sig, B - h, n, 0, n - 1, b_offset=h, **{**kw, "dkw_eps": eps})
+    assert float((0.5 * (a[0:3] + b[0:3]) - st[0:3, :, :8]).abs().max()) < 1e-12                 # W is linear in the draws
+    assert float((0.5 * (a[3:9] + b[3:9]) - st[3:9, :, :8]).abs().max()) < 1e-12                 # so are the Q counts
+    assert torch.equal(torch.maximum(a[12:], b[12:]), st[12:, :, :8])                            # worst case = max of halves
+    W, Wu, Wl = st[0], st[1], st[2]
+    assert bool((Wu >= W - 1e-15).all()) and bool((Wl <= W + 1e-15).all())                       # upper / lower bracket
+    assert bool((st[3:9] <= 0).all()) and bool((st[3:9] >= -1).all()) and bool((st[9:12] >= 0).all())
+    if S > 1:                                                                                    # sigma = 0 row
+        sub = np.arange(0, C, max(1, C // 7))
+        nominal = orc.fidelity_batch(ctrl[sub], n, 0, n - 1, zz=zz)
+        assert np.abs(st[0, 0, sub].cpu().numpy() - (1 - nominal)).max() < FID_TOL
+        assert bool((st[9, 0] == 0).all())                                                       # std of identical samples
+    # the draws behind these statistics, replayed through the oracle on a slice (controller 5, draws 1000..1007)
+    s_idx = S - 1
+    nrm = rb.engine.philox_normals(1, n, S, 8, seed=2024, c_offset=5, b_offset=1000).cpu().numpy()
+    f_dev = rb.engine.fidelity_mc(ctrl[5:6], sig, 8, n, 0, n - 1, seed=2024, c_offset=5, b_offset=1000, zz=zz).cpu().numpy()
+    f_or = orc.fidelity_mc_replay(ctrl[5:6], sig, nrm, n, 0, n - 1, zz=zz)
+    assert np.abs(f_dev - f_or)[s_idx].max() < FID_TOL
+
+
 def test_rank_consistency_single_call(rb):
     """rc_rank_consistency == per-group composition of the reference functions (top-k in original
     column order, clustered vs ordinal ranks, Kendall matrix), incl. the host-buffer sweep call."""
