@@ -221,14 +221,22 @@ static void fused_chunking_threads(long long threads, long long B, long long* ch
     *nchunks = (B + ch - 1) / ch;
     if (*nchunks < 1) *nchunks = 1;
 }
-// Draws per warp item of the warp-autonomous (Philox mode) fused kernels: 512 (16 passes), or the whole segment
+// Draws per warp item of the warp-autonomous (Philox mode) fused kernels: 256 (8 passes), or the whole segment
 // rounded up to 32 when it is shorter.  A function of B ONLY: the grouping of draws into partials fixes the
 // order of the floating-point merges, so it must not depend on how many controllers this launch (this GPU's
-// shard) holds — the statistics are bit-identical for any controller sharding.  512 keeps the tail of the static
-// round-robin distribution small already for modest sweeps (>= 30 items per warp from 5e7 evaluations on) at
-// 0.27 B of partials per draw.
-constexpr long long WARP_CHUNK = 512;
-static long long warp_chunk_for(long long B) { return B < WARP_CHUNK ? (B + 31) / 32 * 32 : WARP_CHUNK; }
+// shard) holds — the statistics are bit-identical for any controller sharding.  256 keeps the tail of the static
+// round-robin distribution small already for modest sweeps (>= 30 items per warp from 3e7 evaluations on) at
+// 0.53 B of partials per draw.
+constexpr long long WARP_CHUNK = 256;
+static long long warp_chunk_for(long long B) {
+    static long long chunk = 0;   // RC_WARP_CHUNK (environment, multiple of 32) overrides for tuning
+    if (!chunk) {
+        const char* e = getenv("RC_WARP_CHUNK");
+        const long long v = e ? atoll(e) : 0;
+        chunk = (v >= 32 && v % 32 == 0) ? v : WARP_CHUNK;
+    }
+    return B < chunk ? (B + 31) / 32 * 32 : chunk;
+}
 
 static void fused_chunking(int nspin, bool replay, long long nseg, long long B, long long* chunk, long long* nchunks) {
     if (!replay) {

@@ -294,7 +294,9 @@ __device__ __forceinline__ void moments_block_merge(Moments& m, double* scratch 
 // pass totals to the warp's 16-double accumulator in shared memory.  Sums are taken about a shift (the item's
 // first sample) so the variance does not cancel; at the end of the item the accumulator becomes a Moments
 // partial; fused_finalize_kernel merges the partials of a segment in chunk order as before.  Fixed order
-// everywhere => deterministic.
+// everywhere => deterministic.  (Tried instead: per-lane running sums in private shared-memory slots behind the
+// lane's row, warp merge once per item — +2-3 % at N <= 6 but -2 % at N = 7 and -16 % at N = 8: the larger
+// shared-memory carve-out leaves too little L1 for the kernel's register spills.)
 // ---------------------------------------------------------------------------------------------
 constexpr int WACC_DOUBLES = 16;   // sy[3] syy[3] c95[3] c98[3] | mn shift n nan
 enum WaccSlot { WA_SY = 0, WA_SYY = 3, WA_C95 = 6, WA_C98 = 9, WA_MN = 12, WA_SHIFT = 13, WA_N = 14, WA_NAN = 15 };
