@@ -7,6 +7,7 @@
 
 One step = one pass of the hot path over one synthetic batch: Philox noise -> perturbed
 Hamiltonians -> fidelities [S][C][B] -> 15 statistics (sort-free streaming pass) -> per-group top-k ->
+(all launches of a step issued from one C call, rc_robustness_sweep, on device-resident buffers)
 clustered/ordinal ranks -> Kendall tau matrices (+ one all-gather of the statistics for N > 1).
 Default workload `paper_n7` = BASELINE.json configs[2]: nspin=7 0->6, 19 controller groups x 1000
 controllers (the paper's fig-5 sweep size per problem), S=11 sigma_sim levels, B=100 draws.
@@ -212,21 +213,18 @@ def run_ours(args):
     fused = B > 512   # long segments: streaming statistics (no fidelity tensor); short ones: materialise + sort-free statistics pass
     fid_events = []
 
+    # the device-resident step: ONE C call issues every launch (rc_robustness_sweep); the evolution kernel is
+    # timed by a pair of events recorded inside that call, on the launching stream, within the timed region
+    plan = eng.RobustnessSweepPlan(C_local, S, B, nspin, inspin, outspin, groups=groups, topk=topk, dkw_eps=eps, zz=zz,
+                                   fused=fused, fids=None if fused else fids)
+
     def step(seed, timed=False):
-        if fused:
-            st = eng.fidelity_stats(ctrl, sig, B, nspin, inspin, outspin, dkw_eps=eps, seed=seed, c_offset=lo, zz=zz,
-                                    check_convergence=False)
-        else:
-            if timed:
-                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                e0.record()
-            eng.fidelity_mc(ctrl, sig, B, nspin, inspin, outspin, seed=seed, c_offset=lo, zz=zz, out=fids,
-                            check_convergence=False)
-            if timed:
-                e1.record(); fid_events.append((e0, e1))
-            st = eng.stats_unsorted(fids, eps, check_legal=False)   # sort-free streaming pass (rc_stats_unsorted)
-        tau, sel, wsel = eng.grouped_rank_consistency(st[0], groups, topk=topk)
-        arim, arim_std = eng.arim_bootstrap_device(wsel, 100, seed=seed)     # fig-5 ARIM + bootstrap error bar
+        ev = None
+        if timed:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(); ev[1].record()          # creates the CUDA handles; re-recorded inside the call
+            fid_events.append(ev)
+        st, tau = plan.run(ctrl, sig, seed=seed, c_offset=lo, evolution_events=ev)
         if world > 1:
             st = rb.dist.all_gather_stats(st, C_total)
         return st, tau
@@ -257,15 +255,6 @@ def run_ours(args):
     launches = (eng.LAUNCHES - launches0)
     # the kernel-only time of the dominant (evolution) kernel, events on the launching stream
     fid_ms = float(np.mean([a.elapsed_time(b) for a, b in fid_events])) if fid_events else None
-    if fused:
-        # fused path: the evolution kernel is the whole rc_fidelity_stats call; time it separately
-        ev = []
-        for k in range(3):
-            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-            a.record()
-            eng.fidelity_stats(ctrl, sig, B, nspin, inspin, outspin, dkw_eps=eps, seed=k, c_offset=lo, zz=zz, check_convergence=False)
-            b.record(); torch.cuda.synchronize(); ev.append(a.elapsed_time(b))
-        fid_ms = float(np.mean(ev))
     # ---- e2e: host buffers through the public API, copies inside the timed region --------------------
     ctrl_pinned = torch.as_tensor(ctrl_np).pin_memory()
     sig_host = np.ascontiguousarray(sig_np)

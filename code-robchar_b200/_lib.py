@@ -55,6 +55,9 @@ _SIGNATURES = {
     "rc_rank_consistency": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _f64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rc_robustness_sweep_host": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64,
                                            _f64, _i32, _i64, _i64, _f64, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "rc_robustness_sweep_workspace_bytes": (_sz, [_i64, _i32, _i64, _i32, _i64, _i64]),
+    "rc_robustness_sweep": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64, _f64, _i32,
+                                      _i64, _i64, _f64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "rc_arim_bootstrap": (C.c_int, [_vp, _i64, _i64, _i32, _u64, _vp, _vp, _vp]),
     "rc_mc_sweep_host": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64, _vp, _f64,
                                    _i32, _vp, _vp, _vp]),

@@ -103,6 +103,70 @@ extern "C" int rc_fp64_peak_tflops(double* tflops, void* stream) {
     return RC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Whole fig-4/5 sweep on DEVICE buffers: every launch of the step issued from one C call (no allocation, no
+// synchronisation) — the device-resident twin of rc_robustness_sweep_host.
+// ------------------------------------------------------------------------------------------------
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+extern "C" size_t rc_robustness_sweep_workspace_bytes(int64_t C, int S, int64_t B, int fused, int64_t G, int64_t topk) {
+    if (C <= 0 || S <= 0 || B <= 0 || G <= 0 || C % G) return 256;
+    const size_t ws_f = fused ? rc_fidelity_stats_workspace_bytes((int64_t)S * C, B) : 0;
+    const size_t ws_r = rc_rank_consistency_workspace_bytes(S, G, C / G, topk);
+    if (ws_r == 0) return 0;
+    return align256(ws_f) + align256(ws_r) + 256;
+}
+
+extern "C" int rc_robustness_sweep(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
+                                   const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed,
+                                   int64_t c_offset, int64_t b_offset, double dkw_eps, int fused, int64_t G, int64_t topk,
+                                   double alpha_cluster, double* fids_dev, double* stats_dev, double* tau_dev,
+                                   int64_t* sel_dev, double* wsel_dev, int nboot, double* arim_dev, double* arim_std_dev,
+                                   unsigned long long* counters_dev, void* workspace_dev, size_t workspace_bytes,
+                                   void* ev_evolution_begin, void* ev_evolution_end, void* stream) {
+    if (C < 0 || S < 0 || B < 1) return set_error(RC_ERR_BAD_ARG, "rc_robustness_sweep: bad sizes C=%lld S=%d B=%lld", (long long)C, S, (long long)B);
+    if ((long long)S * C == 0) return RC_OK;
+    if (G < 1 || C % G) return set_error(RC_ERR_BAD_ARG, "rc_robustness_sweep: C=%lld is not a multiple of G=%lld", (long long)C, (long long)G);
+    if (!stats_dev || !tau_dev || !sel_dev || !wsel_dev) return set_error(RC_ERR_NULL, "rc_robustness_sweep: null stats/tau/sel/wsel output");
+    if (!fused && !fids_dev) return set_error(RC_ERR_NULL, "rc_robustness_sweep: the materialising path needs fids_dev");
+    const size_t need = rc_robustness_sweep_workspace_bytes(C, S, B, fused, G, topk);
+    if (need == 0) return set_error(RC_ERR_BAD_ARG, "rc_robustness_sweep: ranking problem too large");
+    if (!workspace_dev || workspace_bytes < need)
+        return set_error(RC_ERR_WORKSPACE, "rc_robustness_sweep: workspace %zu < required %zu bytes", workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nseg = (long long)S * C;
+    unsigned long long* nonconv = counters_dev;
+    unsigned long long* illegal = counters_dev ? counters_dev + 1 : nullptr;
+    char* ws = (char*)workspace_dev;
+    const size_t ws_f = fused ? rc_fidelity_stats_workspace_bytes(nseg, B) : 0;
+    int rcode;
+    // optional caller-owned events around the evolution launch(es): lets a benchmark time the dominant kernel
+    // inside its timed region without splitting the step into several calls
+    if (ev_evolution_begin) RC_CUDA_TRY(cudaEventRecord((cudaEvent_t)ev_evolution_begin, st));
+    if (fused) {
+        rcode = rc_fidelity_stats(ctrl_dev, C, nspin, inspin, outspin, sigma_dev, S, B, model, zz, seed, c_offset, b_offset,
+                                  nullptr, dkw_eps, stats_dev, nonconv, ws, ws_f, st);
+        if (rcode) return rcode;
+        if (ev_evolution_end) RC_CUDA_TRY(cudaEventRecord((cudaEvent_t)ev_evolution_end, st));
+    } else {
+        rcode = fidelity_mc_impl("rc_robustness_sweep", ctrl_dev, C, nspin, inspin, outspin, sigma_dev, S, B, model, zz, seed,
+                                 c_offset, b_offset, nullptr, fids_dev, nonconv, 0, st);
+        if (rcode) return rcode;
+        if (ev_evolution_end) RC_CUDA_TRY(cudaEventRecord((cudaEvent_t)ev_evolution_end, st));
+        rcode = stats_unsorted_impl(fids_dev, nseg, B, dkw_eps, stats_dev, nseg, illegal, st);
+        if (rcode) return rcode;
+    }
+    char* ws_rank = ws + align256(ws_f);
+    rcode = rc_rank_consistency(stats_dev, S, G, C / G, topk, alpha_cluster, tau_dev, sel_dev, wsel_dev, ws_rank,
+                                rc_rank_consistency_workspace_bytes(S, G, C / G, topk), st);
+    if (rcode) return rcode;
+    if (arim_dev && arim_std_dev) {
+        const int64_t Cg = C / G, k = topk < Cg ? topk : Cg;
+        rcode = rc_arim_bootstrap(wsel_dev, G * S, k, nboot > 0 ? nboot : 100, seed ^ 0x9E3779B97F4A7C15ull, arim_dev, arim_std_dev, st);
+    }
+    return rcode;
+}
+
 static int sweep_host_impl(const double* ctrl_host, int64_t C, int nspin, int inspin, int outspin,
                            const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
                            int64_t c_offset, int64_t b_offset, const double* replay_host, double dkw_eps,

@@ -415,6 +415,57 @@ def objective_host(x, rows, nspin: int, inspin: int, outspin: int, *, model: int
     return res if len(res) > 1 else res[0]
 
 
+class RobustnessSweepPlan:
+    """Device buffers + workspace of rc_robustness_sweep for one problem shape, allocated once; run() issues the
+    whole fig-4/5 sweep (evolution, statistics, top-k, Kendall matrices, ARIM bootstrap) from ONE C call with no
+    allocation and no synchronisation — the device-resident twin of robustness_sweep_host."""
+
+    def __init__(self, C_: int, S: int, B: int, nspin: int, inspin: int, outspin: int, *, groups: int = 1, topk: int = 100,
+                 alpha_cluster: float = 0.05, dkw_eps: float = 0.0, model: int = MODEL_COMPLEX3, zz: bool = False,
+                 fused: bool = False, nboot: int = 100, fids: torch.Tensor | None = None):
+        dev = require_cuda()
+        if C_ % groups:
+            raise ValueError("controller count must be a multiple of the group count")
+        self.shape = (C_, S, B, nspin, inspin, outspin)
+        self.groups, self.topk, self.alpha, self.eps = groups, topk, float(alpha_cluster), float(dkw_eps)
+        self.model, self.zz, self.fused, self.nboot = model, int(bool(zz)), int(bool(fused)), int(nboot)
+        k = min(topk, C_ // groups)
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.fids = None if fused else (fids if fids is not None else torch.empty((S, C_, B), **f64))
+        self.stats = torch.empty((NUM_STATS, S, C_), **f64)
+        self.tau = torch.empty((groups, S, S), **f64)
+        self.sel = torch.empty((groups, k), dtype=torch.int64, device=dev)
+        self.wsel = torch.empty((groups, S, k), **f64)
+        self.arim = torch.empty((groups, S), **f64)
+        self.arim_std = torch.empty((groups, S), **f64)
+        self.counters = Counters(dev)
+        self.wb = lib().rc_robustness_sweep_workspace_bytes(C_, S, B, self.fused, groups, topk)
+        if self.wb == 0:
+            raise ValueError("ranking problem too large")
+        self.ws = torch.empty(self.wb, dtype=torch.uint8, device=dev)
+
+    def run(self, ctrl: torch.Tensor, sigmas: torch.Tensor, *, seed: int = 0, c_offset: int = 0, b_offset: int = 0,
+            evolution_events=None):
+        """ctrl [C][N+1], sigmas [S]: contiguous float64 CUDA tensors.  Returns (stats, tau); the other outputs are
+        the plan's attributes (sel, wsel, arim, arim_std, fids, counters).  evolution_events: optional pair of
+        torch.cuda.Event(enable_timing=True) recorded around the evolution launch (they must have been recorded
+        once before so that their CUDA handles exist)."""
+        C_, S, B, nspin, inspin, outspin = self.shape
+        if not (ctrl.is_cuda and ctrl.dtype == torch.float64 and ctrl.is_contiguous() and tuple(ctrl.shape) == (C_, nspin + 1)):
+            raise ValueError(f"ctrl must be a contiguous float64 CUDA tensor [{C_}][{nspin + 1}]")
+        if not (sigmas.is_cuda and sigmas.dtype == torch.float64 and sigmas.is_contiguous() and sigmas.numel() == S):
+            raise ValueError(f"sigmas must be a contiguous float64 CUDA tensor [{S}]")
+        check(lib().rc_robustness_sweep(_ptr(ctrl), C_, nspin, inspin, outspin, _ptr(sigmas), S, B, self.model, self.zz,
+                                        C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, self.eps, self.fused,
+                                        self.groups, self.topk, self.alpha, _ptr(self.fids), _ptr(self.stats),
+                                        _ptr(self.tau), _ptr(self.sel), _ptr(self.wsel), self.nboot, _ptr(self.arim),
+                                        _ptr(self.arim_std), self.counters.nonconv_ptr, _ptr(self.ws), self.wb,
+                                        C.c_void_p(evolution_events[0].cuda_event if evolution_events else 0),
+                                        C.c_void_p(evolution_events[1].cuda_event if evolution_events else 0), _stream()))
+        _count(12)  # evolution + (finalize when fused | sort-free statistics otherwise) + 9 ranking kernels + ARIM bootstrap
+        return self.stats, self.tau
+
+
 def arim_bootstrap_device(rims, nboot: int = 100, seed: int = 0):
     """(ARIM [R], bootstrap std [R]) of RIM rows [R][k] entirely on the device (rc_arim_bootstrap, Philox
     resampling indices)."""

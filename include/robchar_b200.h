@@ -175,6 +175,23 @@ int rc_robustness_sweep_host(const double* ctrl_host, int64_t C, int nspin, int 
                              int64_t topk, double alpha_cluster, double* stats_host, double* tau_host,
                              int64_t* sel_host, int nboot, double* arim_host, double* arim_std_host, void* stream);
 
+/* The same fig-4/5 sweep on DEVICE buffers: evolution (+ statistics), per-group top-k / Kendall matrices and the
+ * ARIM bootstrap issued from one C call, no allocation and no synchronisation inside (what bench.py times as the
+ * device-resident step).  fids_dev [S][C][B] is required unless `fused`; stats_dev [15][S][C], tau_dev [G][S][S],
+ * sel_dev int64 [G][k], wsel_dev [G][S][k] (k = min(topk, C/G)); arim_dev / arim_std_dev [G][S] optional;
+ * counters_dev optional uint64[2] = {non-converged evaluations, illegal samples}, accumulated (zero them first).
+ * ev_evolution_begin / ev_evolution_end: optional caller-owned cudaEvent_t recorded on `stream` around the
+ * evolution launch (with its finalize kernel when fused), so a benchmark can time the dominant kernel inside its
+ * timed region.  workspace: rc_robustness_sweep_workspace_bytes(C, S, B, fused, G, topk). */
+size_t rc_robustness_sweep_workspace_bytes(int64_t C, int S, int64_t B, int fused, int64_t G, int64_t topk);
+int rc_robustness_sweep(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
+                        const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed,
+                        int64_t c_offset, int64_t b_offset, double dkw_eps, int fused, int64_t G, int64_t topk,
+                        double alpha_cluster, double* fids_dev, double* stats_dev, double* tau_dev, int64_t* sel_dev,
+                        double* wsel_dev, int nboot, double* arim_dev, double* arim_std_dev,
+                        unsigned long long* counters_dev, void* workspace_dev, size_t workspace_bytes,
+                        void* ev_evolution_begin, void* ev_evolution_end, void* stream);
+
 /* Low-latency objective evaluation for optimiser loops: ONE controller x_host [N+1] against m explicit
  * perturbations, host buffers in and out, one H2D + one launch + one D2H through cached pinned staging (no
  * allocation in steady state).  rows_host [m][K]: the perturbation of each evaluation in replay layout with

@@ -628,6 +628,36 @@ def test_rank_consistency_single_call(rb):
     assert np.array_equal(out["tau"], t2.cpu().numpy(), equal_nan=True) and np.array_equal(out["topk_idx"], s2.cpu().numpy())
 
 
+@pytest.mark.parametrize("fused", [False, True])
+def test_device_sweep_plan_equals_composition(rb, fused):
+    """rc_robustness_sweep (one C call on device buffers, what bench.py times) == the same stages called one by
+    one, bit for bit; the optional events bracket the evolution launch."""
+    n, G, Cg, S, B, k = 6, 3, 40, 5, (700 if fused else 64), 12
+    ctrl = torch.as_tensor(orc.synthetic_controllers(G * Cg, n)).cuda()
+    sig = torch.linspace(0, 0.1, S, dtype=torch.float64).cuda()
+    eps = float(orc.compute_dkw_error(0.05, B))
+    plan = rb.engine.RobustnessSweepPlan(G * Cg, S, B, n, 0, 3, groups=G, topk=k, dkw_eps=eps, fused=fused, nboot=50)
+    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev[0].record(); ev[1].record()
+    st, tau = plan.run(ctrl, sig, seed=6, c_offset=2, evolution_events=ev)
+    torch.cuda.synchronize()
+    assert ev[0].elapsed_time(ev[1]) > 0
+    plan.counters.raise_if_set()
+    if fused:
+        st_ref = rb.engine.fidelity_stats(ctrl, sig, B, n, 0, 3, dkw_eps=eps, seed=6, c_offset=2)
+    else:
+        f_ref, st_ref = rb.engine.fidelity_mc_stats(ctrl, sig, B, n, 0, 3, dkw_eps=eps, seed=6, c_offset=2)
+        assert torch.equal(plan.fids, f_ref)
+    assert torch.equal(st, st_ref)
+    tau_ref, sel_ref, wsel_ref = rb.engine.grouped_rank_consistency(st_ref[0], G, topk=k)
+    assert torch.equal(tau.nan_to_num(nan=9.0), tau_ref.nan_to_num(nan=9.0))
+    assert torch.equal(plan.sel, sel_ref) and torch.equal(plan.wsel, wsel_ref)
+    a_ref, s_ref = rb.engine.arim_bootstrap_device(wsel_ref, 50, seed=6 ^ 0x9E3779B97F4A7C15)
+    assert torch.equal(plan.arim, a_ref) and torch.equal(plan.arim_std, s_ref)
+    with pytest.raises(ValueError):
+        plan.run(ctrl[:, :3].contiguous(), sig)
+
+
 def test_optimiser_objectives_match_reference(rb):
     """LBFGS-compatible evaluator vs the unmodified qnewton.LBFGS (fidelity_ss_av, wass_cost, shot noise)."""
     g = load_golden("objective_arim.npz")
