@@ -257,3 +257,27 @@ def test_rl_environment_host_logic_matches_reference(monkeypatch):
     assert np.array_equal(env.sys, g["env_tl_sys"])
     r, tf, _ = drive(env, 18)
     assert np.abs(r - g["env_tl_reward"]).max() < 1e-12 and np.abs(tf - g["env_tl_tf"]).max() < 1e-12
+
+
+def test_lbfgs_objective_host_logic_matches_reference(monkeypatch):
+    """Host side of the qnewton.LBFGS mirror (fixed Hamiltonian sets from seed 4, perturbation draw order, binomial
+    and adaptive shot noise, W1 objective) against the goldens recorded from the unmodified reference, with the
+    device evaluation replaced by the oracle stand-in (GPU version: test_optimiser_objectives_match_reference)."""
+    monkeypatch.setattr(rb.engine, "objective_host", _oracle_objective_host)
+    g = load_golden("objective_arim.npz")
+    n, i, o, train = (int(v) for v in g["obj_meta"])
+    env = rb.qnewton.LBFGS(n, i, o, noise=0.05, opt_train_size=train, opt_test_size=200)
+    assert np.array_equal(env.randH[0], g["obj_randH0"])
+    X = g["obj_X"]
+    av10 = np.array([env.fidelity_ss_av(x, reps=10) for x in X])
+    assert np.abs(av10 - g["obj_av10"]).max() < 1e-12
+    np.random.seed(11)
+    w = np.array([env.wass_cost(x, 7) for x in X])
+    assert np.abs(w - g["obj_wass7"]).max() < 1e-12
+    np.random.seed(12)
+    shot = np.array([env.fidelity_ss(x, noisy=True, ham_noisy=True) for x in X])
+    assert np.array_equal(shot, g["obj_shot"])
+    env.adaptive = True
+    np.random.seed(13)
+    ad = np.array([env.fidelity_ss(x, noisy=True, ham_noisy=False) for x in X])
+    assert np.abs(ad - g["obj_adaptive"]).max() < 1e-12
