@@ -126,6 +126,49 @@ RC_HD void rc_sincos(double x, double* sn, double* cs) {
 #endif
 }
 
+// Table-driven sincos for the phase sum (7 per evaluation at N = 7): reduce by pi/32 instead of pi/2 (same
+// three-constant Cody-Waite split scaled by 1/16: exact for |k| < 2^20, i.e. |x| < 1e5), look up
+// (sin, cos)(j pi/32) — 64 correctly rounded pairs, 1 KB, L1 resident — and finish with degree-7 / degree-8
+// polynomials on |r| <= pi/64 and the angle-addition formulas: 17 FP64 instructions and no quadrant selects
+// instead of 23 + selects.  Max error 1.6e-16 on [-1e5, 1e5] (tools/sincos_check.cpp).
+struct RcSinCos { double s, c; };
+#if defined(__CUDACC__)
+static __device__ const RcSinCos RC_SC_TAB[64] = {
+#include "rc_sincos_table.inc"
+};
+#endif
+static const RcSinCos RC_SC_TAB_HOST[64] = {
+#include "rc_sincos_table.inc"
+};
+RC_COEF RC_PIO32_C[4] = {6.36619772367581382433e-01 * 16.0, 1.57079632673412561417e+00 / 16.0,
+                         6.07710050630396597660e-11 / 16.0, 2.02226624871116645580e-21 / 16.0};
+RC_COEF RC_SCP_C[7] = {-1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0,               // sin: r + r^3 (c3 + r^2 (c5 + r^2 c7))
+                       1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0, -0.5};       // cos: 1 + r^2 (c2 + r^2 (c4 + r^2 (c6 + r^2 c8)))
+
+RC_HD void rc_sincos_tab_core(double x, const RcSinCos* tab, double* sn, double* cs) {
+    const double k = rint(x * RC_PIO32_C[0]);
+    double r = fma(-k, RC_PIO32_C[1], x);
+    r = fma(-k, RC_PIO32_C[2], r);
+    r = fma(-k, RC_PIO32_C[3], r);
+    const RcSinCos t = tab[(int)k & 63];
+    const double r2 = r * r;
+    const double ps = fma(r2, fma(r2, RC_SCP_C[0], RC_SCP_C[1]), RC_SCP_C[2]);
+    const double s = fma(r * r2, ps, r);
+    const double pc = fma(r2, fma(r2, fma(r2, RC_SCP_C[3], RC_SCP_C[4]), RC_SCP_C[5]), RC_SCP_C[6]);
+    const double c = fma(r2, pc, 1.0);
+    *sn = fma(t.s, c, t.c * s);
+    *cs = fma(t.c, c, -(t.s * s));
+}
+
+RC_HD void rc_sincos_tab(double x, double* sn, double* cs) {
+#if defined(__CUDA_ARCH__)
+    if (!(fabs(x) < 1.0e5)) { sincos(x, sn, cs); return; }
+    rc_sincos_tab_core(x, RC_SC_TAB, sn, cs);
+#else
+    sincos(x, sn, cs);
+#endif
+}
+
 // sincos(2 pi u) for u in [0,1): exact reduction (k = rint(4u), r = (2u - k/2) pi).
 RC_HD void rc_sincos_2pi(double u, double* sn, double* cs) {
 #if defined(__CUDA_ARCH__)

@@ -317,7 +317,7 @@ RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int ou
 #endif
     for (int k = 0; k < N; ++k) {
         double sn, cs;
-        rc_sincos(scratch[(size_t)k * sstride] * T, &sn, &cs);
+        rc_sincos_tab(scratch[(size_t)k * sstride] * T, &sn, &cs);
         const double w = scratch[(size_t)(N + k) * sstride];
         re = fma(w, cs, re);
         im = fma(-w, sn, im);
@@ -416,7 +416,7 @@ RC_HD void amplitude_strided(double* d, double* e, double* zi, double* zo, int l
     double re = 0.0, im = 0.0;
     for (int k = 0; k < n; ++k) {
         double sn, cs;
-        rc_sincos(AT(d, k) * T, &sn, &cs);
+        rc_sincos_tab(AT(d, k) * T, &sn, &cs);
         double w = AT(zo, k) * AT(zi, k);
         re = fma(w, cs, re);
         im = fma(-w, sn, im);
