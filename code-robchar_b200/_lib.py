@@ -40,6 +40,7 @@ _SIGNATURES = {
     "rc_fidelity_mc_stats": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64, _vp, _f64,
                                        _vp, _vp, _vp, _vp, _vp]),
     "rc_stats_unsorted": (C.c_int, [_vp, _i64, _i64, _f64, _vp, _vp, _vp]),
+    "rc_spectral_fallbacks": (C.c_int, [_vp, _i32, _vp]),
     "rc_philox_normals": (C.c_int, [_i64, _i32, _i32, _i64, _i32, _u64, _i64, _i64, _vp, _vp]),
     "rc_stats_workspace_bytes": (_sz, [_i64, _i64]),
     "rc_stats": (C.c_int, [_vp, _i64, _i64, _f64, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -100,7 +100,7 @@ int fused_reg_threads(int n, bool replay, long long B) {
 // RC_SMEM_THREADS (environment) overrides for tuning.
 constexpr size_t SMEM_BYTES_MAX = 227 * 1024;
 constexpr size_t FUSED_STATIC_SMEM = (SMEM_FUSED_MAX_THREADS / 32) * PART_DOUBLES * sizeof(double);   // merge scratch
-static int smem_threads(int n, int cap = SMEM_MAX_THREADS, size_t static_bytes = 0) {
+static int smem_threads_bytes(size_t lane_bytes, int cap = SMEM_MAX_THREADS, size_t static_bytes = 0) {
     static int env = -1;
     if (env < 0) {
         const char* e = getenv("RC_SMEM_THREADS");
@@ -109,30 +109,78 @@ static int smem_threads(int n, int cap = SMEM_MAX_THREADS, size_t static_bytes =
     }
     int t = env;
     if (!t) {
-        const int lanes = (int)((SMEM_BYTES_MAX - static_bytes) / ((size_t)32 * n));
+        const int lanes = (int)((SMEM_BYTES_MAX - static_bytes) / lane_bytes);
         t = lanes >= 256 ? lanes / 128 * 128 : lanes / 32 * 32;
     }
+    if ((size_t)t * lane_bytes + static_bytes > SMEM_BYTES_MAX) t = (int)((SMEM_BYTES_MAX - static_bytes) / lane_bytes) / 32 * 32;
     return t > cap ? cap : t;
 }
 
-template <int MODEL, bool REPLAY, bool AMPS = false>
-static cudaError_t launch_smem(const FidArgs& a, int sm_count, cudaStream_t st) {
-    const int threads = smem_threads(a.N);
-    size_t smem = (size_t)4 * a.N * threads * sizeof(double);
-    auto kern = fidelity_smem_kernel<MODEL, REPLAY, AMPS>;
+// Algorithm of the shared-memory family: spectral weights (rc_spectral.cuh) from N = 11 on — measured on B200
+// (profiles/r02a): N=9 2.05e9 vs 2.14e9 evals/s in favour of the eigenvector rows, N=10 equal, N=12 +10 %,
+// N=16 +26 %, N=24 +50 %, N=32 +58 % in favour of the spectral weights (both fit 768 lanes below N = 11, so
+// the footprint does not matter there and the N^2 weight products cost what the shorter rotations save).
+// RC_SMEM_ALGO=vectors|spectral (environment) forces one for A/B measurements.
+constexpr int SPEC_MIN_N = 11;
+static int smem_algo(int n) {
+    static int v = -2;
+    if (v == -2) {
+        const char* s = getenv("RC_SMEM_ALGO");
+        v = !s ? -1 : ((s[0] == 'v' || s[0] == '0') ? ALGO_VECTORS : ALGO_SPECTRAL);
+    }
+    return v >= 0 ? v : (n >= SPEC_MIN_N ? ALGO_SPECTRAL : ALGO_VECTORS);
+}
+// bytes of shared memory per lane for a launch
+static size_t lane_bytes_for(int algo, int n, int in, int out) {
+    return algo == ALGO_SPECTRAL ? (size_t)spec_lane_doubles(n, in, out) * sizeof(double) : (size_t)32 * n;
+}
+
+// device counter of spectral evaluations that fell back to the eigenvector rows (one per device, never freed)
+unsigned long long* respec_counter_device() {
+    static unsigned long long* cached[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!cached[dev]) {
+        unsigned long long* p = nullptr;
+        if (cudaMalloc(&p, sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, sizeof(unsigned long long));
+        cached[dev] = p;
+    }
+    return cached[dev];
+}
+
+template <class Kern>
+static cudaError_t launch_persistent(Kern kern, int threads, size_t smem, long long need_blocks, int sm_count, cudaStream_t st,
+                                     const void* arg) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int occ = 0;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
     if (err != cudaSuccess) return err;
     if (occ < 1) occ = 1;
-    long long total = (long long)a.S * a.C * a.B;
-    long long nblk = (total + threads - 1) / threads;
     long long grid = (long long)sm_count * occ;
-    if (grid > nblk) grid = nblk;
+    if (grid > need_blocks) grid = need_blocks;
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, threads, smem, st>>>(a);
-    return cudaGetLastError();
+    void* args[1] = {const_cast<void*>(arg)};
+    return cudaLaunchKernel((const void*)kern, dim3((unsigned)grid), dim3(threads), args, smem, st);
+}
+
+template <int MODEL, bool REPLAY, bool AMPS = false>
+static cudaError_t launch_smem(const FidArgs& a0, int sm_count, cudaStream_t st) {
+    FidArgs a = a0;
+    const int algo = smem_algo(a.N);
+    const size_t lane = lane_bytes_for(algo, a.N, a.in, a.out);
+    const int threads = smem_threads_bytes(lane);
+    const size_t smem = lane * threads;
+    const long long total = (long long)a.S * a.C * a.B;
+    const long long nblk = (total + threads - 1) / threads;
+    if (algo == ALGO_SPECTRAL) {
+        a.respec = respec_counter_device();
+        if (threads <= SMEM_WIDE_THREADS)
+            return launch_persistent(fidelity_smem_kernel<MODEL, REPLAY, AMPS, ALGO_SPECTRAL, SMEM_WIDE_THREADS>, threads, smem, nblk, sm_count, st, &a);
+        return launch_persistent(fidelity_smem_kernel<MODEL, REPLAY, AMPS, ALGO_SPECTRAL>, threads, smem, nblk, sm_count, st, &a);
+    }
+    return launch_persistent(fidelity_smem_kernel<MODEL, REPLAY, AMPS, ALGO_VECTORS>, threads, smem, nblk, sm_count, st, &a);
 }
 
 // RC_REG_MAX_N=<n> (environment) moves the register/shared-memory crossover for tuning.
@@ -159,43 +207,41 @@ cudaError_t launch_fidelity(const FidArgs& a, cudaStream_t st) {
 }
 
 template <int MODEL>
-static cudaError_t launch_fused_smem_warp(const FusedArgs& g, int sm_count, cudaStream_t st) {
-    const int threads = smem_threads(g.f.N, SMEM_MAX_THREADS, (SMEM_MAX_THREADS / 32) * WACC_DOUBLES * sizeof(double));
-    size_t smem = (size_t)4 * g.f.N * threads * sizeof(double);
-    auto kern = fidelity_stats_smem_warp_kernel<MODEL>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    int occ = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
-    if (err != cudaSuccess) return err;
-    if (occ < 1) occ = 1;
+static cudaError_t launch_fused_smem_warp(const FusedArgs& g0, int sm_count, cudaStream_t st) {
+    FusedArgs g = g0;
+    const int algo = smem_algo(g.f.N);
+    const size_t lane = lane_bytes_for(algo, g.f.N, g.f.in, g.f.out);
+    const int threads = smem_threads_bytes(lane, SMEM_MAX_THREADS, (SMEM_MAX_THREADS / 32) * WACC_DOUBLES * sizeof(double));
+    const size_t smem = lane * threads;
     const long long wpc = threads / 32;
     const long long nitems = (long long)g.f.S * g.f.C * g.nchunks;
-    long long grid = (long long)sm_count * occ;
     const long long need = (nitems + wpc - 1) / wpc;
-    if (grid > need) grid = need;
-    if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, threads, smem, st>>>(g);
-    return cudaGetLastError();
+    if (algo == ALGO_SPECTRAL) {
+        g.f.respec = respec_counter_device();
+        if (threads <= SMEM_WIDE_THREADS)
+            return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL, SMEM_WIDE_THREADS>, threads, smem, need, sm_count, st, &g);
+        return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL>, threads, smem, need, sm_count, st, &g);
+    }
+    return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_VECTORS>, threads, smem, need, sm_count, st, &g);
+}
+
+static int fused_smem_cta_threads(int n, int in, int out) {
+    return smem_threads_bytes(lane_bytes_for(smem_algo(n), n, in, out), SMEM_FUSED_MAX_THREADS, FUSED_STATIC_SMEM);
 }
 
 template <int MODEL, bool REPLAY>
-static cudaError_t launch_fused_smem(const FusedArgs& g, int sm_count, cudaStream_t st) {
-    const int threads = smem_threads(g.f.N, SMEM_FUSED_MAX_THREADS, FUSED_STATIC_SMEM);
-    size_t smem = (size_t)4 * g.f.N * threads * sizeof(double);
-    auto kern = fidelity_stats_smem_kernel<MODEL, REPLAY>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    int occ = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
-    if (err != cudaSuccess) return err;
-    if (occ < 1) occ = 1;
-    long long nitems = (long long)g.f.S * g.f.C * g.nchunks;
-    long long grid = (long long)sm_count * occ;
-    if (grid > nitems) grid = nitems;
-    if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, threads, smem, st>>>(g);
-    return cudaGetLastError();
+static cudaError_t launch_fused_smem(const FusedArgs& g0, int sm_count, cudaStream_t st) {
+    FusedArgs g = g0;
+    const int algo = smem_algo(g.f.N);
+    const size_t lane = lane_bytes_for(algo, g.f.N, g.f.in, g.f.out);
+    const int threads = fused_smem_cta_threads(g.f.N, g.f.in, g.f.out);
+    const size_t smem = lane * threads;
+    const long long nitems = (long long)g.f.S * g.f.C * g.nchunks;
+    if (algo == ALGO_SPECTRAL) {
+        g.f.respec = respec_counter_device();
+        return launch_persistent(fidelity_stats_smem_kernel<MODEL, REPLAY, ALGO_SPECTRAL>, threads, smem, nitems, sm_count, st, &g);
+    }
+    return launch_persistent(fidelity_stats_smem_kernel<MODEL, REPLAY, ALGO_VECTORS>, threads, smem, nitems, sm_count, st, &g);
 }
 
 cudaError_t launch_fused(const FusedArgs& g, cudaStream_t st) {
@@ -238,14 +284,14 @@ static long long warp_chunk_for(long long B) {
     return B < chunk ? (B + 31) / 32 * 32 : chunk;
 }
 
-static void fused_chunking(int nspin, bool replay, long long nseg, long long B, long long* chunk, long long* nchunks) {
+static void fused_chunking(int nspin, int in, int out, bool replay, long long nseg, long long B, long long* chunk, long long* nchunks) {
     if (!replay) {
         *chunk = warp_chunk_for(B);
         *nchunks = (B + *chunk - 1) / *chunk;
         return;
     }
     const long long threads = nspin <= reg_crossover() ? fused_reg_threads(nspin, replay, B)
-                                                       : smem_threads(nspin, SMEM_FUSED_MAX_THREADS, FUSED_STATIC_SMEM);
+                                                       : fused_smem_cta_threads(nspin, in, out);
     fused_chunking_threads(threads, B, chunk, nchunks);
 }
 
@@ -311,7 +357,19 @@ __global__ void philox_normals_kernel(long long C, long long B, int S, int n, in
 
 using namespace rc;
 
-extern "C" int rc_version(void) { return 100; }
+extern "C" int rc_version(void) { return 200; }
+
+extern "C" int rc_spectral_fallbacks(unsigned long long* count_host, int reset, void* stream) {
+    unsigned long long* p = respec_counter_device();
+    if (!p) return set_error(RC_ERR_CUDA, "rc_spectral_fallbacks: no counter on this device");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (count_host) {
+        RC_CUDA_TRY(cudaMemcpyAsync(count_host, p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        RC_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    if (reset) RC_CUDA_TRY(cudaMemsetAsync(p, 0, sizeof(unsigned long long), st));
+    return RC_OK;
+}
 extern "C" const char* rc_last_error(void) { return last_error_buffer(); }
 
 extern "C" int rc_device_info(int* sm_count, int* cc_major, int* cc_minor) {
@@ -424,7 +482,7 @@ extern "C" int rc_fidelity_stats(const double* ctrl_dev, int64_t C, int nspin, i
     a.c_offset = c_offset; a.b_offset = b_offset;
     RC_CUDA_TRY(zig_tables_device(&a.zig));
     g.eps = dkw_eps;
-    fused_chunking(nspin, replay_dev != nullptr, nseg, B, &g.chunk, &g.nchunks);
+    fused_chunking(nspin, inspin, outspin, replay_dev != nullptr, nseg, B, &g.chunk, &g.nchunks);
     const size_t need = (size_t)nseg * g.nchunks * PART_DOUBLES * sizeof(double);
     if (!workspace_dev || workspace_bytes < need)
         return set_error(RC_ERR_WORKSPACE, "rc_fidelity_stats: workspace %zu < required %zu bytes", workspace_bytes, need);

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "rc_ql.cuh"
+#include "rc_spectral.cuh"
 #include "rc_philox.cuh"
 #include "rc_stats.cuh"
 
@@ -24,6 +25,7 @@ struct FidArgs {
     const double* replay;   // [S][C][B][K] standard normals in reference draw order, or nullptr (Philox)
     double* fids;           // [S][C][B]
     unsigned long long* nonconv;  // device counter of QL non-convergences (may be nullptr)
+    unsigned long long* respec;   // device counter of spectral-path evaluations recomputed with eigenvector rows (may be nullptr)
     long long C, B;
     int S, N, in, out, model, zz;
     uint32_t seed_lo, seed_hi;
@@ -161,6 +163,7 @@ __host__ __device__ constexpr int reg_cta_min_blocks(int n, bool replay) {
 }
 constexpr int MAX_CTA_WARPS = 32;
 constexpr int SMEM_MAX_THREADS = 768;         // launch bound of the shared-memory evolution kernel
+constexpr int SMEM_WIDE_THREADS = 512;        // ... of its long-chain instantiation (N >= 23: fewer lanes fit, 128 registers each)
 constexpr int SMEM_FUSED_MAX_THREADS = 512;   // ... and of its fused-statistics variant (more live registers)
 
 template <int N, int MODEL, bool REPLAY>
@@ -496,24 +499,181 @@ __device__ __forceinline__ double eval_smem(const FidArgs& a, long long s, long 
         dst[0] = re;
         dst[1] = im;
     }
-    return re * re + im * im;
+    return fma(re, re, im * im);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Spectral-weights evaluation (rc_spectral.cuh) for the shared-memory family: each lane owns TWO [N] columns
+// (d, e) plus, when in / out are not the chain ends, the original entries of the two outer blocks
+// (2 * nx doubles, nx = min(in,out) + N-1-max(in,out)).  Half the footprint of eval_smem => twice the lanes.
+// ---------------------------------------------------------------------------------------------
+constexpr int ALGO_VECTORS = 0;    // QL accumulating the in / out eigenvector rows (rc_ql.cuh)
+constexpr int ALGO_SPECTRAL = 1;   // eigenvalues only + characteristic-polynomial weights (rc_spectral.cuh)
+
+__host__ __device__ inline int spec_outer_sites(int n, int in, int out) {
+    const int lo = in < out ? in : out, hi = in < out ? out : in;
+    return lo + (n - 1 - hi);
+}
+__host__ __device__ inline int spec_lane_doubles(int n, int in, int out) { return 2 * n + 2 * spec_outer_sites(n, in, out); }
+
+// d / e of the gauge-transformed Hamiltonian of one evaluation into this lane's columns (same arithmetic, same
+// rounding order as build_tridiagonal / eval_smem).  Philox mode, complex model: three draws per site but two
+// columns — the imaginary coupling draw nn2_i is parked in the spare slot e[n-1] and folded into
+// e[i-1] = |1 + sigma nn_i + i sigma nn2_i| as soon as its Philox block is complete (a block holds at most one).
+template <int MODEL, bool REPLAY>
+__device__ __forceinline__ void build_spec(const FidArgs& a, long long s, long long c, long long b, const double* row,
+                                           double* d, double* e, int ld) {
+    const int n = a.N;
+    constexpr int P = draws_per_site(MODEL);
+    const double* x = a.ctrl + c * (n + 1);
+    const double sigma = __ldg(a.sigma + s);
+    if (REPLAY) {
+        for (int i = 0; i < n; ++i) {
+            d[(size_t)i * ld] = __ldg(row + P * i);
+            if (i >= 1) {
+                const double aa = __dadd_rn(1.0, __dmul_rn(sigma, __ldg(row + P * i + 1)));
+                if (MODEL == MODEL_COMPLEX3) {
+                    const double bb = __dmul_rn(sigma, __ldg(row + P * i + 2));
+                    e[(size_t)(i - 1) * ld] = rc_sqrt(fma(aa, aa, bb * bb));
+                } else {
+                    e[(size_t)(i - 1) * ld] = aa;
+                }
+            }
+        }
+    } else if (MODEL == MODEL_REAL2) {
+        normals_fill(noise_key(a, s, c, b), P * n - (P - 1), a.zig, [&](int jc) -> double& {
+            const int site = jc == 0 ? 0 : 1 + (jc - 1) / P, kind = jc == 0 ? 0 : (jc - 1) % P;
+            return *(kind == 0 ? d + (size_t)site * ld : e + (size_t)(site - 1) * ld);
+        });
+        for (int i = 1; i < n; ++i) e[(size_t)(i - 1) * ld] = __dadd_rn(1.0, __dmul_rn(sigma, e[(size_t)(i - 1) * ld]));
+    } else {
+        const NoiseKey key = noise_key(a, s, c, b);
+        const int nc = 3 * n - 2, np = (nc + 1) / 2;
+        double* spare = e + (size_t)(n - 1) * ld;
+        auto slot = [&](int jc) -> double* {
+            const int site = jc == 0 ? 0 : 1 + (jc - 1) / 3, kind = jc == 0 ? 0 : (jc - 1) % 3;
+            return kind == 0 ? d + (size_t)site * ld : (kind == 1 ? e + (size_t)(site - 1) * ld : spare);
+        };
+        uint32_t pend = 0;   // parked draw indices (jc + 1), 8 bits each — see normals_fill
+#pragma unroll 1
+        for (int p = 0; p < np; ++p) {
+            const Philox4 r = philox_block(key, (uint32_t)p);
+            const int j0 = 2 * p;
+            bool miss;
+            *slot(j0) = zig_try(r.x, r.y, a.zig.kw, &miss);
+            if (miss) pend = (pend << 8) | (uint32_t)(j0 + 1);
+            if (j0 + 1 < nc) {
+                *slot(j0 + 1) = zig_try(r.z, r.w, a.zig.kw, &miss);
+                if (miss) pend = (pend << 8) | (uint32_t)(j0 + 2);
+            }
+            // the block's imaginary coupling draw, if any (jc = 3 i, i >= 1): uniform over the warp
+            const int jk = (j0 % 3 == 0 && j0 > 0) ? j0 : ((j0 + 1) % 3 == 0 ? j0 + 1 : -1);
+            const bool fold = jk > 0 && jk < nc;
+            if (fold || (pend >> 16) || p == np - 1) {
+                while (pend) {
+                    const uint32_t jc = (pend & 0xFFu) - 1u;
+                    pend >>= 8;
+                    double* q = slot((int)jc);
+                    *q = zig_complete(key, jc, *q, a.zig);
+                }
+            }
+            if (fold) {
+                double* ec = e + (size_t)(jk / 3 - 1) * ld;
+                const double aa = __dadd_rn(1.0, __dmul_rn(sigma, *ec));
+                const double bb = __dmul_rn(sigma, *spare);
+                *ec = rc_sqrt(fma(aa, aa, bb * bb));
+            }
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        const double base = a.zz ? zz_diag(i, n) : 0.0;
+        d[(size_t)i * ld] = __dadd_rn(__dadd_rn(base, __dmul_rn(sigma, d[(size_t)i * ld])), __ldg(x + i));
+    }
+}
+
+// One evaluation per lane; ALL 32 lanes of the warp must call it converged (`valid` = this lane has work): the
+// rare evaluations whose spectral error estimate is rejected are recomputed inside the call with the
+// eigenvector-accumulating QL, two lanes' columns per matrix (own columns for d / e, the idle neighbour's for the
+// in / out rows), even lanes first, then odd lanes.
 template <int MODEL, bool REPLAY, bool AMPS = false>
-__global__ void __launch_bounds__(SMEM_MAX_THREADS) fidelity_smem_kernel(FidArgs a) {
+__device__ __forceinline__ double eval_spec(const FidArgs& a, bool valid, long long s, long long c, long long b,
+                                            const double* row /* global replay row */, double* sm) {
+    const int n = a.N, ld = blockDim.x;
+    const int lo = a.in < a.out ? a.in : a.out, hi = a.in < a.out ? a.out : a.in;
+    const int nx = lo + (n - 1 - hi);
+    double* d = sm + threadIdx.x;
+    double* e = d + (size_t)n * ld;
+    double* xd = e + (size_t)n * ld;
+    double* xe = xd + (size_t)nx * ld;
+    double re = NAN, im = NAN, T = 0.0;
+    bool ok = true;
+    if (valid) {
+        T = fabs(__ldg(a.ctrl + c * (n + 1) + n));
+        build_spec<MODEL, REPLAY>(a, s, c, b, row, d, e, ld);
+        SpecBlocks xb;
+        xb.xd = xd; xb.xe = xe; xb.na = lo; xb.nb = n - 1 - hi;
+        for (int j = 0; j < lo; ++j) { xd[(size_t)j * ld] = d[(size_t)j * ld]; xe[(size_t)j * ld] = e[(size_t)j * ld]; }
+        for (int j = 0; j < xb.nb; ++j) {
+            xd[(size_t)(lo + j) * ld] = d[(size_t)(hi + 1 + j) * ld];
+            xe[(size_t)(lo + j) * ld] = j + 1 < xb.nb ? e[(size_t)(hi + 1 + j) * ld] : 0.0;
+        }
+        double pb = 1.0;
+        for (int i = lo; i < hi; ++i) pb *= e[(size_t)i * ld];
+        ok = amplitude_spectral_strided(d, e, ld, n, T, pb, xb, re, im);
+    }
+    const unsigned redo = __ballot_sync(0xffffffffu, valid && !ok);
+    if (redo) {
+        const int lane = threadIdx.x & 31;
+#pragma unroll 1
+        for (int par = 0; par < 2; ++par) {
+            __syncwarp();
+            if (valid && !ok && (lane & 1) == par) {
+                build_spec<MODEL, REPLAY>(a, s, c, b, row, d, e, ld);
+                double* zi = sm + (threadIdx.x ^ 1);
+                double* zo = zi + (size_t)n * ld;
+                for (int i = 0; i < n; ++i) {
+                    zi[(size_t)i * ld] = (i == a.in) ? 1.0 : 0.0;
+                    zo[(size_t)i * ld] = (i == a.out) ? 1.0 : 0.0;
+                }
+                int fail = 0;
+                amplitude_strided(d, e, zi, zo, ld, n, T, &fail, re, im);
+                if (fail && a.nonconv) atomicAdd(a.nonconv, 1ull);
+                if (a.respec) atomicAdd(a.respec, 1ull);
+            }
+            __syncwarp();
+        }
+    }
+    if (AMPS && valid) {
+        double* dst = a.amps + 2 * ((s * a.C + c) * a.B + b);
+        dst[0] = re;
+        dst[1] = im;
+    }
+    return fma(re, re, im * im);
+}
+
+template <int MODEL, bool REPLAY, bool AMPS = false, int ALGO = ALGO_VECTORS, int MAXT = SMEM_MAX_THREADS>
+__global__ void __launch_bounds__(MAXT) fidelity_smem_kernel(FidArgs a) {
     extern __shared__ double sm[];
     const long long K = (long long)draws_per_site(MODEL) * a.N;
     const long long total = (long long)a.S * a.C * a.B;
-    for (long long ev = (long long)blockIdx.x * blockDim.x + threadIdx.x; ev < total;
-         ev += (long long)gridDim.x * blockDim.x) {
-        EvalIndex ix = decode_eval(ev, a.C, a.B);
-        a.fids[ev] = eval_smem<MODEL, REPLAY, AMPS>(a, ix.s, ix.c, ix.b, REPLAY ? a.replay + ev * K : nullptr, sm);
+    // CTA-uniform trip count: the spectral evaluator is a warp-collective call
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
+        const long long ev = base + threadIdx.x;
+        const bool valid = ev < total;
+        EvalIndex ix = decode_eval(valid ? ev : 0, a.C, a.B);
+        const double* row = REPLAY ? a.replay + (valid ? ev : 0) * K : nullptr;
+        if (ALGO == ALGO_SPECTRAL) {
+            const double f = eval_spec<MODEL, REPLAY, AMPS>(a, valid, ix.s, ix.c, ix.b, row, sm);
+            if (valid) a.fids[ev] = f;
+        } else if (valid) {
+            a.fids[ev] = eval_smem<MODEL, REPLAY, AMPS>(a, ix.s, ix.c, ix.b, row, sm);
+        }
     }
 }
 
 // Warp-autonomous fused variant of the shared-memory kernel (Philox mode): see fidelity_stats_reg_warp_kernel.
-template <int MODEL>
-__global__ void __launch_bounds__(SMEM_MAX_THREADS) fidelity_stats_smem_warp_kernel(FusedArgs g) {
+template <int MODEL, int ALGO = ALGO_VECTORS, int MAXT = SMEM_MAX_THREADS>
+__global__ void __launch_bounds__(MAXT) fidelity_stats_smem_warp_kernel(FusedArgs g) {
     extern __shared__ double sm[];
     __shared__ double wacc_all[(SMEM_MAX_THREADS / 32) * WACC_DOUBLES];
     double* wacc = wacc_all + (threadIdx.x >> 5) * WACC_DOUBLES;
@@ -530,7 +690,8 @@ __global__ void __launch_bounds__(SMEM_MAX_THREADS) fidelity_stats_smem_warp_ker
             const long long b = bt + lane;
             const bool valid = b < b1;
             double f = 0.0;
-            if (valid) f = eval_smem<MODEL, false>(a, s, c, b, nullptr, sm);
+            if (ALGO == ALGO_SPECTRAL) f = eval_spec<MODEL, false>(a, valid, s, c, b, nullptr, sm);
+            else if (valid) f = eval_smem<MODEL, false>(a, s, c, b, nullptr, sm);
             warp_acc_pass(wacc, bt == b0, valid, f, g.eps);
         }
         __syncwarp();
@@ -543,7 +704,7 @@ __global__ void __launch_bounds__(SMEM_MAX_THREADS) fidelity_stats_smem_warp_ker
     }
 }
 
-template <int MODEL, bool REPLAY>
+template <int MODEL, bool REPLAY, int ALGO = ALGO_VECTORS>
 __global__ void __launch_bounds__(SMEM_FUSED_MAX_THREADS) fidelity_stats_smem_kernel(FusedArgs g) {
     extern __shared__ double sm[];
     __shared__ double scratch[(SMEM_FUSED_MAX_THREADS / 32) * PART_DOUBLES];
@@ -559,9 +720,14 @@ __global__ void __launch_bounds__(SMEM_FUSED_MAX_THREADS) fidelity_stats_smem_ke
         Moments m;
         moments_init(m);
         double shift[3] = {0.0, 0.0, 0.0};
-        for (long long b = b0 + threadIdx.x; b < b1; b += blockDim.x) {
-            double f = eval_smem<MODEL, REPLAY>(a, s, c, b, REPLAY ? a.replay + (seg * a.B + b) * K : nullptr, sm);
-            moments_add(m, f, g.eps, shift, m.n == 0.0);
+        for (long long bt = b0; bt < b1; bt += blockDim.x) {   // CTA-uniform trips (warp-collective evaluator)
+            const long long b = bt + threadIdx.x;
+            const bool valid = b < b1;
+            const double* row = REPLAY ? a.replay + (seg * a.B + (valid ? b : b0)) * K : nullptr;
+            double f = 0.0;
+            if (ALGO == ALGO_SPECTRAL) f = eval_spec<MODEL, REPLAY>(a, valid, s, c, b, row, sm);
+            else if (valid) f = eval_smem<MODEL, REPLAY>(a, s, c, b, row, sm);
+            if (valid) moments_add(m, f, g.eps, shift, m.n == 0.0);
         }
         moments_finish_thread(m, shift);
         moments_block_merge(m, scratch);

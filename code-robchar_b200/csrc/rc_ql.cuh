@@ -89,16 +89,16 @@ struct QlSweep {
                 s = f * rinv;
                 c = g * rinv;
                 g = d[i + 1] - p;
-                r = (d[i] - g) * s + 2.0 * c * b;
+                r = fma(d[i] - g, s, (2.0 * c) * b);
                 p = s * r;
                 d[i + 1] = g + p;
                 g = c * r - b;
                 double t = zi[i + 1];
-                zi[i + 1] = s * zi[i] + c * t;
-                zi[i] = c * zi[i] - s * t;
+                zi[i + 1] = fma(s, zi[i], c * t);
+                zi[i] = fma(c, zi[i], -(s * t));
                 t = zo[i + 1];
-                zo[i + 1] = s * zo[i] + c * t;
-                zo[i] = c * zo[i] - s * t;
+                zo[i + 1] = fma(s, zo[i], c * t);
+                zo[i] = fma(c, zo[i], -(s * t));
             }
         }
         d[L] -= p;
@@ -195,7 +195,7 @@ RC_HD double fidelity_reg(double (&d)[N], double (&e)[N], int in, int out, doubl
     if (f) return NAN;
     double re, im;
     phase_sum<N>(d, zi, zo, T, re, im);
-    return re * re + im * im;
+    return fma(re, re, im * im);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -322,7 +322,7 @@ RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int ou
         re = fma(w, cs, re);
         im = fma(-w, sn, im);
     }
-    return re * re + im * im;
+    return fma(re, re, im * im);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -390,14 +390,14 @@ RC_HD void amplitude_strided(double* d, double* e, double* zi, double* zo, int l
             s = f * rinv;
             c = g * rinv;
             g = d_up - p;
-            r = (di - g) * s + 2.0 * c * b;
+            r = fma(di - g, s, (2.0 * c) * b);
             p = s * r;
             pd[ld] = g + p;
             g = c * r - b;
-            pzi[ld] = s * zii + c * zi_up;
-            zi_up = c * zii - s * zi_up;
-            pzo[ld] = s * zoi + c * zo_up;
-            zo_up = c * zoi - s * zo_up;
+            pzi[ld] = fma(s, zii, c * zi_up);
+            zi_up = fma(c, zii, -(s * zi_up));
+            pzo[ld] = fma(s, zoi, c * zo_up);
+            zo_up = fma(c, zoi, -(s * zo_up));
             d_up = di;
             ei = ein; di = din; zii = ziin; zoi = zoin;
             pe -= ld; pd -= ld; pzi -= ld; pzo -= ld;
@@ -428,7 +428,7 @@ RC_HD void amplitude_strided(double* d, double* e, double* zi, double* zo, int l
 RC_HD double fidelity_strided(double* d, double* e, double* zi, double* zo, int ld, int n, double T, int* fail) {
     double re, im;
     amplitude_strided(d, e, zi, zo, ld, n, T, fail, re, im);
-    return re * re + im * im;
+    return fma(re, re, im * im);
 }
 
 }  // namespace rc

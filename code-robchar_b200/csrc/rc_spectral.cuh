@@ -1,0 +1,237 @@
+// Transfer amplitude from eigenvalues alone ("spectral weights"), lane-private, strided storage.
+//
+// Same quantity as rc_ql.cuh — <out| exp(-i H T) |in> of the real symmetric tridiagonal H that replaces the
+// reference's dense `scipy.linalg.expm(-1j*T*H)[out, in]` (noise_model.py:105-109, qnewton.py:397-400) — but
+// without accumulating eigenvector rows.  For an unreduced symmetric tridiagonal matrix with diagonal d and
+// couplings b the residue of the resolvent gives, for a <= b,
+//
+//     V[a,k] V[b,k] = chi_{0..a-1}(lambda_k) * (b_a ... b_{b-1}) * chi_{b+1..N-1}(lambda_k) / chi'(lambda_k),
+//     chi'(lambda_k) = prod_{j != k} (lambda_k - lambda_j),
+//
+// chi_{p..q} = characteristic polynomial of the principal block on sites p..q (three-term recurrence, empty
+// block = 1).  So the evaluation is: implicit-shift QL for the EIGENVALUES only (21 instead of 29 FP64
+// instructions per rotation, and two [N] arrays per lane instead of four: twice the resident lanes per SM in
+// the shared-memory kernels), N(N-1) differences and products, and the phase sum.  For the end-to-end transfer
+// (in = 0, out = N-1: BASELINE configs 3-5) there are no minors at all.
+//
+// Accuracy.  The weights only see DIFFERENCES of computed eigenvalues; a pair at distance g carries a relative
+// error ~ eps*|H|/g, identical for both members of the pair, which multiplies that pair's contribution to the
+// amplitude.  An a-posteriori estimate (per eigenvalue: |w_k| (N-1) 4 eps |H| / min_j |lambda_k - lambda_j|,
+// plus 8 eps times the uncancelled magnitude of the minors) is accumulated next to the amplitude; when it
+// exceeds SPEC_EST_THR (or is not finite: exactly coincident computed eigenvalues), the caller recomputes that
+// evaluation with the eigenvector-accumulating QL of rc_ql.cuh.  Measured against that QL on 5e6 evaluations of
+// the reference's controllers (N = 4..7, sigma <= 0.1): max |delta fid| 2.5e-13, no fallback taken; mirror-
+// symmetric / double-well chains up to N = 32 (near-degenerate pairs with O(1) weights): <= 3e-14 where the
+// estimate accepts (tools/spectral_sim.cpp).
+#pragma once
+#include "rc_ql.cuh"
+
+namespace rc {
+
+constexpr double SPEC_EST_THR = 1e-11;   // accepted a-posteriori error estimate of the amplitude
+
+#define RC_AT(a, i) a[(size_t)(i) * ld]
+
+// Eigenvalues of the symmetric tridiagonal (d, e), in place in d (unordered); e is destroyed.  Same flat
+// deflate / sweep loop and the same `rmin` split test as amplitude_strided, minus the eigenvector rows.
+// Returns 1 when an eigenvalue needed more than QL_MAX_SWEEPS sweeps.
+RC_HD int ql_eigenvalues_strided(double* d, double* e, int ld, int n, int tolhi, double tiny) {
+    int rmin = 0, l = 0, it = 0;
+    while (l < n - 1 && it <= QL_MAX_SWEEPS) {
+        if (negligible_hi(RC_AT(e, l), tolhi)) { ++l; it = 0; }
+        if (l < n - 1 && !negligible_hi(RC_AT(e, l), tolhi)) {
+            int m = n - 1;
+            if (rmin < tolhi) {
+                m = l + 1;
+                while (m < n - 1 && !negligible_hi(RC_AT(e, m), tolhi)) ++m;
+            }
+            const bool split = m != n - 1;
+            ++it;
+            double g = wilkinson_g(RC_AT(d, l), RC_AT(d, l + 1), RC_AT(e, l), RC_AT(d, m));
+            double r, s = 1.0, c = 1.0, p = 0.0;
+            double d_up = RC_AT(d, m);
+            double* pe = e + (size_t)(m - 1) * ld;
+            double* pd = d + (size_t)(m - 1) * ld;
+            double ei = *pe, di = *pd;
+            rmin = 0x7fffffff;
+            for (int i = m - 1; i >= l; --i) {
+                const int back = i > l ? ld : 0;   // operands of rotation i-1, loaded while rotation i computes
+                const double ein = *(pe - back), din = *(pd - back);
+                const double f = s * ei, b = c * ei;
+                const double h = fma(f, f, fma(g, g, tiny));
+                const double rinv = rc_rsqrt(h);
+                r = h * rinv;
+                pe[ld] = r;
+                rmin = hi_word(r) < rmin ? hi_word(r) : rmin;
+                s = f * rinv;
+                c = g * rinv;
+                g = d_up - p;
+                r = fma(di - g, s, (2.0 * c) * b);
+                p = s * r;
+                pd[ld] = g + p;
+                g = c * r - b;
+                d_up = di;
+                ei = ein; di = din;
+                pe -= ld; pd -= ld;
+            }
+            RC_AT(d, l) = d_up - p;
+            RC_AT(e, l) = g;
+            RC_AT(e, m) = 0.0;
+            if (split) rmin = 0;
+        }
+    }
+    return l < n - 1;
+}
+
+// 1/x to full precision for finite non-zero x (seed 2^-22 + two Newton steps); x = 0 gives inf.
+RC_HD double rc_rcp_full(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(y, fma(-x, y, 1.0), y);
+    return fma(y, fma(-x, y, 1.0), y);
+#else
+    return 1.0 / x;
+#endif
+}
+// 1/x to ~20 bits (error-estimate arithmetic only)
+RC_HD double rc_rcp_seed(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+#else
+    return 1.0 / x;
+#endif
+}
+RC_HD double hi_as_double(int hi) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, 0);
+#else
+    long long b = (long long)(unsigned)hi << 32;
+    double x;
+    memcpy(&x, &b, 8);
+    return x;
+#endif
+}
+
+// Original entries of the principal blocks before `a = min(in,out)` and after `b = max(in,out)`, kept aside
+// before the QL destroys (d, e):  xd[0..na)   = d[0..a),      xe[j] couples xd[j], xd[j+1]   (j < na-1)
+//                                 xd[na..na+nb) = d[b+1..n),  xe[na+j] couples xd[na+j], xd[na+j+1]
+struct SpecBlocks { const double* xd; const double* xe; int na, nb; };
+
+// amp = sum_k w_k exp(-i lambda_k T) from the eigenvalues in d[0..n); pb = product of the couplings between
+// the two sites; anorm = max_i(|d_i| + |e_i|) of the original matrix.  *est receives the error estimate.
+RC_HD void spectral_phase_sum(const double* d, int ld, int n, double T, double pb, double anorm, const SpecBlocks& xb,
+                              double& re_out, double& im_out, double* est_out) {
+    double re = 0.0, im = 0.0, est = 0.0;
+    const double cgap = (double)(n - 1) * 4.0 * DBL_EPSILON * anorm;
+    const bool minors = (xb.na + xb.nb) > 0;
+    // four eigenvalues per pass over the spectrum: four independent product chains, one load per four pairs
+    for (int k0 = 0; k0 < n; k0 += 4) {
+        double lam[4], P[4];
+        int mh[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + q < n ? k0 + q : n - 1;
+            lam[q] = RC_AT(d, k);
+            P[q] = 1.0;
+            mh[q] = 0x7fffffff;
+        }
+        for (int j = 0; j < k0; ++j) {
+            const double lj = RC_AT(d, j);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double df = lam[q] - lj;
+                P[q] *= df;
+                const int h = hi_word(df) & 0x7fffffff;
+                mh[q] = h < mh[q] ? h : mh[q];
+            }
+        }
+        const int kend = k0 + 4 < n ? k0 + 4 : n;
+        for (int j = k0; j < kend; ++j) {   // the block itself: skip j == k
+            const double lj = RC_AT(d, j);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double df = lam[q] - lj;
+                const bool self = (k0 + q == j) || (k0 + q >= n);
+                P[q] *= self ? 1.0 : df;
+                const int h = self ? 0x7fffffff : (hi_word(df) & 0x7fffffff);
+                mh[q] = h < mh[q] ? h : mh[q];
+            }
+        }
+        for (int j = kend; j < n; ++j) {
+            const double lj = RC_AT(d, j);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double df = lam[q] - lj;
+                P[q] *= df;
+                const int h = hi_word(df) & 0x7fffffff;
+                mh[q] = h < mh[q] ? h : mh[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (k0 + q < n) {
+                double num = pb, mag = fabs(pb);
+                if (minors) {
+                    const double l0 = lam[q];
+                    if (xb.na > 0) {
+                        double p0 = 1.0, p1 = l0 - RC_AT(xb.xd, 0), a0 = 1.0, a1 = fabs(p1);
+                        for (int j = 1; j < xb.na; ++j) {
+                            const double x = l0 - RC_AT(xb.xd, j), b2 = RC_AT(xb.xe, j - 1) * RC_AT(xb.xe, j - 1);
+                            const double t = fma(x, p1, -b2 * p0), at = fma(fabs(x), a1, b2 * a0);
+                            p0 = p1; p1 = t; a0 = a1; a1 = at;
+                        }
+                        num *= p1; mag *= a1;
+                    }
+                    if (xb.nb > 0) {
+                        const int top = xb.na + xb.nb - 1;
+                        double p0 = 1.0, p1 = l0 - RC_AT(xb.xd, top), a0 = 1.0, a1 = fabs(p1);
+                        for (int j = top - 1; j >= xb.na; --j) {
+                            const double x = l0 - RC_AT(xb.xd, j), b2 = RC_AT(xb.xe, j) * RC_AT(xb.xe, j);
+                            const double t = fma(x, p1, -b2 * p0), at = fma(fabs(x), a1, b2 * a0);
+                            p0 = p1; p1 = t; a0 = a1; a1 = at;
+                        }
+                        num *= p1; mag *= a1;
+                    }
+                }
+                const double y = rc_rcp_full(P[q]);
+                double w = num * y;
+                w = fma(fma(-w, P[q], num), y, w);
+                est = fma(fabs(w) * cgap, rc_rcp_seed(hi_as_double(mh[q])), est);
+                if (minors) est = fma(8.0 * DBL_EPSILON * mag, fabs(y), est);
+                double sn, cs;
+                rc_sincos_tab(lam[q] * T, &sn, &cs);
+                re = fma(w, cs, re);
+                im = fma(-w, sn, im);
+            }
+        }
+    }
+    re_out = re; im_out = im; *est_out = est;
+}
+
+// Whole evaluation on strided storage.  On entry d[0..n), e[0..n-1) hold the matrix; xb the blocks outside
+// [a, b] (already copied aside by the caller), pb the coupling product.  Returns true when the result is
+// accepted; false = recompute with amplitude_strided (non-finite estimate, estimate above threshold, or
+// eigenvalue non-convergence).  NaN / Inf input: accepted with NaN output, like amplitude_strided.
+RC_HD bool amplitude_spectral_strided(double* d, double* e, int ld, int n, double T, double pb, const SpecBlocks& xb,
+                                      double& re_out, double& im_out) {
+    double anorm = 0.0, chk = T;
+    RC_AT(e, n - 1) = 0.0;
+    for (int k = 0; k < n; ++k) {
+        anorm = fmax(anorm, fabs(RC_AT(d, k)) + fabs(RC_AT(e, k)));
+        chk += RC_AT(d, k) + RC_AT(e, k);
+    }
+    re_out = NAN; im_out = NAN;
+    if (!(fabs(chk) <= DBL_MAX)) return true;
+    const double tol = DBL_EPSILON * anorm;
+    if (ql_eigenvalues_strided(d, e, ld, n, threshold_hi(tol), fmin(tol, 1e-280))) return false;
+    double est;
+    spectral_phase_sum(d, ld, n, T, pb, anorm, xb, re_out, im_out, &est);
+    return est <= SPEC_EST_THR;   // false for NaN / inf as well
+}
+
+#undef RC_AT
+
+}  // namespace rc

@@ -158,6 +158,15 @@ def stats_unsorted(fids: torch.Tensor, dkw_eps: float = 0.0, *, check_legal: boo
     return out
 
 
+def spectral_fallbacks(reset: bool = False) -> int:
+    """Evaluations of the N >= 11 kernels that were recomputed with accumulated eigenvector rows because the
+    spectral-weights error estimate rejected them (rc_spectral_fallbacks), since the last reset."""
+    require_cuda()
+    v = C.c_ulonglong(0)
+    check(lib().rc_spectral_fallbacks(C.byref(v), int(bool(reset)), _stream()))
+    return int(v.value)
+
+
 def philox_normals(C_: int, nspin: int, S: int, B: int, *, model: int = MODEL_COMPLEX3, seed: int = 0,
                    c_offset: int = 0, b_offset: int = 0) -> torch.Tensor:
     dev = require_cuda()

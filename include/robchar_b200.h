@@ -72,6 +72,13 @@ int rc_fidelity_mc_stats(const double* ctrl_dev, int64_t C, int nspin, int inspi
                          double* fids_dev, double* stats_dev, unsigned long long* nonconv_dev,
                          unsigned long long* illegal_dev, void* stream);
 
+/* Chain lengths above the register-resident range (N >= 11) evaluate <out|exp(-iHT)|in> from the eigenvalues
+ * alone (characteristic-polynomial weights, csrc/rc_spectral.cuh) and recompute an evaluation with accumulated
+ * eigenvector rows when its a-posteriori error estimate exceeds 1e-11 (near-coincident eigenvalues with large
+ * weights).  This diagnostic returns how many evaluations took that fallback on the current device since the
+ * last reset (synchronises `stream` when count_host != NULL). */
+int rc_spectral_fallbacks(unsigned long long* count_host, int reset, void* stream);
+
 /* The standard normals rc_fidelity_mc's Philox mode uses, written in replay layout [S][C][B][K]
  * (discarded site-0 coupling slots are zero).  Lets callers replay a GPU sweep through the
  * reference CPU path. */

@@ -151,6 +151,54 @@ def test_every_chain_length_vs_oracle(rb, n, model):
     assert np.abs(f - ref).max() < FID_TOL
 
 
+def _mirror_controllers(C, n, seed, scale=10.0):
+    rs = np.random.RandomState(seed)
+    x = rs.uniform(-0.5, 0.5, (C, n))
+    ctrl = np.empty((C, n + 1))
+    ctrl[:, :n] = (x + x[:, ::-1]) / 2 * scale          # mirror-symmetric biases: near-degenerate pairs
+    ctrl[:, n] = rs.uniform(1, 30, C)
+    return ctrl
+
+
+@pytest.mark.parametrize("n", [11, 12, 16, 24, 32])
+def test_spectral_weights_path_and_its_fallback(rb, n):
+    """N >= 11 evaluates from eigenvalues alone (csrc/rc_spectral.cuh).  Mirror-symmetric and double-well
+    chains have near-coincident eigenvalue pairs with O(1) weights: the error estimate must reject those
+    evaluations and the in-kernel recomputation with eigenvector rows must give the oracle's value; regular
+    sweeps must (almost) never take the fallback.  End-to-end and interior in/out, replay and Philox mode."""
+    C, B = 12, 33
+    ctrl = _mirror_controllers(C, n, seed=n)
+    dw = np.full(n, 6.0); dw[:2] = 0; dw[-2:] = 0       # double well
+    ctrl[0, :n] = dw
+    ctrl[1, :n] = 0.0                                    # uniform chain
+    ctrl[2, :n] = np.random.RandomState(n).uniform(-0.5, 0.5, n)   # small biases: delocalised, O(1) transfer
+    sig = np.array([0.0, 1e-9, 0.02])
+    rb.engine.spectral_fallbacks(reset=True)
+    for (i, o) in [(0, n - 1), (2, n - 3), (n - 2, 1), (0, n // 2), (3, 3)]:
+        nrm = np.random.RandomState(7 * n + i).standard_normal((3, C, B, 3 * n))
+        f = rb.engine.fidelity_mc(ctrl, sig, B, n, i, o, replay=nrm).cpu().numpy()
+        ref = orc.fidelity_mc_replay(ctrl, sig, nrm, n, i, o)
+        assert np.abs(f - ref).max() < FID_TOL, (n, i, o, np.abs(f - ref).max())
+        assert ref.max() > 1e-3                          # the set contains evaluations with real transfer
+    nfb = rb.engine.spectral_fallbacks(reset=True)
+    assert nfb > 0                                       # the degenerate rows did exercise the fallback
+    # Philox mode == replay of its own normals, bit for bit, through the fallback as well
+    kw = dict(seed=5, c_offset=2, b_offset=1)
+    z = rb.engine.philox_normals(C, n, 3, B, **kw)
+    fa = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, n - 1, **kw)
+    fb = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, n - 1, replay=z)
+    assert torch.equal(fa, fb)
+    # a regular sweep: random controllers, sigma up to 0.1 -> (almost) no fallback
+    rb.engine.spectral_fallbacks(reset=True)
+    reg = orc.synthetic_controllers(200, n, seed=1)
+    reg[:, :n] *= 0.1                                    # biases in [-1, 1]: delocalised eigenvectors, weights O(1/N)
+    fr = rb.engine.fidelity_mc(reg, np.linspace(0, 0.1, 3), 40, n, 0, n - 1, seed=3)
+    assert rb.engine.spectral_fallbacks() <= 24          # < 0.1 % of 24 000 evaluations
+    zr = rb.engine.philox_normals(200, n, 3, 40, seed=3)[:, :20]
+    refr = orc.fidelity_mc_replay(reg[:20], np.linspace(0, 0.1, 3), zr.cpu().numpy(), n, 0, n - 1)
+    assert np.abs(fr[:, :20].cpu().numpy() - refr).max() < FID_TOL
+
+
 def test_nan_controllers_and_empty(rb):
     n = 5
     ctrl = orc.synthetic_controllers(6, n)
