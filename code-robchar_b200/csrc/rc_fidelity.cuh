@@ -521,8 +521,8 @@ __host__ __device__ inline int spec_lane_doubles(int n, int in, int out) { retur
 // columns — the imaginary coupling draw nn2_i is parked in the spare slot e[n-1] and folded into
 // e[i-1] = |1 + sigma nn_i + i sigma nn2_i| as soon as its Philox block is complete (a block holds at most one).
 template <int MODEL, bool REPLAY>
-__device__ __forceinline__ void build_spec(const FidArgs& a, long long s, long long c, long long b, const double* row,
-                                           double* d, double* e, int ld) {
+__device__ __noinline__ void build_spec(const FidArgs& a, long long s, long long c, long long b, const double* row,
+                                        double* d, double* e, int ld) {
     const int n = a.N;
     constexpr int P = draws_per_site(MODEL);
     const double* x = a.ctrl + c * (n + 1);
@@ -591,10 +591,40 @@ __device__ __forceinline__ void build_spec(const FidArgs& a, long long s, long l
     }
 }
 
+// Cold path of eval_spec (kept out of line: the hot code of this kernel family has to fit the instruction cache).
+// Called by the whole warp; lanes with `mine` recompute their evaluation with the eigenvector-accumulating QL,
+// two lanes' columns per matrix (own columns for d / e, the idle neighbour's for the in / out rows), even lanes
+// first, then odd lanes.
+template <int MODEL, bool REPLAY>
+__device__ __noinline__ double2 spec_recompute(const FidArgs& a, bool mine, long long s, long long c, long long b,
+                                               const double* row, double* sm, double T) {
+    const int n = a.N, ld = blockDim.x, lane = threadIdx.x & 31;
+    double* d = sm + threadIdx.x;
+    double* e = d + (size_t)n * ld;
+    double re = NAN, im = NAN;
+#pragma unroll 1
+    for (int par = 0; par < 2; ++par) {
+        __syncwarp();
+        if (mine && (lane & 1) == par) {
+            build_spec<MODEL, REPLAY>(a, s, c, b, row, d, e, ld);
+            double* zi = sm + (threadIdx.x ^ 1);
+            double* zo = zi + (size_t)n * ld;
+            for (int i = 0; i < n; ++i) {
+                zi[(size_t)i * ld] = (i == a.in) ? 1.0 : 0.0;
+                zo[(size_t)i * ld] = (i == a.out) ? 1.0 : 0.0;
+            }
+            int fail = 0;
+            amplitude_strided(d, e, zi, zo, ld, n, T, &fail, re, im);
+            if (fail && a.nonconv) atomicAdd(a.nonconv, 1ull);
+            if (a.respec) atomicAdd(a.respec, 1ull);
+        }
+        __syncwarp();
+    }
+    return make_double2(re, im);
+}
+
 // One evaluation per lane; ALL 32 lanes of the warp must call it converged (`valid` = this lane has work): the
-// rare evaluations whose spectral error estimate is rejected are recomputed inside the call with the
-// eigenvector-accumulating QL, two lanes' columns per matrix (own columns for d / e, the idle neighbour's for the
-// in / out rows), even lanes first, then odd lanes.
+// rare evaluations whose spectral error estimate is rejected are recomputed inside the call (spec_recompute).
 template <int MODEL, bool REPLAY, bool AMPS = false>
 __device__ __forceinline__ double eval_spec(const FidArgs& a, bool valid, long long s, long long c, long long b,
                                             const double* row /* global replay row */, double* sm) {
@@ -623,25 +653,8 @@ __device__ __forceinline__ double eval_spec(const FidArgs& a, bool valid, long l
     }
     const unsigned redo = __ballot_sync(0xffffffffu, valid && !ok);
     if (redo) {
-        const int lane = threadIdx.x & 31;
-#pragma unroll 1
-        for (int par = 0; par < 2; ++par) {
-            __syncwarp();
-            if (valid && !ok && (lane & 1) == par) {
-                build_spec<MODEL, REPLAY>(a, s, c, b, row, d, e, ld);
-                double* zi = sm + (threadIdx.x ^ 1);
-                double* zo = zi + (size_t)n * ld;
-                for (int i = 0; i < n; ++i) {
-                    zi[(size_t)i * ld] = (i == a.in) ? 1.0 : 0.0;
-                    zo[(size_t)i * ld] = (i == a.out) ? 1.0 : 0.0;
-                }
-                int fail = 0;
-                amplitude_strided(d, e, zi, zo, ld, n, T, &fail, re, im);
-                if (fail && a.nonconv) atomicAdd(a.nonconv, 1ull);
-                if (a.respec) atomicAdd(a.respec, 1ull);
-            }
-            __syncwarp();
-        }
+        const double2 r = spec_recompute<MODEL, REPLAY>(a, valid && !ok, s, c, b, row, sm, T);
+        if (valid && !ok) { re = r.x; im = r.y; }
     }
     if (AMPS && valid) {
         double* dst = a.amps + 2 * ((s * a.C + c) * a.B + b);
@@ -652,7 +665,7 @@ __device__ __forceinline__ double eval_spec(const FidArgs& a, bool valid, long l
 }
 
 template <int MODEL, bool REPLAY, bool AMPS = false, int ALGO = ALGO_VECTORS, int MAXT = SMEM_MAX_THREADS>
-__global__ void __launch_bounds__(MAXT) fidelity_smem_kernel(FidArgs a) {
+__global__ void __launch_bounds__(MAXT, 1) fidelity_smem_kernel(FidArgs a) {
     extern __shared__ double sm[];
     const long long K = (long long)draws_per_site(MODEL) * a.N;
     const long long total = (long long)a.S * a.C * a.B;
@@ -673,7 +686,7 @@ __global__ void __launch_bounds__(MAXT) fidelity_smem_kernel(FidArgs a) {
 
 // Warp-autonomous fused variant of the shared-memory kernel (Philox mode): see fidelity_stats_reg_warp_kernel.
 template <int MODEL, int ALGO = ALGO_VECTORS, int MAXT = SMEM_MAX_THREADS>
-__global__ void __launch_bounds__(MAXT) fidelity_stats_smem_warp_kernel(FusedArgs g) {
+__global__ void __launch_bounds__(MAXT, 1) fidelity_stats_smem_warp_kernel(FusedArgs g) {
     extern __shared__ double sm[];
     __shared__ double wacc_all[(SMEM_MAX_THREADS / 32) * WACC_DOUBLES];
     double* wacc = wacc_all + (threadIdx.x >> 5) * WACC_DOUBLES;

@@ -127,7 +127,9 @@ RC_HD void spectral_phase_sum(const double* d, int ld, int n, double T, double p
     double re = 0.0, im = 0.0, est = 0.0;
     const double cgap = (double)(n - 1) * 4.0 * DBL_EPSILON * anorm;
     const bool minors = (xb.na + xb.nb) > 0;
-    // four eigenvalues per pass over the spectrum: four independent product chains, one load per four pairs
+    // four eigenvalues per pass over the spectrum: four independent product chains, one load per four pairs.
+    // Code size matters (the kernel shares the instruction cache between warps that are in different phases):
+    // the pair loops and the per-eigenvalue epilogue are deliberately NOT unrolled.
     for (int k0 = 0; k0 < n; k0 += 4) {
         double lam[4], P[4];
         int mh[4];
@@ -138,74 +140,79 @@ RC_HD void spectral_phase_sum(const double* d, int ld, int n, double T, double p
             P[q] = 1.0;
             mh[q] = 0x7fffffff;
         }
-        for (int j = 0; j < k0; ++j) {
-            const double lj = RC_AT(d, j);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const double df = lam[q] - lj;
-                P[q] *= df;
-                const int h = hi_word(df) & 0x7fffffff;
-                mh[q] = h < mh[q] ? h : mh[q];
-            }
-        }
         const int kend = k0 + 4 < n ? k0 + 4 : n;
-        for (int j = k0; j < kend; ++j) {   // the block itself: skip j == k
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < n; ++j) {
             const double lj = RC_AT(d, j);
+            const bool inblock = j >= k0 && j < kend;      // warp uniform
+            if (!inblock) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const double df = lam[q] - lj;
-                const bool self = (k0 + q == j) || (k0 + q >= n);
-                P[q] *= self ? 1.0 : df;
-                const int h = self ? 0x7fffffff : (hi_word(df) & 0x7fffffff);
-                mh[q] = h < mh[q] ? h : mh[q];
-            }
-        }
-        for (int j = kend; j < n; ++j) {
-            const double lj = RC_AT(d, j);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const double df = lam[q] - lj;
-                P[q] *= df;
-                const int h = hi_word(df) & 0x7fffffff;
-                mh[q] = h < mh[q] ? h : mh[q];
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (k0 + q < n) {
-                double num = pb, mag = fabs(pb);
-                if (minors) {
-                    const double l0 = lam[q];
-                    if (xb.na > 0) {
-                        double p0 = 1.0, p1 = l0 - RC_AT(xb.xd, 0), a0 = 1.0, a1 = fabs(p1);
-                        for (int j = 1; j < xb.na; ++j) {
-                            const double x = l0 - RC_AT(xb.xd, j), b2 = RC_AT(xb.xe, j - 1) * RC_AT(xb.xe, j - 1);
-                            const double t = fma(x, p1, -b2 * p0), at = fma(fabs(x), a1, b2 * a0);
-                            p0 = p1; p1 = t; a0 = a1; a1 = at;
-                        }
-                        num *= p1; mag *= a1;
-                    }
-                    if (xb.nb > 0) {
-                        const int top = xb.na + xb.nb - 1;
-                        double p0 = 1.0, p1 = l0 - RC_AT(xb.xd, top), a0 = 1.0, a1 = fabs(p1);
-                        for (int j = top - 1; j >= xb.na; --j) {
-                            const double x = l0 - RC_AT(xb.xd, j), b2 = RC_AT(xb.xe, j) * RC_AT(xb.xe, j);
-                            const double t = fma(x, p1, -b2 * p0), at = fma(fabs(x), a1, b2 * a0);
-                            p0 = p1; p1 = t; a0 = a1; a1 = at;
-                        }
-                        num *= p1; mag *= a1;
-                    }
+                for (int q = 0; q < 4; ++q) {
+                    const double df = lam[q] - lj;
+                    P[q] *= df;
+                    const int h = hi_word(df) & 0x7fffffff;
+                    mh[q] = h < mh[q] ? h : mh[q];
                 }
-                const double y = rc_rcp_full(P[q]);
-                double w = num * y;
-                w = fma(fma(-w, P[q], num), y, w);
-                est = fma(fabs(w) * cgap, rc_rcp_seed(hi_as_double(mh[q])), est);
-                if (minors) est = fma(8.0 * DBL_EPSILON * mag, fabs(y), est);
-                double sn, cs;
-                rc_sincos_tab(lam[q] * T, &sn, &cs);
-                re = fma(w, cs, re);
-                im = fma(-w, sn, im);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {               // the block itself: skip j == k (and the clamped duplicates)
+                    const double df = lam[q] - lj;
+                    const bool self = (k0 + q == j) || (k0 + q >= n);
+                    P[q] *= self ? 1.0 : df;
+                    const int h = self ? 0x7fffffff : (hi_word(df) & 0x7fffffff);
+                    mh[q] = h < mh[q] ? h : mh[q];
+                }
             }
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int q = 0; q < kend - k0; ++q) {
+            // q is a run-time index: select from the named registers instead of indexing the arrays
+            double l0 = lam[0], Pq = P[0];
+            int mq = mh[0];
+            if (q == 1) { l0 = lam[1]; Pq = P[1]; mq = mh[1]; }
+            if (q == 2) { l0 = lam[2]; Pq = P[2]; mq = mh[2]; }
+            if (q == 3) { l0 = lam[3]; Pq = P[3]; mq = mh[3]; }
+            double num = pb, mag = fabs(pb);
+            if (minors) {
+                if (xb.na > 0) {
+                    double p0 = 1.0, p1 = l0 - RC_AT(xb.xd, 0), a0 = 1.0, a1 = fabs(p1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                    for (int j = 1; j < xb.na; ++j) {
+                        const double x = l0 - RC_AT(xb.xd, j), b2 = RC_AT(xb.xe, j - 1) * RC_AT(xb.xe, j - 1);
+                        const double t = fma(x, p1, -(b2 * p0)), at = fma(fabs(x), a1, b2 * a0);
+                        p0 = p1; p1 = t; a0 = a1; a1 = at;
+                    }
+                    num *= p1; mag *= a1;
+                }
+                if (xb.nb > 0) {
+                    const int top = xb.na + xb.nb - 1;
+                    double p0 = 1.0, p1 = l0 - RC_AT(xb.xd, top), a0 = 1.0, a1 = fabs(p1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                    for (int j = top - 1; j >= xb.na; --j) {
+                        const double x = l0 - RC_AT(xb.xd, j), b2 = RC_AT(xb.xe, j) * RC_AT(xb.xe, j);
+                        const double t = fma(x, p1, -(b2 * p0)), at = fma(fabs(x), a1, b2 * a0);
+                        p0 = p1; p1 = t; a0 = a1; a1 = at;
+                    }
+                    num *= p1; mag *= a1;
+                }
+            }
+            const double y = rc_rcp_full(Pq);
+            double w = num * y;
+            w = fma(fma(-w, Pq, num), y, w);
+            est = fma(fabs(w) * cgap, rc_rcp_seed(hi_as_double(mq)), est);
+            if (minors) est = fma(8.0 * DBL_EPSILON * mag, fabs(y), est);
+            double sn, cs;
+            rc_sincos_tab(l0 * T, &sn, &cs);
+            re = fma(w, cs, re);
+            im = fma(-w, sn, im);
         }
     }
     re_out = re; im_out = im; *est_out = est;
