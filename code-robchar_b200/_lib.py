@@ -40,6 +40,7 @@ _SIGNATURES = {
     "rc_fidelity_mc_stats": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64, _vp, _f64,
                                        _vp, _vp, _vp, _vp, _vp]),
     "rc_stats_unsorted": (C.c_int, [_vp, _i64, _i64, _f64, _vp, _vp, _vp]),
+    "rc_evolution_kernel_name": (C.c_int, [_i32, _i32, _i32, C.c_char_p, _sz]),
     "rc_spectral_fallbacks": (C.c_int, [_vp, _i32, _vp]),
     "rc_philox_normals": (C.c_int, [_i64, _i32, _i32, _i64, _i32, _u64, _i64, _i64, _vp, _vp]),
     "rc_stats_workspace_bytes": (_sz, [_i64, _i64]),
@@ -47,6 +48,18 @@ _SIGNATURES = {
     "rc_fidelity_stats_workspace_bytes": (_sz, [_i64, _i64]),
     "rc_fidelity_stats": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64, _vp, _f64,
                                     _vp, _vp, _vp, _sz, _vp]),
+    "rc_draw_shard_range": (C.c_int, [_i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "rc_fidelity_stats_blocks_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "rc_fidelity_stats_blocks": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64, _i32, _i32,
+                                           _f64, _vp, _vp, _vp, _sz, _vp]),
+    "rc_stats_from_blocks": (C.c_int, [_vp, _i64, _i64, _f64, _vp, _vp]),
+    "rc_peer_alloc": (C.c_int, [_sz, _vp, _vp]),
+    "rc_peer_open": (C.c_int, [_vp, _vp]),
+    "rc_peer_close": (C.c_int, [_vp]),
+    "rc_peer_free": (C.c_int, [_vp]),
+    "rc_peer_push_columns": (C.c_int, [_vp, _i32, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "rc_peer_signal": (C.c_int, [_vp, _i32, _i32, _u64, _vp]),
+    "rc_peer_wait": (C.c_int, [_vp, _i32, _u64, _f64, _vp, _vp]),
     "rc_ranks_workspace_bytes": (_sz, [_i64, _i64]),
     "rc_ranks": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "rc_clustered_ranks": (C.c_int, [_vp, _i64, _i64, _f64, _f64, _vp, _vp, _sz, _vp]),
@@ -56,6 +69,8 @@ _SIGNATURES = {
     "rc_rank_consistency": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _f64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rc_robustness_sweep_host": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64,
                                            _f64, _i32, _i64, _i64, _f64, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "rc_robustness_sweep_host_keep": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64,
+                                                _f64, _i32, _i64, _i64, _f64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "rc_robustness_sweep_workspace_bytes": (_sz, [_i64, _i32, _i64, _i32, _i64, _i64]),
     "rc_robustness_sweep": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64, _f64, _i32,
                                       _i64, _i64, _f64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),

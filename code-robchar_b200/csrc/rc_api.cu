@@ -17,8 +17,8 @@ struct DevBuf {
     template <class T> T* as() { return (T*)p; }
 };
 
-// Stream-ordered scratch comes from the device's default memory pool; keep freed blocks cached in
-// the pool (default behaviour returns them to the OS at every synchronisation, which makes each
+// Stream-ordered scratch comes from the device's default memory pool; keep up to 2 GiB of freed blocks cached
+// in the pool (default behaviour returns them to the OS at every synchronisation, which makes each
 // sweep pay cudaMalloc/cudaFree of the fidelity tensor again).
 static cudaError_t keep_pool_memory() {
     static bool done[64] = {false};
@@ -29,7 +29,10 @@ static cudaError_t keep_pool_memory() {
     cudaMemPool_t pool;
     e = cudaDeviceGetDefaultMemPool(&pool, dev);
     if (e != cudaSuccess) return e;
-    unsigned long long thr = ~0ull;
+    // bounded: the pool keeps at most this much freed memory cached (the scratch of a paper-size sweep is a few
+    // hundred MB); anything above goes back to the driver at the next synchronisation, so other users of the
+    // default pool (PyTorch's allocator in the same process) are not starved after one large sweep
+    unsigned long long thr = 2ull << 30;
     e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     if (e == cudaSuccess) done[dev] = true;
     return e;
@@ -172,7 +175,7 @@ static int sweep_host_impl(const double* ctrl_host, int64_t C, int nspin, int in
                            int64_t c_offset, int64_t b_offset, const double* replay_host, double dkw_eps,
                            int fused, double* fids_host, double* stats_host, int64_t G, int64_t topk,
                            double alpha_cluster, double* tau_host, int64_t* sel_host, int nboot, double* arim_host,
-                           double* arim_std_host, void* stream) {
+                           double* arim_std_host, void* stream, double* stats_dev_keep = nullptr) {
     if (nspin < 2 || nspin > RC_MAX_NSPIN) return set_error(RC_ERR_BAD_ARG, "nspin=%d outside [2,%d]", nspin, RC_MAX_NSPIN);
     if (C < 0 || S < 0 || B < 1) return set_error(RC_ERR_BAD_ARG, "sweep: bad sizes C=%lld S=%d B=%lld", (long long)C, S, (long long)B);
     const long long nseg = (long long)S * C, total = nseg * B;
@@ -198,11 +201,23 @@ static int sweep_host_impl(const double* ctrl_host, int64_t C, int nspin, int in
     }
     unsigned long long* nonconv = counters.as<unsigned long long>();
     unsigned long long* illegal = nonconv + 1;
-    if (stats_host || want_rank) RC_CUDA_TRY(stats.alloc((size_t)RC_NUM_STATS * nseg * 8));
+    // stats_dev_keep: caller-owned device tensor [15][S][C] that receives the statistics and stays valid after the
+    // call (the multi-GPU sweep pushes it to its peers while the next call runs)
+    if (stats_dev_keep) stats.p = stats_dev_keep;
+    else if (stats_host || want_rank) RC_CUDA_TRY(stats.alloc((size_t)RC_NUM_STATS * nseg * 8));
+    struct Unown { DevBuf& b; bool on; ~Unown() { if (on) b.p = nullptr; } } unown{stats, stats_dev_keep != nullptr};
     int rcode;
     SweepAsync* async = nullptr;
     cudaStream_t copy = nullptr;
     bool stats_copied = false;
+    // every exit path (error returns included): the stream-ordered frees of the scratch buffers above are issued on
+    // st by the DevBuf destructors, so st must first wait for the copy stream that may still be reading them
+    struct CopyJoin {
+        cudaStream_t st; cudaStream_t* copy; SweepAsync** async;
+        ~CopyJoin() {
+            if (*copy && *async && cudaEventRecord((*async)->done, *copy) == cudaSuccess) cudaStreamWaitEvent(st, (*async)->done, 0);
+        }
+    } copy_join{st, &copy, &async};
     if (fused) {
         size_t wb = rc_fidelity_stats_workspace_bytes(nseg, B);
         RC_CUDA_TRY(ws.alloc(wb));
@@ -311,6 +326,19 @@ extern "C" int rc_robustness_sweep_host(const double* ctrl_host, int64_t C, int 
     return sweep_host_impl(ctrl_host, C, nspin, inspin, outspin, sigma_host, S, B, model, zz, seed, c_offset, b_offset,
                            nullptr, dkw_eps, fused, nullptr, stats_host, G, topk, alpha_cluster, tau_host, sel_host, nboot,
                            arim_host, arim_std_host, stream);
+}
+
+extern "C" int rc_robustness_sweep_host_keep(const double* ctrl_host, int64_t C, int nspin, int inspin, int outspin,
+                                             const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
+                                             int64_t c_offset, int64_t b_offset, double dkw_eps, int fused, int64_t G,
+                                             int64_t topk, double alpha_cluster, double* stats_host, double* tau_host,
+                                             int64_t* sel_host, int nboot, double* arim_host, double* arim_std_host,
+                                             double* stats_dev_keep, void* stream) {
+    if (!tau_host) return set_error(RC_ERR_NULL, "rc_robustness_sweep_host_keep: null tau output");
+    if (!stats_dev_keep) return set_error(RC_ERR_NULL, "rc_robustness_sweep_host_keep: null device statistics tensor");
+    return sweep_host_impl(ctrl_host, C, nspin, inspin, outspin, sigma_host, S, B, model, zz, seed, c_offset, b_offset,
+                           nullptr, dkw_eps, fused, nullptr, stats_host, G, topk, alpha_cluster, tau_host, sel_host, nboot,
+                           arim_host, arim_std_host, stream, stats_dev_keep);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -274,14 +274,18 @@ static void fused_chunking_threads(long long threads, long long B, long long* ch
 // round-robin distribution small already for modest sweeps (>= 30 items per warp from 3e7 evaluations on) at
 // 0.53 B of partials per draw.
 constexpr long long WARP_CHUNK = 256;
+constexpr long long WARP_MAX_CHUNKS = 512;   // per segment: bounds the partials workspace (136 B each) for B >= 1.3e5
 static long long warp_chunk_for(long long B) {
-    static long long chunk = 0;   // RC_WARP_CHUNK (environment, multiple of 32) overrides for tuning
-    if (!chunk) {
+    static long long base = 0;   // RC_WARP_CHUNK (environment, multiple of 32) overrides for tuning
+    if (!base) {
         const char* e = getenv("RC_WARP_CHUNK");
         const long long v = e ? atoll(e) : 0;
-        chunk = (v >= 32 && v % 32 == 0) ? v : WARP_CHUNK;
+        base = (v >= 32 && v % 32 == 0) ? v : WARP_CHUNK;
     }
-    return B < chunk ? (B + 31) / 32 * 32 : chunk;
+    if (B < base) return (B + 31) / 32 * 32;
+    long long chunk = base;      // long segments: double the item until a segment has at most WARP_MAX_CHUNKS of them
+    while ((B + chunk - 1) / chunk > WARP_MAX_CHUNKS) chunk *= 2;
+    return chunk;
 }
 
 static void fused_chunking(int nspin, int in, int out, bool replay, long long nseg, long long B, long long* chunk, long long* nchunks) {
@@ -295,9 +299,47 @@ static void fused_chunking(int nspin, int in, int out, bool replay, long long ns
     fused_chunking_threads(threads, B, chunk, nchunks);
 }
 
-// One WARP per segment merges its chunk partials (lane L takes chunks L, L+32, ... in order, then a fixed
-// shuffle tree: deterministic) and lane 0 emits the 15 statistics.  The warp-autonomous fused kernels write up
-// to B/128 partials per segment, so a single thread per segment would serialise hundreds of dependent L2 reads.
+// Merging the chunk partials of a segment.  The order of the floating-point merges is FIXED and independent of
+// how the draw axis is sharded over GPUs: the chunks of a segment are cut into MERGE_BLOCKS contiguous blocks
+// (block v = chunks [v*nchunks/8, (v+1)*nchunks/8)); inside a block one warp merges lane-strided, then a fixed
+// shuffle tree; the eight block results are merged sequentially.  A rank of a draw-sharded sweep owns whole
+// blocks, so merging its blocks locally, all-gathering the [8][nseg] block results and finishing with
+// blocks_finalize_kernel gives the single-GPU statistics bit for bit.
+constexpr int MERGE_BLOCKS = 8;
+
+// block v of a segment whose local partials start at global chunk index chunk0; result valid in lane 0
+__device__ __forceinline__ Moments merge_block_warp(const double* __restrict__ seg_partials, long long nchunks_total,
+                                                    long long chunk0, long long nchunks_local, int v) {
+    const int lane = threadIdx.x & 31;
+    long long lo = (long long)v * nchunks_total / MERGE_BLOCKS - chunk0;
+    long long hi = (long long)(v + 1) * nchunks_total / MERGE_BLOCKS - chunk0;
+    if (lo < 0) lo = 0;
+    if (hi > nchunks_local) hi = nchunks_local;
+    Moments m;
+    moments_init(m);
+    for (long long ch = lo + lane; ch < hi; ch += 32) {
+        Moments o;
+        moments_load(o, seg_partials + ch * PART_DOUBLES);
+        moments_merge(m, o);
+    }
+    moments_warp_merge(m);
+    return m;
+}
+
+__device__ __forceinline__ void emit_statistics(const Moments& m, long long B, double eps, double* __restrict__ stats,
+                                                long long nseg, long long seg) {
+    const double mn[3] = {m.mn, clip01(m.mn - eps), clip01(m.mn + eps)};
+    for (int k = 0; k < 3; ++k) {
+        stats[(ST_W + k) * nseg + seg] = m.s1[k] / (double)B;       // mean(1 - f) == sorted W1 formula
+        stats[(ST_Q95 + k) * nseg + seg] = -1.0 * (m.c95[k] / (double)B);
+        stats[(ST_Q98 + k) * nseg + seg] = -1.0 * (m.c98[k] / (double)B);
+        stats[(ST_STD + k) * nseg + seg] = sqrt(m.m2[k] / (double)B);
+        stats[(ST_WC + k) * nseg + seg] = -mn[k];
+    }
+}
+
+// Whole segment on one GPU: one WARP per segment (the warp-autonomous fused kernels write up to B/256 partials per
+// segment, so a single thread per segment would serialise hundreds of dependent L2 reads).
 __global__ void __launch_bounds__(256) fused_finalize_kernel(const double* __restrict__ partials, long long nseg,
                                                              long long nchunks, long long B, double eps,
                                                              double* __restrict__ stats) {
@@ -305,24 +347,45 @@ __global__ void __launch_bounds__(256) fused_finalize_kernel(const double* __res
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long seg = warp0; seg < nseg; seg += nwarps) {
-        Moments m;
-        moments_init(m);
-        for (long long ch = lane; ch < nchunks; ch += 32) {
-            Moments o;
-            moments_load(o, partials + (seg * nchunks + ch) * PART_DOUBLES);
-            moments_merge(m, o);
+        Moments total;
+        moments_init(total);
+        for (int v = 0; v < MERGE_BLOCKS; ++v) {
+            const Moments mb = merge_block_warp(partials + seg * nchunks * PART_DOUBLES, nchunks, 0, nchunks, v);
+            if (lane == 0) moments_merge(total, mb);
         }
-        moments_warp_merge(m);
-        if (lane == 0) {
-            const double mn[3] = {m.mn, clip01(m.mn - eps), clip01(m.mn + eps)};
-            for (int k = 0; k < 3; ++k) {
-                stats[(ST_W + k) * nseg + seg] = m.s1[k] / (double)B;       // mean(1 - f) == sorted W1 formula
-                stats[(ST_Q95 + k) * nseg + seg] = -1.0 * (m.c95[k] / (double)B);
-                stats[(ST_Q98 + k) * nseg + seg] = -1.0 * (m.c98[k] / (double)B);
-                stats[(ST_STD + k) * nseg + seg] = sqrt(m.m2[k] / (double)B);
-                stats[(ST_WC + k) * nseg + seg] = -mn[k];
-            }
+        if (lane == 0) emit_statistics(total, B, eps, stats, nseg, seg);
+    }
+}
+
+// Draw-sharded sweep, local part: the blocks [v_lo, v_hi) of every segment -> blocks_out [v_hi - v_lo][nseg][17].
+__global__ void __launch_bounds__(256) block_merge_kernel(const double* __restrict__ partials, long long nseg,
+                                                          long long nchunks_local, long long chunk0, long long nchunks_total,
+                                                          int v_lo, int v_hi, double* __restrict__ blocks_out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long seg = warp0; seg < nseg; seg += nwarps) {
+        for (int v = v_lo; v < v_hi; ++v) {
+            const Moments mb = merge_block_warp(partials + seg * nchunks_local * PART_DOUBLES, nchunks_total, chunk0,
+                                                nchunks_local, v);
+            if (lane == 0) moments_store(mb, blocks_out + ((long long)(v - v_lo) * nseg + seg) * PART_DOUBLES);
         }
+    }
+}
+
+// ... and the finish on the gathered block results [8][nseg][17]: one thread per segment, same sequence of merges as
+// lane 0 of fused_finalize_kernel.
+__global__ void __launch_bounds__(256) blocks_finalize_kernel(const double* __restrict__ blocks, long long nseg, long long B,
+                                                              double eps, double* __restrict__ stats) {
+    for (long long seg = (long long)blockIdx.x * blockDim.x + threadIdx.x; seg < nseg; seg += (long long)gridDim.x * blockDim.x) {
+        Moments total;
+        moments_init(total);
+        for (int v = 0; v < MERGE_BLOCKS; ++v) {
+            Moments mb;
+            moments_load(mb, blocks + ((long long)v * nseg + seg) * PART_DOUBLES);
+            moments_merge(total, mb);
+        }
+        emit_statistics(total, B, eps, stats, nseg, seg);
     }
 }
 
@@ -358,6 +421,19 @@ __global__ void philox_normals_kernel(long long C, long long B, int S, int n, in
 using namespace rc;
 
 extern "C" int rc_version(void) { return 200; }
+
+// Name of the evolution kernel the launcher picks for a sweep of this shape (bench.py labels its roofline with it).
+extern "C" int rc_evolution_kernel_name(int nspin, int replay, int fused, char* buf, size_t buf_bytes) {
+    if (!buf || buf_bytes < 8) return set_error(RC_ERR_NULL, "rc_evolution_kernel_name: no buffer");
+    if (nspin < 2 || nspin > MAX_N) return set_error(RC_ERR_BAD_ARG, "nspin=%d outside [2,%d]", nspin, MAX_N);
+    const bool reg = nspin <= reg_crossover();
+    const char* algo = smem_algo(nspin) == ALGO_SPECTRAL ? "spectral" : "vectors";
+    if (reg)
+        snprintf(buf, buf_bytes, "%s<%d>", fused ? (replay ? "fidelity_stats_reg_kernel" : "fidelity_stats_reg_warp_kernel") : "fidelity_reg_kernel", nspin);
+    else
+        snprintf(buf, buf_bytes, "%s<%s>", fused ? (replay ? "fidelity_stats_smem_kernel" : "fidelity_stats_smem_warp_kernel") : "fidelity_smem_kernel", algo);
+    return RC_OK;
+}
 
 extern "C" int rc_spectral_fallbacks(unsigned long long* count_host, int reset, void* stream) {
     unsigned long long* p = respec_counter_device();
@@ -492,6 +568,86 @@ extern "C" int rc_fidelity_stats(const double* ctrl_dev, int64_t C, int nspin, i
     long long blocks = (nseg + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
     fused_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(g.partials, nseg, g.nchunks, B, dkw_eps, stats_dev);
+    RC_CUDA_TRY(cudaGetLastError());
+    return RC_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Draw-sharded sweep (fewer controllers than GPUs: NStochOpt.get_rims, gen_fig_8_arim_fcall_scaling.py:121-132,
+// one controller x B draws; LBFGS.wass_cost, qnewton.py:447-455).
+// ------------------------------------------------------------------------------------------------
+extern "C" int rc_draw_shard_range(int64_t B, int world, int rank, int64_t* b_lo, int64_t* b_hi, int* v_lo, int* v_hi) {
+    if (B < 1 || world < 1 || world > MERGE_BLOCKS || MERGE_BLOCKS % world || rank < 0 || rank >= world)
+        return set_error(RC_ERR_BAD_ARG, "rc_draw_shard_range: B=%lld world=%d rank=%d (world must divide %d)", (long long)B,
+                         world, rank, MERGE_BLOCKS);
+    const long long chunk = warp_chunk_for(B), nchunks = (B + chunk - 1) / chunk;
+    const int vl = rank * (MERGE_BLOCKS / world), vh = (rank + 1) * (MERGE_BLOCKS / world);
+    const long long cl = (long long)vl * nchunks / MERGE_BLOCKS, ch = (long long)vh * nchunks / MERGE_BLOCKS;
+    if (b_lo) *b_lo = cl * chunk;
+    if (b_hi) *b_hi = ch * chunk < B ? ch * chunk : B;
+    if (v_lo) *v_lo = vl;
+    if (v_hi) *v_hi = vh;
+    return RC_OK;
+}
+
+extern "C" size_t rc_fidelity_stats_blocks_workspace_bytes(int64_t nseg, int64_t B, int world) {
+    if (nseg <= 0 || B <= 0 || world < 1) return 256;
+    const long long chunk = warp_chunk_for(B), nchunks = (B + chunk - 1) / chunk;
+    const long long local = (nchunks + world - 1) / world + MERGE_BLOCKS;
+    return (size_t)nseg * local * PART_DOUBLES * sizeof(double) + 256;
+}
+
+extern "C" int rc_fidelity_stats_blocks(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
+                                        const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed,
+                                        int64_t c_offset, int64_t b_offset, int world, int rank, double dkw_eps,
+                                        double* blocks_dev, unsigned long long* nonconv_dev, void* workspace_dev,
+                                        size_t workspace_bytes, void* stream) {
+    int rcode = check_model_args(C, nspin, inspin, outspin, S, B, model);
+    if (rcode) return rcode;
+    const long long nseg = (long long)S * C;
+    if (nseg == 0) return RC_OK;
+    int64_t b_lo, b_hi;
+    int v_lo, v_hi;
+    rcode = rc_draw_shard_range(B, world, rank, &b_lo, &b_hi, &v_lo, &v_hi);
+    if (rcode) return rcode;
+    if (!ctrl_dev || !sigma_dev || !blocks_dev) return set_error(RC_ERR_NULL, "rc_fidelity_stats_blocks: null ctrl/sigma/blocks pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long chunk = warp_chunk_for(B), nchunks_total = (B + chunk - 1) / chunk;
+    const long long B_local = b_hi - b_lo;
+    long long blocks = (nseg + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    FusedArgs g = {};
+    g.chunk = chunk;
+    g.nchunks = B_local > 0 ? (B_local + chunk - 1) / chunk : 0;
+    const size_t need = (size_t)nseg * (g.nchunks > 0 ? g.nchunks : 1) * PART_DOUBLES * sizeof(double);
+    if (!workspace_dev || workspace_bytes < need)
+        return set_error(RC_ERR_WORKSPACE, "rc_fidelity_stats_blocks: workspace %zu < required %zu bytes", workspace_bytes, need);
+    g.partials = (double*)workspace_dev;
+    if (B_local > 0) {
+        FidArgs& a = g.f;
+        a.ctrl = ctrl_dev; a.sigma = sigma_dev; a.replay = nullptr; a.fids = nullptr; a.nonconv = nonconv_dev;
+        a.C = C; a.B = B_local; a.S = S; a.N = nspin; a.in = inspin; a.out = outspin; a.model = model; a.zz = zz;
+        a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+        a.c_offset = c_offset; a.b_offset = b_offset + b_lo;
+        RC_CUDA_TRY(zig_tables_device(&a.zig));
+        g.eps = dkw_eps;
+        RC_CUDA_TRY(launch_fused(g, st));
+    }
+    block_merge_kernel<<<(unsigned)blocks, 256, 0, st>>>(g.partials, nseg, g.nchunks, b_lo / chunk, nchunks_total, v_lo, v_hi,
+                                                         blocks_dev);
+    RC_CUDA_TRY(cudaGetLastError());
+    return RC_OK;
+}
+
+extern "C" int rc_stats_from_blocks(const double* blocks_dev, int64_t nseg, int64_t B, double dkw_eps, double* stats_dev,
+                                    void* stream) {
+    if (nseg < 0 || B < 1) return set_error(RC_ERR_BAD_ARG, "rc_stats_from_blocks: nseg=%lld B=%lld", (long long)nseg, (long long)B);
+    if (nseg == 0) return RC_OK;
+    if (!blocks_dev || !stats_dev) return set_error(RC_ERR_NULL, "rc_stats_from_blocks: null pointer");
+    long long blocks = (nseg + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    blocks_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(blocks_dev, nseg, B, dkw_eps, stats_dev);
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }

@@ -158,6 +158,12 @@ def stats_unsorted(fids: torch.Tensor, dkw_eps: float = 0.0, *, check_legal: boo
     return out
 
 
+def evolution_kernel_name(nspin: int, replay: bool = False, fused: bool = False) -> str:
+    buf = C.create_string_buffer(128)
+    check(lib().rc_evolution_kernel_name(nspin, int(bool(replay)), int(bool(fused)), buf, 128))
+    return buf.value.decode()
+
+
 def spectral_fallbacks(reset: bool = False) -> int:
     """Evaluations of the N >= 11 kernels that were recomputed with accumulated eigenvector rows because the
     spectral-weights error estimate rejected them (rc_spectral_fallbacks), since the last reset."""
@@ -219,6 +225,45 @@ def fidelity_stats(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, 
     _count(2)
     if check_convergence:
         cnt.raise_if_set()
+    return out
+
+
+def fidelity_stats_blocks(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, *, world: int, rank: int,
+                          dkw_eps: float = 0.0, model: int = MODEL_COMPLEX3, zz: bool = False, seed: int = 0,
+                          c_offset: int = 0, b_offset: int = 0, counters: Counters | None = None) -> torch.Tensor:
+    """Draw-sharded sweep, this rank's part: fused evolution + streaming statistics over the draw range
+    rc_draw_shard_range(B, world, rank) of every controller, merged into the rank's block results
+    [8/world][S*C][17] (rc_fidelity_stats_blocks).  All-gathered in rank order they feed stats_from_blocks."""
+    dev = require_cuda()
+    ctrl = _f64(ctrl, dev)
+    sigmas = _f64(sigmas, dev).reshape(-1)
+    Cn, S = ctrl.shape[0], sigmas.shape[0]
+    if world < 1 or 8 % world:
+        raise ValueError("draw sharding needs a world size that divides 8")
+    out = torch.empty((8 // world, S * Cn, 17), dtype=torch.float64, device=dev)
+    wb = lib().rc_fidelity_stats_blocks_workspace_bytes(S * Cn, B, world)
+    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+    cnt = counters or Counters(dev)
+    check(lib().rc_fidelity_stats_blocks(_ptr(ctrl), Cn, nspin, inspin, outspin, _ptr(sigmas), S, B, model, int(bool(zz)),
+                                         C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, world, rank, float(dkw_eps),
+                                         _ptr(out), cnt.nonconv_ptr, _ptr(ws), wb, _stream()))
+    _count(2)
+    if counters is None:
+        cnt.raise_if_set()
+    return out
+
+
+def stats_from_blocks(blocks: torch.Tensor, B: int, dkw_eps: float = 0.0) -> torch.Tensor:
+    """[15][nseg] statistics from the gathered block results [8][nseg][17] (rc_stats_from_blocks): the fixed-order
+    finish of a draw-sharded sweep, bit-identical to fidelity_stats on one GPU."""
+    dev = require_cuda()
+    blocks = _f64(blocks, dev)
+    if blocks.dim() != 3 or blocks.shape[0] != 8 or blocks.shape[2] != 17:
+        raise ValueError("blocks must be [8][nseg][17]")
+    nseg = blocks.shape[1]
+    out = torch.empty((NUM_STATS, nseg), dtype=torch.float64, device=dev)
+    check(lib().rc_stats_from_blocks(_ptr(blocks), nseg, B, float(dkw_eps), _ptr(out), _stream()))
+    _count(1)
     return out
 
 
@@ -454,25 +499,30 @@ class RobustnessSweepPlan:
         self.ws = torch.empty(self.wb, dtype=torch.uint8, device=dev)
 
     def run(self, ctrl: torch.Tensor, sigmas: torch.Tensor, *, seed: int = 0, c_offset: int = 0, b_offset: int = 0,
-            evolution_events=None):
+            evolution_events=None, stats: torch.Tensor | None = None):
         """ctrl [C][N+1], sigmas [S]: contiguous float64 CUDA tensors.  Returns (stats, tau); the other outputs are
         the plan's attributes (sel, wsel, arim, arim_std, fids, counters).  evolution_events: optional pair of
         torch.cuda.Event(enable_timing=True) recorded around the evolution launch (they must have been recorded
-        once before so that their CUDA handles exist)."""
+        once before so that their CUDA handles exist).  stats: optional contiguous float64 CUDA tensor [15][S][C] that
+        receives the statistics instead of the plan's own (the multi-GPU exchange hands in its staging block)."""
         C_, S, B, nspin, inspin, outspin = self.shape
+        if stats is None:
+            stats = self.stats
+        elif not (stats.is_cuda and stats.dtype == torch.float64 and stats.is_contiguous() and stats.numel() == NUM_STATS * S * C_):
+            raise ValueError(f"stats must be a contiguous float64 CUDA tensor [{NUM_STATS}][{S}][{C_}]")
         if not (ctrl.is_cuda and ctrl.dtype == torch.float64 and ctrl.is_contiguous() and tuple(ctrl.shape) == (C_, nspin + 1)):
             raise ValueError(f"ctrl must be a contiguous float64 CUDA tensor [{C_}][{nspin + 1}]")
         if not (sigmas.is_cuda and sigmas.dtype == torch.float64 and sigmas.is_contiguous() and sigmas.numel() == S):
             raise ValueError(f"sigmas must be a contiguous float64 CUDA tensor [{S}]")
         check(lib().rc_robustness_sweep(_ptr(ctrl), C_, nspin, inspin, outspin, _ptr(sigmas), S, B, self.model, self.zz,
                                         C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, self.eps, self.fused,
-                                        self.groups, self.topk, self.alpha, _ptr(self.fids), _ptr(self.stats),
+                                        self.groups, self.topk, self.alpha, _ptr(self.fids), _ptr(stats),
                                         _ptr(self.tau), _ptr(self.sel), _ptr(self.wsel), self.nboot, _ptr(self.arim),
                                         _ptr(self.arim_std), self.counters.nonconv_ptr, _ptr(self.ws), self.wb,
                                         C.c_void_p(evolution_events[0].cuda_event if evolution_events else 0),
                                         C.c_void_p(evolution_events[1].cuda_event if evolution_events else 0), _stream()))
         _count(12)  # evolution + (finalize when fused | sort-free statistics otherwise) + 9 ranking kernels + ARIM bootstrap
-        return self.stats, self.tau
+        return stats, self.tau
 
 
 def arim_bootstrap_device(rims, nboot: int = 100, seed: int = 0):

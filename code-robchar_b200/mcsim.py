@@ -161,6 +161,7 @@ class MCDataSim:
         self.noises = noises
         self.numcontrollers = numcontrollers
         self.seed = seed
+        self._fresh_metrics = {}
         if rng_mode not in ("philox", "numpy"):
             raise ValueError("rng_mode must be 'philox' or 'numpy'")
         self.rng_mode = rng_mode
@@ -292,8 +293,15 @@ class MCDataSim:
     def get_algo_fid_dist(self, algoname: str, allalgoallfids: dict, noises, training_noise):
         "mcsim.py:422-460: fills allalgoallfids[algoname] with nested lists [S][C][B] and dumps the .mc"
         fids = self.simulate_fid_tensor(algoname, noises, training_noise)
+        # the metric tensors of a freshly simulated group are taken from the device tensor right here (one launch)
+        # instead of after the list -> JSON -> ndarray -> device round trip; get_metrics_dict picks them up
+        dkw_error = float(compute_dkw_error(self.alpha, self.bootreps))
+        st = engine.stats_unsorted(fids, dkw_error).cpu().numpy() if fids.numel() else None
         allalgoallfids[algoname] = fids.cpu().numpy().tolist()
-        json.dump(allalgoallfids, open(self.get_mcname(training_noise, noises), "w"))
+        if st is not None:
+            self._fresh_metrics[algoname] = (allalgoallfids[algoname], {k: st[i].tolist() for i, k in enumerate(engine.STAT_KEYS)})
+        with open(self.get_mcname(training_noise, noises), "w") as fh:
+            json.dump(allalgoallfids, fh)
         return allalgoallfids
 
     def get_fid_dists(self, training_noise: str = None, noises: np.ndarray = None, algoname=None) -> dict:
@@ -344,8 +352,13 @@ class MCDataSim:
             algofiddists = self.get_fid_dists(training_noise, noises, algoname)
             allalgos_metrics_dict = {}
             for algo in algos:
-                allalgos_metrics_dict[algo] = self.metrics_from_tensor(algofiddists[algo])
-            json.dump(allalgos_metrics_dict, open(self.get_mcname(training_noise, noises) + "m", "w"))
+                fresh = self._fresh_metrics.pop(algo, None)
+                if fresh is not None and fresh[0] is algofiddists[algo]:      # simulated in this call: already reduced
+                    allalgos_metrics_dict[algo] = fresh[1]
+                else:
+                    allalgos_metrics_dict[algo] = self.metrics_from_tensor(algofiddists[algo])
+            with open(self.get_mcname(training_noise, noises) + "m", "w") as fh:
+                json.dump(allalgos_metrics_dict, fh)
             return allalgos_metrics_dict
 
         if os.path.exists(self.get_mcname(training_noise, noises) + "m"):

@@ -37,16 +37,21 @@ def rim_sweep(controllers, noises, bootreps: int, Nspin: int, inspin: int, outsp
 def robustness_sweep(controllers: np.ndarray, noises: np.ndarray, bootreps: int, Nspin: int, inspin: int, outspin: int,
                      *, groups: int = 1, topk: int = 100, alpha_dkw: float = 0.05, alpha_cluster: float = 0.05,
                      seed: int = 0, fused: bool = False, model: int = engine.MODEL_COMPLEX3, zz: bool = False,
-                     nboot: int = 100) -> dict:
+                     nboot: int = 100, c_offset: int = 0, b_offset: int = 0, copy: bool = True) -> dict:
     """The paper's fig-4/5 sweep for `groups` controller sets given as HOST arrays: evolution,
     the 15 statistics, per-group top-k selection and Kendall matrices.  Host in, host out: the
     controllers travel to the device and the statistics / tau matrices come back (the end-to-end
     call bench.py times).  Returns {"stats": {key: [S][C]}, "tau": [G][S][S], "topk_idx": [G][k], "arim": [G][S],
-    "arim_std": [G][S]} (ARIM and its bootstrap error bar over the top-k controllers, fig 5)."""
+    "arim_std": [G][S]} (ARIM and its bootstrap error bar over the top-k controllers, fig 5).
+    c_offset / b_offset: global index of the first controller / draw (Philox counters), for callers that shard a larger
+    sweep themselves.  The arrays are the caller's own (copies); copy=False returns views of the engine's cached pinned
+    staging buffers instead, which the NEXT call with the same shapes overwrites (benchmark loops only)."""
     eps = float(compute_dkw_error(alpha_dkw, bootreps))
     st, tau, sel, ar, ars = engine.robustness_sweep_host(np.asarray(controllers), np.asarray(noises), bootreps, Nspin,
                                                          inspin, outspin, groups=groups, topk=topk,
                                                          alpha_cluster=alpha_cluster, dkw_eps=eps, seed=seed, fused=fused,
-                                                         model=model, zz=zz, nboot=nboot)
+                                                         model=model, zz=zz, nboot=nboot, c_offset=c_offset, b_offset=b_offset)
+    if copy:
+        st, tau, sel, ar, ars = (np.array(a) for a in (st, tau, sel, ar, ars))
     return {"stats": {k: st[i] for i, k in enumerate(engine.STAT_KEYS)}, "tau": tau, "topk_idx": sel, "arim": ar,
             "arim_std": ars}

@@ -72,6 +72,10 @@ int rc_fidelity_mc_stats(const double* ctrl_dev, int64_t C, int nspin, int inspi
                          double* fids_dev, double* stats_dev, unsigned long long* nonconv_dev,
                          unsigned long long* illegal_dev, void* stream);
 
+/* Name of the evolution kernel the launcher picks for this chain length / mode (register family N <= 8,
+ * shared-memory family above, eigenvector rows or spectral weights): what a benchmark labels its roofline with. */
+int rc_evolution_kernel_name(int nspin, int replay, int fused, char* buf, size_t buf_bytes);
+
 /* Chain lengths above the register-resident range (N >= 11) evaluate <out|exp(-iHT)|in> from the eigenvalues
  * alone (characteristic-polynomial weights, csrc/rc_spectral.cuh) and recompute an evaluation with accumulated
  * eigenvector rows when its a-posteriori error estimate exceeds 1e-11 (near-coincident eigenvalues with large
@@ -115,6 +119,43 @@ int rc_fidelity_stats(const double* ctrl_dev, int64_t C, int nspin, int inspin, 
                       int64_t c_offset, int64_t b_offset, const double* replay_dev, double dkw_eps,
                       double* stats_dev, unsigned long long* nonconv_dev, void* workspace_dev,
                       size_t workspace_bytes, void* stream);
+
+/* Draw-sharded sweep (fewer controllers than GPUs: NStochOpt.get_rims, gen_fig_8_arim_fcall_scaling.py:121-132 —
+ * one controller x B draws per sigma level — and LBFGS.wass_cost, qnewton.py:447-455).  The chunk partials of a
+ * segment are always merged in the same fixed order: eight contiguous blocks of chunks, each merged by one warp,
+ * the eight results merged sequentially.  Rank r of `world` (1, 2, 4 or 8) owns blocks [8r/world, 8(r+1)/world),
+ * i.e. the draws [b_lo, b_hi) rc_draw_shard_range reports (Philox counters use the global draw index).
+ * rc_fidelity_stats_blocks runs the fused evolution + streaming statistics on that range and writes the rank's
+ * block results blocks_dev [8/world][S*C][17]; all-gathered in rank order they form [8][S*C][17], which
+ * rc_stats_from_blocks turns into stats_dev [15][S*C] — bit-identical to rc_fidelity_stats on one GPU. */
+int rc_draw_shard_range(int64_t B, int world, int rank, int64_t* b_lo, int64_t* b_hi, int* v_lo, int* v_hi);
+size_t rc_fidelity_stats_blocks_workspace_bytes(int64_t nseg, int64_t B, int world);
+int rc_fidelity_stats_blocks(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
+                             const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed,
+                             int64_t c_offset, int64_t b_offset, int world, int rank, double dkw_eps,
+                             double* blocks_dev, unsigned long long* nonconv_dev, void* workspace_dev,
+                             size_t workspace_bytes, void* stream);
+int rc_stats_from_blocks(const double* blocks_dev, int64_t nseg, int64_t B, double dkw_eps, double* stats_dev,
+                         void* stream);
+
+/* Peer exchange of the per-rank statistics blocks (controller-sharded sweep, one process per GPU): what assembles
+ * MCDataSim.get_metrics_dict's tensors (mcsim.py:463-510) for the whole controller set from the shards.  The
+ * reference has no multi-device path.  rc_peer_alloc: cudaMalloc'ed, zeroed exchange buffer + its 64-byte CUDA IPC
+ * handle; rc_peer_open maps a peer's buffer from its handle (NVLink peer access enabled lazily); rc_peer_close /
+ * rc_peer_free undo them.  rc_peer_push_columns: local_dev [rows][c_local] -> columns [col_offset, col_offset +
+ * c_local) of the [rows][c_total] tensor at peer_tensors[r] of EVERY rank r (host array of `world` device addresses,
+ * this rank's own buffer included): one 2-D copy-engine transfer per destination on `stream`, no kernel.
+ * rc_peer_signal: afterwards, writes `seq` into slot `rank` of every rank's flag array (peer_flags[r], uint64[world]).
+ * rc_peer_wait: on the consumer's stream, waits until all `world` slots of local_flags have reached `seq`; after
+ * timeout_s seconds it gives up and increments *timed_out_dev (uint64, optional) instead of hanging the GPU. */
+int rc_peer_alloc(size_t bytes, void** dev_ptr_out, unsigned char* handle64_out);
+int rc_peer_open(const unsigned char* handle64, void** dev_ptr_out);
+int rc_peer_close(void* dev_ptr);
+int rc_peer_free(void* dev_ptr);
+int rc_peer_push_columns(void* const* peer_tensors, int world, const double* local_dev, int64_t rows, int64_t c_local,
+                         int64_t c_total, int64_t col_offset, void* stream);
+int rc_peer_signal(void* const* peer_flags, int world, int rank, uint64_t seq, void* stream);
+int rc_peer_wait(const void* local_flags, int world, uint64_t seq, double timeout_s, void* timed_out_dev, void* stream);
 
 /* Ordinal ranks 0..n-1 of each row, ascending, NaN last, ties by index (stable).
  * MCDataSim.get_ranks (mcsim.py:513-518).  values [R][n] -> ranks int64 [R][n]. */
@@ -181,6 +222,16 @@ int rc_robustness_sweep_host(const double* ctrl_host, int64_t C, int nspin, int 
                              int64_t c_offset, int64_t b_offset, double dkw_eps, int fused, int64_t G,
                              int64_t topk, double alpha_cluster, double* stats_host, double* tau_host,
                              int64_t* sel_host, int nboot, double* arim_host, double* arim_std_host, void* stream);
+
+/* rc_robustness_sweep_host that ALSO leaves the statistics in the caller's device tensor stats_dev_keep [15][S][C]
+ * (valid after the call): the multi-GPU sweep pushes that block to its peers (rc_peer_push_columns) while the next
+ * call computes. */
+int rc_robustness_sweep_host_keep(const double* ctrl_host, int64_t C, int nspin, int inspin, int outspin,
+                                  const double* sigma_host, int S, int64_t B, int model, int zz, uint64_t seed,
+                                  int64_t c_offset, int64_t b_offset, double dkw_eps, int fused, int64_t G,
+                                  int64_t topk, double alpha_cluster, double* stats_host, double* tau_host,
+                                  int64_t* sel_host, int nboot, double* arim_host, double* arim_std_host,
+                                  double* stats_dev_keep, void* stream);
 
 /* The same fig-4/5 sweep on DEVICE buffers: evolution (+ statistics), per-group top-k / Kendall matrices and the
  * ARIM bootstrap issued from one C call, no allocation and no synchronisation inside (what bench.py times as the

@@ -62,3 +62,58 @@ def test_sharded_sweep_world2(tmp_path, C):
     m = orc.metrics(f, 0.05)
     want = np.stack([m[k] for k in rb.engine.STAT_KEYS])
     assert np.array_equal(a, want)
+
+
+def _worker_draws(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    import robchar_b200 as rb
+    nseg, B = 6, 5000
+    ctrl = np.zeros((2, 5))            # 2 controllers < ... the mode is forced below; "auto" is checked separately
+
+    def blocks_fn(w, r):
+        nv = 8 // w
+        t = torch.empty((nv, nseg, 17), dtype=torch.float64)
+        for v in range(nv):
+            t[v] = 1000.0 * (r * nv + v) + torch.arange(nseg, dtype=torch.float64)[:, None] + 0.01 * torch.arange(17, dtype=torch.float64)
+        return t
+
+    got = rb.dist.sharded_rim_sweep(ctrl, np.linspace(0, 0.1, 3), B, 4, 0, 2, shard="draws", blocks_fn=blocks_fn,
+                                    finalize_fn=lambda b: b)
+    lo, hi = rb.dist.draw_shard_range(B, world, rank)
+    np.save(os.path.join(out_dir, f"d{rank}.npy"), got.numpy())
+    np.save(os.path.join(out_dir, f"db{rank}.npy"), np.array([lo, hi]))
+    # one controller on two ranks: "auto" picks the draw axis
+    one = rb.dist.sharded_rim_sweep(ctrl[:1], np.linspace(0, 0.1, 3), B, 4, 0, 2, blocks_fn=blocks_fn, finalize_fn=lambda b: b)
+    assert one.shape == (8, nseg, 17)
+    td.destroy_process_group()
+
+
+def test_draw_sharded_sweep_world2(tmp_path):
+    """Host logic of the draw-sharded mode: ranks own whole merge blocks in rank order, the all-gather assembles the
+    [8][nseg][17] block results in global block order on every rank, the draw ranges tile [0, B) on the chunk grid."""
+    port = _free_port()
+    tmp.spawn(_worker_draws, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = np.load(tmp_path / "d0.npy"); b = np.load(tmp_path / "d1.npy")
+    assert a.shape == (8, 6, 17) and np.array_equal(a, b)
+    assert np.array_equal(a[:, 0, 0], 1000.0 * np.arange(8))               # global block order
+    r0 = np.load(tmp_path / "db0.npy"); r1 = np.load(tmp_path / "db1.npy")
+    assert r0[0] == 0 and r0[1] == r1[0] and r1[1] == 5000 and r0[1] % 256 == 0
+
+
+def test_draw_shard_ranges_tile_the_draw_axis():
+    import robchar_b200 as rb
+    for B in (1, 31, 100, 256, 257, 5000, 100000, 10**8):
+        for world in (1, 2, 4, 8):
+            edges = [rb.dist.draw_shard_range(B, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == B
+            for (a0, a1), (b0, b1) in zip(edges, edges[1:]):
+                assert a1 == b0 and a0 <= a1
+            # the ranges of world w are unions of the ranges of world 8 (same merge blocks)
+            fine = [rb.dist.draw_shard_range(B, 8, r) for r in range(8)]
+            for r, (lo, hi) in enumerate(edges):
+                k = 8 // world
+                assert lo == fine[r * k][0] and hi == fine[(r + 1) * k - 1][1]
+    with pytest.raises(ValueError):
+        rb.dist.draw_shard_range(100, 3, 0)

@@ -947,3 +947,25 @@ def test_arim_bootstrap_device(rb):
         cols = gi * 20 + out["topk_idx"][gi]
         assert np.abs(out["arim"][gi] - W[:, cols].mean(axis=1)).max() < 1e-15
     assert out["arim_std"].shape == (3, 4) and np.all(out["arim_std"] >= 0)
+
+
+@pytest.mark.parametrize("n,C,B", [(7, 1, 100000), (5, 3, 5000), (12, 2, 1000), (4, 2, 100), (7, 1, 777)])
+def test_draw_sharded_statistics_equal_single_gpu_bit_for_bit(rb, n, C, B):
+    """Draw-sharded mode (gen_fig_8_arim_fcall_scaling.py:121-132: one controller x B draws): the ranks of a world of
+    2, 4 or 8 are emulated one after the other on this GPU; their block results, concatenated in rank order and
+    finished by rc_stats_from_blocks, equal rc_fidelity_stats on the whole draw axis bit for bit, and the oracle's
+    statistics of the same draws to 1e-12."""
+    ctrl = orc.synthetic_controllers(C, n, seed=n)
+    sig = np.array([0.0, 0.05, 0.1])
+    eps = float(orc.compute_dkw_error(0.05, B))
+    kw = dict(seed=21, c_offset=4, zz=bool(n % 2))
+    whole = rb.engine.fidelity_stats(ctrl, sig, B, n, 0, n - 1, dkw_eps=eps, **kw)
+    for world in (1, 2, 4, 8):
+        parts = [rb.engine.fidelity_stats_blocks(ctrl, sig, B, n, 0, n - 1, world=world, rank=r, dkw_eps=eps, **kw)
+                 for r in range(world)]
+        got = rb.engine.stats_from_blocks(torch.cat(parts, dim=0), B, eps).view(15, 3, C)
+        assert torch.equal(got, whole), world
+    f = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, n - 1, **kw).cpu().numpy()
+    m = orc.metrics(f, 0.05)
+    for k, key in enumerate(rb.engine.STAT_KEYS):
+        assert np.abs(whole[k].cpu().numpy() - m[key]).max() < 1e-12, key
