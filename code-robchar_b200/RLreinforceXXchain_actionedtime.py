@@ -117,11 +117,27 @@ class Environment(object):
         rows[:, 3::2] = np.diagonal(H, offset=-1, axis1=1, axis2=2) - 1.0
         return rows
 
+    def _is_real_symmetric_tridiagonal(self, H) -> bool:
+        """What a replay row can carry; cached per array object (the fixed training stack is checked once)."""
+        key = id(H)
+        hit = getattr(self, "_tridiag_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        Hs = np.asarray(H).reshape(-1, self.Nspin, self.Nspin)
+        band = np.abs(np.subtract.outer(np.arange(self.Nspin), np.arange(self.Nspin))) <= 1
+        ok = (not np.any(np.imag(Hs) != 0)) and (not np.any(Hs[:, ~band] != 0)) and \
+            np.array_equal(np.diagonal(Hs, offset=-1, axis1=1, axis2=2), np.diagonal(Hs, offset=1, axis1=1, axis2=2))
+        if isinstance(H, np.ndarray):
+            self._tridiag_cache = (key, ok)
+        return ok
+
     def _amplitudes(self, H, action, t):
         """<out| exp(-i t (H_k + action)) |in> for every Hamiltonian of the stack H [m][N][N]."""
         action = np.asarray(action, dtype=np.float64)
         bias = np.diag(action) if action.ndim == 2 else action
-        if self.topo != "ring" and (action.ndim != 2 or not np.any(action - np.diag(bias))):
+        tridiag = self._is_real_symmetric_tridiagonal(H)
+        # replay rows carry real symmetric tridiagonal Hamiltonians only; anything else takes the dense path below
+        if self.topo != "ring" and tridiag and (action.ndim != 2 or not np.any(action - np.diag(bias))):
             x = np.concatenate([bias, [t]])
             _, amps = engine.objective_host(x, self._rows(H), self.Nspin, self.in_spin, self.out_spin, model=MODEL_REAL2,
                                             want_amps=True)

@@ -341,81 +341,3 @@ extern "C" int rc_robustness_sweep_host_keep(const double* ctrl_host, int64_t C,
                            arim_host, arim_std_host, stream, stats_dev_keep);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Low-latency objective evaluation for optimiser loops (one controller, m explicit perturbations).
-// ------------------------------------------------------------------------------------------------
-namespace rc {
-// Pinned staging + device scratch kept per (host thread, device): an optimiser calls the objective thousands
-// of times with the same shapes, so nothing is allocated in steady state.
-struct ObjectiveCtx {
-    char* pin = nullptr;
-    char* dev = nullptr;
-    size_t bytes = 0;
-};
-static cudaError_t objective_ctx(size_t need, ObjectiveCtx** out) {
-    static thread_local ObjectiveCtx cache[64];
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    ObjectiveCtx& c = cache[dev];
-    if (c.bytes < need) {
-        if (c.pin) cudaFreeHost(c.pin);
-        if (c.dev) cudaFree(c.dev);
-        c.pin = c.dev = nullptr;
-        c.bytes = 0;
-        size_t cap = 4096;
-        while (cap < need) cap *= 2;
-        e = cudaHostAlloc((void**)&c.pin, cap, cudaHostAllocDefault);
-        if (e != cudaSuccess) return e;
-        e = cudaMalloc((void**)&c.dev, cap);
-        if (e != cudaSuccess) { cudaFreeHost(c.pin); c.pin = nullptr; return e; }
-        c.bytes = cap;
-    }
-    *out = &c;
-    return cudaSuccess;
-}
-}  // namespace rc
-
-extern "C" int rc_objective_host(const double* x_host, int nspin, int inspin, int outspin, const double* rows_host,
-                                 int64_t m, int model, int zz, double dkw_eps, double* fids_host, double* stats_host,
-                                 double* amps_host, void* stream) {
-    if (nspin < 2 || nspin > RC_MAX_NSPIN) return set_error(RC_ERR_BAD_ARG, "nspin=%d outside [2,%d]", nspin, RC_MAX_NSPIN);
-    if (model != RC_MODEL_COMPLEX3 && model != RC_MODEL_REAL2) return set_error(RC_ERR_BAD_ARG, "unknown model %d", model);
-    if (m < 0) return set_error(RC_ERR_BAD_ARG, "rc_objective_host: m=%lld", (long long)m);
-    if (m == 0) return RC_OK;
-    if (!x_host || (!fids_host && !stats_host && !amps_host)) return set_error(RC_ERR_NULL, "rc_objective_host: null x / no output");
-    if (!rows_host && m != 1) return set_error(RC_ERR_BAD_ARG, "rc_objective_host: the nominal evaluation (rows == NULL) takes m = 1");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int K = (model == RC_MODEL_COMPLEX3 ? 3 : 2) * nspin;
-    // one buffer, same layout on both sides: [x (N+1)] [sigma] [rows m*K] | [nonconv counter] [fids m] [stats 15] [amps 2m]
-    const size_t n_in = (size_t)(nspin + 2) + (rows_host ? (size_t)m * K : 0);
-    const size_t in_bytes = (n_in + 1) * 8;                 // inputs + the zeroed counter
-    const size_t out_bytes = (1 + (size_t)m + ((stats_host || amps_host) ? RC_NUM_STATS : 0) + (amps_host ? 2 * (size_t)m : 0)) * 8;
-    ObjectiveCtx* c = nullptr;
-    RC_CUDA_TRY(objective_ctx((n_in + 1 + 3 * (size_t)m + RC_NUM_STATS) * 8, &c));
-    double* hp = (double*)c->pin;
-    double* dp = (double*)c->dev;
-    memcpy(hp, x_host, (size_t)(nspin + 1) * 8);
-    hp[nspin + 1] = rows_host ? 1.0 : 0.0;                  // rows are explicit perturbations (sigma 1); none: sigma 0
-    if (rows_host) memcpy(hp + nspin + 2, rows_host, (size_t)m * K * 8);
-    hp[n_in] = 0.0;                                          // bit pattern of the uint64 counter 0
-    RC_CUDA_TRY(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
-    int rcode = fidelity_mc_impl("rc_objective_host", dp, 1, nspin, inspin, outspin, dp + nspin + 1, 1, m, model, zz, 0, 0, 0,
-                                 rows_host ? dp + nspin + 2 : nullptr, dp + n_in + 1, (unsigned long long*)(dp + n_in), 0, st,
-                                 amps_host ? dp + n_in + 1 + m + RC_NUM_STATS : nullptr);
-    if (rcode) return rcode;
-    if (stats_host) {   // the 15 statistics of the m fidelities as ONE segment (W = wass_cost's objective, 1 - W = their mean)
-        rcode = stats_unsorted_impl(dp + n_in + 1, 1, m, dkw_eps, dp + n_in + 1 + m, 1, nullptr, st);
-        if (rcode) return rcode;
-    }
-    RC_CUDA_TRY(cudaMemcpyAsync(hp + n_in, dp + n_in, out_bytes, cudaMemcpyDeviceToHost, st));
-    RC_CUDA_TRY(cudaStreamSynchronize(st));
-    unsigned long long nonconv;
-    memcpy(&nonconv, hp + n_in, 8);
-    if (fids_host) memcpy(fids_host, hp + n_in + 1, (size_t)m * 8);
-    if (stats_host) memcpy(stats_host, hp + n_in + 1 + m, (size_t)RC_NUM_STATS * 8);
-    if (amps_host) memcpy(amps_host, hp + n_in + 1 + m + RC_NUM_STATS, 2 * (size_t)m * 8);
-    if (nonconv) return set_error(RC_ERR_NONCONV, "eigensolver did not converge for %llu evaluations (NaN written)", nonconv);
-    return RC_OK;
-}

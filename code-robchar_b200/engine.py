@@ -469,6 +469,42 @@ def objective_host(x, rows, nspin: int, inspin: int, outspin: int, *, model: int
     return res if len(res) > 1 else res[0]
 
 
+class ObjectiveEvaluator:
+    """Preallocated call frame of rc_objective_host for ONE shape (chain, model, number of perturbation rows m, wanted
+    outputs): an optimiser calls its objective thousands of times with the same shape, so the numpy staging arrays
+    and the ctypes argument tuple are built once and a call is two small copies plus one foreign call (the Python
+    side of the per-call latency, tools/latency_bench.py).  m = 0: the nominal evaluation (no rows)."""
+
+    def __init__(self, nspin: int, inspin: int, outspin: int, m: int, *, model: int = MODEL_COMPLEX3, zz: bool = False,
+                 want_fids: bool = True, want_stats: bool = False, want_amps: bool = False, dkw_eps: float = 0.0):
+        require_cuda()
+        self.n, self.m = nspin, max(1, m)
+        self.K = draws_per_eval(nspin, model)
+        self.x = np.zeros(nspin + 1)
+        self.rows = np.zeros((m, self.K)) if m > 0 else None
+        self.fids = np.empty(self.m) if want_fids else None
+        self.stats = np.empty(NUM_STATS) if want_stats else None
+        self.amps = np.empty(self.m, dtype=np.complex128) if want_amps else None
+        vp = lambda a: C.c_void_p(a.ctypes.data if a is not None else 0)
+        self._fn = lib().rc_objective_host
+        self._args = (vp(self.x), nspin, inspin, outspin, vp(self.rows), self.m, model, int(bool(zz)), float(dkw_eps),
+                      vp(self.fids), vp(self.stats), vp(self.amps), C.c_void_p(0))
+        self._stream_slot = len(self._args) - 1
+
+    def __call__(self, x, rows=None):
+        """Evaluate; results are in self.fids / self.stats / self.amps (overwritten by the next call)."""
+        self.x[:] = x
+        if self.rows is not None:
+            self.rows[:] = rows
+        stream = torch.cuda.current_stream().cuda_stream
+        args = self._args if stream == 0 else self._args[:self._stream_slot] + (C.c_void_p(stream),)
+        code = self._fn(*args)
+        if code:
+            check(code)
+        _count(1)
+        return self
+
+
 class RobustnessSweepPlan:
     """Device buffers + workspace of rc_robustness_sweep for one problem shape, allocated once; run() issues the
     whole fig-4/5 sweep (evolution, statistics, top-k, Kendall matrices, ARIM bootstrap) from ONE C call with no
@@ -570,6 +606,24 @@ def dense_fidelity(H, T, inspin: int, outspin: int) -> torch.Tensor:
     U = expm_batch(-1j * Tt[:, None, None] * H)
     phi = U[:, outspin, inspin]
     return phi.real * phi.real + phi.imag * phi.imag
+
+
+def fidelity_grad(X, nspin: int, inspin: int, outspin: int, *, rows=None, zz: bool = False):
+    """(err [C], grad [C][N+1]) of eval_static_fidelity_gradient (qnewton.py:162-212) for the controllers X [C][N+1]
+    (host arrays in and out, rc_fidelity_grad_host): infidelity and its analytic gradient w.r.t. biases and time from
+    the eigendecomposition, any N <= 32.  rows [C][2N]: optional explicit perturbations (real 2-draw replay layout)."""
+    require_cuda()
+    X = np.ascontiguousarray(np.asarray(X, dtype=np.float64).reshape(-1, nspin + 1))
+    Cn = X.shape[0]
+    rp = C.c_void_p(0)
+    if rows is not None:
+        rows = np.ascontiguousarray(np.asarray(rows, dtype=np.float64).reshape(Cn, 2 * nspin))
+        rp = C.c_void_p(rows.ctypes.data)
+    err, grad = np.empty(Cn), np.empty((Cn, nspin + 1))
+    check(lib().rc_fidelity_grad_host(C.c_void_p(X.ctypes.data), Cn, nspin, inspin, outspin, rp, int(bool(zz)),
+                                      C.c_void_p(err.ctypes.data), C.c_void_p(grad.ctypes.data), _stream()))
+    _count(1)
+    return err, grad
 
 
 def fp64_peak_tflops() -> float:

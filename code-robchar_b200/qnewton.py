@@ -45,6 +45,7 @@ class LBFGS(object):
         self.train_size = opt_train_size
         self.randH, self.randH_test = self.randHset_constructor(train_size=opt_train_size, test_size=opt_test_size)
         self._rows_train = self._rows_test = None
+        self._evaluators = {}
 
     # ---- model -------------------------------------------------------------------------------------
     def sys_hamiltonian(self):
@@ -93,6 +94,16 @@ class LBFGS(object):
         return out_train, out_test
 
     # ---- packing of explicit Hamiltonians into replay rows (sigma = 1) -----------------------------------
+    def _is_real_symmetric_tridiagonal(self, H: np.ndarray) -> bool:
+        """True when every matrix of the stack [m][N][N] is real, symmetric and tridiagonal — what a replay row can
+        carry.  Anything else (imaginary parts, ring / next-nearest entries, non-symmetric input) must go through the
+        dense path: the reference runs expm on the full complex matrix (qnewton.py:395-397)."""
+        H = np.asarray(H)
+        n = self.Nspin
+        band = np.abs(np.subtract.outer(np.arange(n), np.arange(n))) <= 1
+        return (not np.any(np.imag(H) != 0)) and (not np.any(H[..., ~band] != 0)) and \
+            np.array_equal(np.diagonal(H, offset=-1, axis1=-2, axis2=-1), np.diagonal(H, offset=1, axis1=-2, axis2=-1))
+
     def _rows_from_hamiltonians(self, H: np.ndarray) -> np.ndarray:
         """[m][N][N] real-symmetric tridiagonal Hamiltonians (HH + perturbation) -> [m][2N] replay rows."""
         H = np.asarray(H)
@@ -104,32 +115,61 @@ class LBFGS(object):
         rows[:, 3::2] = lo - 1.0
         return rows
 
+    def _noise_rows(self, reps: int) -> np.ndarray:
+        """`reps` draws of structured_perturabation (qnewton.py:366-379) as replay rows [reps][2N]: the 2N normals of
+        one perturbation in upstream's order (z_ii, nn_i per site) ARE the row, so one vectorised draw consumes the
+        global np.random stream exactly like upstream's scalar calls (same legacy Gaussian sequence)."""
+        return np.random.normal(scale=self.noise, size=(reps, 2 * self.Nspin))
+
+    def _dense_fidelities(self, x, H: np.ndarray) -> np.ndarray:
+        """|expm(-i T (H_k + diag(x)))[out, in]|^2 for explicit full Hamiltonians (ring topology, complex or
+        non-tridiagonal user input): the dense device path (rc_expm_batch)."""
+        n = self.Nspin
+        H = np.asarray(H, dtype=np.complex128).reshape(-1, n, n) + np.diag(np.asarray(x[:n], dtype=np.float64))
+        return engine.dense_fidelity(H, np.full(H.shape[0], abs(x[n])), self.In, self.Out).cpu().numpy()
+
+    def _evaluator(self, m: int, stats: bool) -> "engine.ObjectiveEvaluator":
+        """Cached call frame of the low-latency objective entry point for m perturbation rows (0: nominal)."""
+        key = (m, stats)
+        ev = self._evaluators.get(key)
+        if ev is None:
+            ev = engine.ObjectiveEvaluator(self.Nspin, self.In, self.Out, m, model=MODEL_REAL2, zz=self.heisenberg_int,
+                                           want_fids=not stats, want_stats=stats)
+            if len(self._evaluators) < 64:
+                self._evaluators[key] = ev
+        return ev
+
     def _eval_rows(self, x, rows: np.ndarray | None) -> np.ndarray:
         """Fidelities of x under the perturbation rows (None: nominal) as a host array."""
         if self.topo != "ring":   # tridiagonal: the low-latency objective entry point (one C call, host in/out)
-            return engine.objective_host(x, rows, self.Nspin, self.In, self.Out, model=MODEL_REAL2, zz=self.heisenberg_int)
-        xa = np.asarray(x, dtype=np.float64).reshape(1, self.Nspin + 1)
+            if rows is None:
+                return self._evaluator(0, False)(x).fids
+            return self._evaluator(rows.shape[0], False)(x, rows).fids
+        n = self.Nspin
         if rows is None:
-            rows = np.zeros((1, 2 * self.Nspin))
+            rows = np.zeros((1, 2 * n))
         m = rows.shape[0]
-        if self.topo == "ring":  # not tridiagonal: dense expm path on explicit Hamiltonians
-            n = self.Nspin
-            H = np.broadcast_to(self.HH, (m, n, n)).copy()
-            idx = np.arange(n)
-            H[:, idx, idx] += rows[:, 0::2] + xa[0, :n]
-            lo = np.arange(1, n)
-            H[:, lo, lo - 1] += rows[:, 3::2]
-            H[:, lo - 1, lo] += rows[:, 3::2]
-            return engine.dense_fidelity(H, np.full(m, abs(xa[0, n])), self.In, self.Out).cpu().numpy()
-        raise AssertionError("unreachable")
+        H = np.broadcast_to(self.HH, (m, n, n)).copy()     # ring: not tridiagonal, dense expm on explicit Hamiltonians
+        idx = np.arange(n)
+        H[:, idx, idx] += rows[:, 0::2]
+        lo = np.arange(1, n)
+        H[:, lo, lo - 1] += rows[:, 3::2]
+        H[:, lo - 1, lo] += rows[:, 3::2]
+        return self._dense_fidelities(x, H)
 
     def eval_static_fidelity_gradient(self, x):
-        """qnewton.py:162-212: infidelity and its gradient w.r.t. biases and time.  Same construction as
-        upstream — N block exponentials expm([[TH, 0], [-iT C_l, TH]]) for the bias derivatives and H U for the
-        time derivative — with all N+1 matrix exponentials evaluated on the device (rc_expm_batch)."""
+        """qnewton.py:162-212: infidelity and its gradient w.r.t. biases and time.  Chain topology: from the
+        eigendecomposition of the tridiagonal Hamiltonian on the device (rc_fidelity_grad, any Nspin <= 32) instead
+        of upstream's N + 1 dense matrix exponentials; ham_noisy adds one structured_perturabation() draw exactly
+        like upstream (:179-180).  Ring topology keeps upstream's construction on the dense device path."""
         n = self.Nspin
+        if self.topo != "ring":
+            rows = self._noise_rows(1) if self.ham_noisy else None
+            err, grad = engine.fidelity_grad(np.asarray(x, dtype=np.float64)[None], n, self.In, self.Out, rows=rows,
+                                             zz=self.heisenberg_int)
+            return float(err[0]), grad[0]
         if 2 * n > 32:
-            raise NotImplementedError("gradient path supports Nspin <= 16 (2N x 2N block exponentials)")
+            raise NotImplementedError("ring-topology gradient supports Nspin <= 16 (2N x 2N block exponentials)")
         T = abs(x[n])
         H = self.HH.copy()
         for l in range(n):
@@ -177,11 +217,13 @@ class LBFGS(object):
         if use_fixed_ham:
             if rH is None:
                 raise AssertionError(f"H cannot be {type(rH)}")
-            rows = self._rows_from_hamiltonians(np.asarray(rH)[None])
+            rH = np.asarray(rH)
+            if self.topo == "ring" or not self._is_real_symmetric_tridiagonal(rH):
+                fid = float(self._dense_fidelities(x, rH[None])[0])     # full complex matrix, like upstream's expm
+                return self._shot_noise(fid) if noisy else fid
+            rows = self._rows_from_hamiltonians(rH[None])
         else:
-            rows = None
-            if ham_noisy:
-                rows = self._rows_from_hamiltonians((self.HH + self.structured_perturabation())[None])
+            rows = self._noise_rows(1) if ham_noisy else None
         fid = float(self._eval_rows(x, rows)[0])
         return self._shot_noise(fid) if noisy else fid
 
@@ -195,18 +237,15 @@ class LBFGS(object):
             return float(np.mean([self._shot_noise(v) for v in self._eval_rows(x, rows)]))
         if self.topo == "ring":
             return float(np.mean(self._eval_rows(x, rows)))
-        _, st = engine.objective_host(x, rows, self.Nspin, self.In, self.Out, model=MODEL_REAL2, zz=self.heisenberg_int,
-                                      want_fids=False, want_stats=True)
+        st = self._evaluator(rows.shape[0], True)(x, rows).stats
         return float(1.0 - st[0])                                  # mean fidelity = 1 - W1 (device reduction)
 
     def wass_cost(self, x, bootstrap_reps=5):
         """qnewton.py:447-455: W1 to delta(1) of `bootstrap_reps` noisy fidelities (host draws in upstream order)."""
-        rows = np.stack([self._rows_from_hamiltonians((self.HH + self.structured_perturabation())[None])[0]
-                         for _ in range(bootstrap_reps)])
+        rows = self._noise_rows(bootstrap_reps)
         if self.topo == "ring":
             return float(engine.stats(torch.as_tensor(self._eval_rows(x, rows)).reshape(1, -1), 0.0)[0, 0].item())
-        _, st = engine.objective_host(x, rows, self.Nspin, self.In, self.Out, model=MODEL_REAL2, zz=self.heisenberg_int,
-                                      want_fids=False, want_stats=True)
+        st = self._evaluator(bootstrap_reps, True)(x, rows).stats
         return float(st[0])                                        # W1 to the ideal distribution (wd_from_ideal)
 
     def infidelity(self, x):

@@ -265,6 +265,18 @@ int rc_objective_host(const double* x_host, int nspin, int inspin, int outspin, 
                       int model, int zz, double dkw_eps, double* fids_host, double* stats_host, double* amps_host,
                       void* stream);
 
+/* Infidelity 1 - |U[out,in]|^2 and its analytic gradient w.r.t. the N biases and the evolution time for C controllers
+ * x [C][N+1]: LBFGS.eval_static_fidelity_gradient (qnewton.py:162-212), the L-BFGS inner call (qnewton.py:497,513).
+ * Upstream evaluates N + 1 dense matrix exponentials (N of them on 2N x 2N block matrices); here the derivatives come
+ * from the eigendecomposition of the tridiagonal Hamiltonian (divided differences of exp(-i lambda T), csrc/rc_grad.cu),
+ * one warp per controller, any N <= 32.  rows [C][2N] (optional): explicit perturbation per controller in the real
+ * 2-draw replay layout, sigma = 1 (ham_noisy=True adds structured_perturabation(), qnewton.py:179-180).
+ * err [C], grad [C][N+1].  NaN controllers give NaN outputs. */
+int rc_fidelity_grad(const double* x_dev, int64_t C, int nspin, int inspin, int outspin, const double* rows_dev, int zz,
+                     double* err_dev, double* grad_dev, unsigned long long* nonconv_dev, void* stream);
+int rc_fidelity_grad_host(const double* x_host, int64_t C, int nspin, int inspin, int outspin, const double* rows_host,
+                          int zz, double* err_host, double* grad_host, void* stream);
+
 /* Dense complex matrix exponential of `batch` M x M matrices (M <= 32), interleaved (re, im) float64,
  * row-major: out = expm(A).  The generality path behind the reference's scipy.linalg.expm calls whose
  * argument is not Hermitian tridiagonal: topo="ring" (noise_model.py:83-85), the complex diagonal

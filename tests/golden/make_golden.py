@@ -334,6 +334,34 @@ def make_dense_path():
     print("dense_path done")
 
 
+def make_gradient():
+    """eval_static_fidelity_gradient of the UNMODIFIED reference (qnewton.py:162-212) at N = 4, 7, 16, 32, interior and
+    end-to-end targets, Heisenberg term, and with ham_noisy=True under a fixed numpy seed (the perturbation draw is
+    recorded so the device path can be fed the same matrix)."""
+    import qnewton as ref_q
+    out = {}
+    meta = []
+    rs = np.random.RandomState(77)
+    for n, i, o, scale, hz in [(4, 0, 2, 10.0, False), (7, 0, 6, 10.0, False), (7, 0, 3, 3.0, True), (16, 0, 15, 1.0, False),
+                               (16, 3, 9, 1.0, True), (32, 0, 31, 0.2, False)]:
+        env = ref_q.LBFGS(n, i, o, noise=0.05, opt_train_size=2, heisenberg_int=hz)
+        C = 4 if n <= 16 else 2
+        X = np.concatenate([rs.uniform(-scale, scale, (C, n)), rs.uniform(1, 30, (C, 1)) if n <= 16 else rs.uniform(18, 30, (C, 1))], axis=1)
+        X[0, n] *= -1                                            # abs(T)
+        eg = [env.eval_static_fidelity_gradient(x) for x in X]
+        key = f"n{n}_{i}_{o}"
+        out[key + "_X"] = X
+        out[key + "_err"] = np.array([e for e, g in eg]); out[key + "_grad"] = np.array([g for e, g in eg])
+        env.ham_noisy = True
+        np.random.seed(1000 + n)
+        eg = [env.eval_static_fidelity_gradient(x) for x in X]
+        out[key + "_noisy_err"] = np.array([e for e, g in eg]); out[key + "_noisy_grad"] = np.array([g for e, g in eg])
+        meta.append((key, n, i, o, int(hz), 1000 + n))
+    out["meta"] = np.array(meta)
+    np.savez_compressed(f"{OUT}/gradient.npz", **out)
+    print("gradient:", [m[0] for m in meta])
+
+
 def make_rl_env():
     """Rewards / noise-free fidelities of the UNMODIFIED RL environment (RLreinforceXXchain_actionedtime.py:260-279)
     driven the way ppo.py:338-363 drives it: reset, advance timestep, step(diag(bias increments))."""
@@ -390,4 +418,5 @@ if __name__ == "__main__":
     make_large_n()
     make_objective_and_arim()
     make_dense_path()
+    make_gradient()
     make_rl_env()
