@@ -41,6 +41,7 @@ _SIGNATURES = {
                                        _vp, _vp, _vp, _vp, _vp]),
     "rc_stats_unsorted": (C.c_int, [_vp, _i64, _i64, _f64, _vp, _vp, _vp]),
     "rc_evolution_kernel_name": (C.c_int, [_i32, _i32, _i32, C.c_char_p, _sz]),
+    "rc_rim_p": (C.c_int, [_vp, _i64, _i64, _f64, _vp, _vp, _vp]),
     "rc_spectral_fallbacks": (C.c_int, [_vp, _i32, _vp]),
     "rc_philox_normals": (C.c_int, [_i64, _i32, _i32, _i64, _i32, _u64, _i64, _i64, _vp, _vp]),
     "rc_stats_workspace_bytes": (_sz, [_i64, _i64]),

@@ -34,18 +34,18 @@ def bootstrap_indices_numpy(rows: int, k: int, bootsamples: int) -> np.ndarray:
 def arim_bootstrap(rims, bootsamples: int = 100, rng_mode: str = "numpy", seed: int = 0):
     """(ARIM [S], bootstrap std [S]) for a RIM matrix [S][k].
     rng_mode="numpy": consumes the global np.random stream exactly like upstream's
-    bootstrap_resampling_std loop; "torch": device-side index generation (seeded, faster)."""
+    bootstrap_resampling_std loop (indices drawn on the host, resampled statistics on the device);
+    "device" (alias "torch"): Philox indices generated inside the kernel (rc_arim_bootstrap), seeded, one launch."""
     dev = engine.require_cuda()
     r = torch.as_tensor(np.ascontiguousarray(np.asarray(rims, dtype=np.float64))).to(dev)
     S, k = r.shape
+    if rng_mode in ("device", "torch"):      # resampling indices from in-kernel Philox: one launch (rc_arim_bootstrap)
+        a, s = engine.arim_bootstrap_device(r, nboot=bootsamples, seed=seed)
+        return a.cpu().numpy(), s.cpu().numpy()
+    if rng_mode != "numpy":
+        raise ValueError("rng_mode must be 'numpy' or 'device'")
     centre = 1 - engine.stats(r.clone(), 0.0)[0]
-    if rng_mode == "numpy":
-        idx = torch.as_tensor(bootstrap_indices_numpy(S, k, bootsamples)).to(dev)
-    elif rng_mode == "torch":
-        g = torch.Generator(device=dev); g.manual_seed(seed)
-        idx = torch.randint(0, k, (S, bootsamples, k), generator=g, device=dev)
-    else:
-        raise ValueError("rng_mode must be 'numpy' or 'torch'")
+    idx = torch.as_tensor(bootstrap_indices_numpy(S, k, bootsamples)).to(dev)
     res = torch.gather(r[:, None, :].expand(S, bootsamples, k), 2, idx).contiguous()   # index plumbing
     boot = 1 - engine.stats(res, 0.0)[0]                        # [S][bootsamples] ARIM of every resample
     std = engine.stats(boot.contiguous(), 0.0)[9]               # population std over the resamples (np.std)

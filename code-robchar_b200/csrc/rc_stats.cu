@@ -614,3 +614,46 @@ extern "C" int rc_stats(const double* fids_dev, int64_t nseg, int64_t B, double 
     }
     return RC_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// p-RIM: (mean((1 - f)^p))^(1/p) per segment (RIM_p, wd_sortof_fast_implementation.py:147-174; p = 0 gives 1,
+// p = 1 is the W row of the statistics).  One warp per segment, one streaming pass, fixed reduction tree.
+// ---------------------------------------------------------------------------------------------
+namespace rc {
+__global__ void __launch_bounds__(256) rim_p_kernel(const double* __restrict__ fids, long long nseg, long long B, double p,
+                                                    double* __restrict__ out, unsigned long long* illegal) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long seg = warp0; seg < nseg; seg += nwarps) {
+        const double* src = fids + seg * B;
+        double acc = 0.0;
+        unsigned bad = 0;
+        for (long long j = lane; j < B; j += 32) {
+            const double f = __ldcs(src + j);
+            bad += fabs(f - 1e-8) > 1.0 ? 1u : 0u;          // check_fidtype (wd_sortof_fast_implementation.py:23)
+            acc += pow(1.0 - f, p);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        bad = __reduce_add_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            out[seg] = p == 0.0 ? 1.0 : pow(acc / (double)B, 1.0 / p);
+            if (bad && illegal) atomicAdd(illegal, (unsigned long long)bad);
+        }
+    }
+}
+}  // namespace rc
+
+extern "C" int rc_rim_p(const double* fids_dev, int64_t nseg, int64_t B, double p, double* out_dev,
+                        unsigned long long* illegal_dev, void* stream) {
+    if (nseg < 0 || B < 1) return rc::set_error(RC_ERR_BAD_ARG, "rc_rim_p: nseg=%lld B=%lld", (long long)nseg, (long long)B);
+    if (nseg == 0) return RC_OK;
+    if (!fids_dev || !out_dev) return rc::set_error(RC_ERR_NULL, "rc_rim_p: null pointer");
+    long long blocks = (nseg + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    rc::rim_p_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(fids_dev, nseg, B, p, out_dev, illegal_dev);
+    RC_CUDA_TRY(cudaGetLastError());
+    return RC_OK;
+}

@@ -173,6 +173,22 @@ def spectral_fallbacks(reset: bool = False) -> int:
     return int(v.value)
 
 
+def rim_p(fids, p: float = 2, *, check_legal: bool = True) -> torch.Tensor:
+    """p-RIM (mean((1-f)^p))^(1/p) of fids[*lead, B] per segment on the device (rc_rim_p): [*lead]."""
+    dev = require_cuda()
+    fids = _f64(fids, dev) if not (isinstance(fids, torch.Tensor) and fids.is_cuda and fids.dtype == torch.float64
+                                   and fids.is_contiguous()) else fids
+    lead, B = tuple(fids.shape[:-1]), fids.shape[-1]
+    nseg = int(np.prod(lead)) if lead else 1
+    out = torch.empty(lead if lead else (1,), dtype=torch.float64, device=dev)
+    cnt = Counters(dev)
+    check(lib().rc_rim_p(_ptr(fids), nseg, B, float(p), _ptr(out), cnt.illegal_ptr, _stream()))
+    _count(1)
+    if check_legal:
+        cnt.raise_if_set()
+    return out if lead else out.reshape(())
+
+
 def philox_normals(C_: int, nspin: int, S: int, B: int, *, model: int = MODEL_COMPLEX3, seed: int = 0,
                    c_offset: int = 0, b_offset: int = 0) -> torch.Tensor:
     dev = require_cuda()

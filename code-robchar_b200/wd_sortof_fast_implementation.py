@@ -64,15 +64,15 @@ def wd_from_ideal_zero(fids, sort_fids: bool = True):
 
 
 def RIM_p(fids, p=2) -> float:
-    """(mean((1-f)^p))^(1/p) (wd_sortof_fast_implementation.py:147-174).  p=1 is the W row of the
-    device statistics; other orders reduce the device-resident sample with a torch reduction
-    (plumbing: a single elementwise+mean)."""
+    """(mean((1-f)^p))^(1/p) (wd_sortof_fast_implementation.py:147-174), one device pass (rc_rim_p); p = 0 gives 1.
+    Raises AssertionError for values outside [0,1] like upstream's check_fidtype."""
     f = _as_fids(fids)
     if p == 0:
         return 1
-    dev = engine.require_cuda()
     t = f if isinstance(f, torch.Tensor) else torch.as_tensor(np.asarray(f, dtype=np.float64))
-    t = t.to(dev, torch.float64).reshape(-1)
-    if bool(((t - 1e-8).abs() > 1).any()):
-        raise AssertionError("illegal fids values - must be in [0,1]")
-    return float(torch.pow(torch.pow(1 - t, p).mean(), 1 / p).item())
+    return float(engine.rim_p(t.reshape(1, -1), p)[0].item())
+
+
+def RIM_p_batch(fids, p=2) -> torch.Tensor:
+    """RIM_p of every segment of fids[*lead, B] on the device: [*lead]."""
+    return engine.rim_p(fids, p)

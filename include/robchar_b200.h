@@ -110,6 +110,11 @@ int rc_stats(const double* fids_dev, int64_t nseg, int64_t B, double dkw_eps, do
 int rc_stats_unsorted(const double* fids_dev, int64_t nseg, int64_t B, double dkw_eps, double* stats_dev,
                       unsigned long long* illegal_dev, void* stream);
 
+/* p-RIM of each segment: (mean((1 - f)^p))^(1/p), p = 0 -> 1 (RIM_p, wd_sortof_fast_implementation.py:147-174).
+ * fids_dev [nseg][B] -> out_dev [nseg]; illegal_dev as in rc_stats. */
+int rc_rim_p(const double* fids_dev, int64_t nseg, int64_t B, double p, double* out_dev, unsigned long long* illegal_dev,
+             void* stream);
+
 /* Fused evolution + statistics that never materialises the fidelity tensor (streaming moments;
  * W = mean(1 - f), identical to the sorted formula up to rounding).  Same arguments as
  * rc_fidelity_mc; stats_dev [15][S][C].  workspace: rc_fidelity_stats_workspace_bytes(S*C). */

@@ -220,6 +220,28 @@ def _oracle_objective_host(x, rows, nspin, inspin, outspin, *, model=0, zz=False
     return res if len(res) > 1 else res[0]
 
 
+class _OracleObjectiveEvaluator:
+    """Stand-in for engine.ObjectiveEvaluator (the preallocated call frame of rc_objective_host) on the CPU oracle."""
+
+    def __init__(self, nspin, inspin, outspin, m, *, model=0, zz=False, want_fids=True, want_stats=False, want_amps=False,
+                 dkw_eps=0.0):
+        self.a = (nspin, inspin, outspin)
+        self.kw = dict(model=model, zz=zz, want_fids=True, want_stats=want_stats, dkw_eps=dkw_eps, want_amps=want_amps)
+        self.want_fids, self.want_stats, self.want_amps = want_fids, want_stats, want_amps
+        self.fids = self.stats = self.amps = None
+
+    def __call__(self, x, rows=None):
+        res = _oracle_objective_host(x, None if rows is None else np.asarray(rows), *self.a, **self.kw)
+        res = res if isinstance(res, tuple) else (res,)
+        self.fids = res[0]
+        k = 1
+        if self.want_stats:
+            self.stats = res[k]; k += 1
+        if self.want_amps:
+            self.amps = res[k]
+        return self
+
+
 def test_rl_environment_host_logic_matches_reference(monkeypatch):
     """The Environment mirror's host side (RNG draw order incl. reset's hidden draws, bias accumulation and
     wrapping into the bounds, time wrapping, binomial / adaptive shot noise, mean-propagator reward, transfer-
@@ -264,6 +286,7 @@ def test_lbfgs_objective_host_logic_matches_reference(monkeypatch):
     and adaptive shot noise, W1 objective) against the goldens recorded from the unmodified reference, with the
     device evaluation replaced by the oracle stand-in (GPU version: test_optimiser_objectives_match_reference)."""
     monkeypatch.setattr(rb.engine, "objective_host", _oracle_objective_host)
+    monkeypatch.setattr(rb.engine, "ObjectiveEvaluator", _OracleObjectiveEvaluator)
     g = load_golden("objective_arim.npz")
     n, i, o, train = (int(v) for v in g["obj_meta"])
     env = rb.qnewton.LBFGS(n, i, o, noise=0.05, opt_train_size=train, opt_test_size=200)
