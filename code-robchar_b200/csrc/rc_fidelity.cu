@@ -199,7 +199,11 @@ cudaError_t launch_fidelity(const FidArgs& a, cudaStream_t st) {
     int sm = device_sm_count();
     if (a.amps)   // complex amplitudes (real symmetric model only): the general-N kernel, any chain length
         return a.replay ? launch_smem<MODEL_REAL2, true, true>(a, sm, st) : launch_smem<MODEL_REAL2, false, true>(a, sm, st);
-    if (a.N <= reg_crossover()) return reg_table[a.N](a, sm, st);
+    if (a.N <= reg_crossover()) {
+        FidArgs ar = a;
+        ar.respec = respec_counter_device();
+        return reg_table[a.N](ar, sm, st);
+    }
     const bool replay = a.replay != nullptr;
     if (a.model == MODEL_COMPLEX3)
         return replay ? launch_smem<MODEL_COMPLEX3, true>(a, sm, st) : launch_smem<MODEL_COMPLEX3, false>(a, sm, st);
@@ -246,8 +250,11 @@ static cudaError_t launch_fused_smem(const FusedArgs& g0, int sm_count, cudaStre
 
 cudaError_t launch_fused(const FusedArgs& g, cudaStream_t st) {
     int sm = device_sm_count();
-    if (g.f.N <= reg_crossover())
-        return fused_table[g.f.N](g, fused_reg_threads(g.f.N, g.f.replay != nullptr, g.f.B), sm, st);
+    if (g.f.N <= reg_crossover()) {
+        FusedArgs gr = g;
+        gr.f.respec = respec_counter_device();
+        return fused_table[g.f.N](gr, fused_reg_threads(g.f.N, g.f.replay != nullptr, g.f.B), sm, st);
+    }
     const bool replay = g.f.replay != nullptr;
     if (!replay)
         return g.f.model == MODEL_COMPLEX3 ? launch_fused_smem_warp<MODEL_COMPLEX3>(g, sm, st)

@@ -40,6 +40,22 @@ struct FidArgs {
 
 __host__ __device__ constexpr int draws_per_site(int model) { return model == MODEL_COMPLEX3 ? 3 : 2; }
 
+// Algorithm of the register-resident family (N <= 8): 0 = QL accumulating the in / out eigenvector rows (default),
+// 1 = eigenvalues + spectral weights (rc_spectral.cuh, amplitude_reg_spectral) with the former as in-line
+// recomputation.  Measured on B200 (round 2, kernel only, 2.0e7 evaluations): the spectral variant LOSES at every
+// short chain — N=4 10.2e9 vs 11.0e9, N=5 7.14 vs 7.54, N=6 5.37 vs 5.70, N=7 4.18 vs 4.29, N=8 3.40 vs 3.41
+// evals/s: below N ~ 10 the N(N-1) weight products and the per-eigenvalue reciprocal / error estimate (kept as
+// loops to protect the instruction cache) cost more than the 8 FP64 per rotation they save, and the footprint
+// argument of the shared-memory family does not apply to registers.  Kept for tuning builds only.
+#ifndef RC_REG_SPECTRAL
+#define RC_REG_SPECTRAL 0
+#endif
+// Doubles of the private shared-memory row of one lane in the register kernels: the K normals of the evaluation,
+// reused as eigensolver scratch (2N for the eigenvector solver, 3N - 1 for the spectral one); odd => conflict-free.
+__host__ __device__ constexpr int reg_row_doubles(int model, int n) {
+    return ((draws_per_site(model) * n > 3 * n ? draws_per_site(model) * n : 3 * n)) | 1;
+}
+
 // Heisenberg / Z diagonal of qnewton.py:148-150 for the open chain: t_i = (N-1)/2 - deg_i.
 RC_HD double zz_diag(int i, int n) { return 0.5 * (n - 1) - ((i == 0 || i == n - 1) ? 1.0 : 2.0); }
 
@@ -107,9 +123,8 @@ __device__ __forceinline__ void load_zig_table(const ZigEntry* __restrict__ g, Z
 }
 
 // Coalesced staging of `nvalid` consecutive replay rows (K doubles each) into padded shared rows.
-template <int K>
+template <int K, int KP>
 __device__ __forceinline__ void stage_replay_rows(const double* __restrict__ src, int nvalid, double* stage) {
-    constexpr int KP = K | 1;
     __syncthreads();
     for (int idx = threadIdx.x; idx < nvalid * K; idx += blockDim.x) {
         int row = idx / K, j = idx - row * K;
@@ -119,8 +134,8 @@ __device__ __forceinline__ void stage_replay_rows(const double* __restrict__ src
 }
 
 // One evaluation, register resident.  `row` = this lane's private shared-memory row (K|1 doubles):
-// holds the standard normals on entry (staged replay or Philox) and is reused as the eigenvalue /
-// weight scratch of the eigensolver (2N <= K doubles).
+// holds the standard normals on entry (staged replay or Philox) and is reused as the scratch of the
+// eigensolver (reg_row_doubles).
 template <int N, int MODEL, bool REPLAY>
 __device__ __forceinline__ double eval_reg(const FidArgs& a, long long s, long long c, long long b, double* row,
                                            const ZigEntry* kw) {
@@ -133,7 +148,13 @@ __device__ __forceinline__ double eval_reg(const FidArgs& a, long long s, long l
     double d[N], ee[N];
     build_tridiagonal<N, MODEL>(xr, sigma, a.zz, [&](int j) { return row[j]; }, d, ee);
     int fail = 0;
+#if RC_REG_SPECTRAL
+    int recomputed = 0;
+    double f = fidelity_reg_spectral<N>(d, ee, a.in, a.out, fabs(xr[N]), row, 1, &fail, &recomputed);
+    if (recomputed && a.respec) atomicAdd(a.respec, 1ull);
+#else
     double f = fidelity_reg_compact<N>(d, ee, a.in, a.out, fabs(xr[N]), row, 1, &fail);
+#endif
     if (fail && a.nonconv) atomicAdd(a.nonconv, 1ull);
     return f;
 }
@@ -169,7 +190,7 @@ constexpr int SMEM_FUSED_MAX_THREADS = 512;   // ... and of its fused-statistics
 template <int N, int MODEL, bool REPLAY>
 __global__ void __launch_bounds__(reg_cta_threads(N, REPLAY), reg_cta_min_blocks(N, REPLAY)) fidelity_reg_kernel(FidArgs a) {
     constexpr int K = draws_per_site(MODEL) * N;
-    constexpr int KP = K | 1;
+    constexpr int KP = reg_row_doubles(MODEL, N);
     extern __shared__ __align__(16) double smem_raw[];
     // Philox mode: [ziggurat table 16 KB][one row per lane]; replay mode: rows only
     const ZigEntry* kw = reinterpret_cast<const ZigEntry*>(smem_raw);
@@ -182,7 +203,7 @@ __global__ void __launch_bounds__(reg_cta_threads(N, REPLAY), reg_cta_min_blocks
         const long long e = e0 + threadIdx.x;
         if (REPLAY) {
             long long nvalid = total - e0 < (long long)blockDim.x ? total - e0 : (long long)blockDim.x;
-            stage_replay_rows<K>(a.replay + e0 * K, (int)nvalid, stage);
+            stage_replay_rows<K, KP>(a.replay + e0 * K, (int)nvalid, stage);
         }
 #if RC_TILE_SYNC
         if (!REPLAY) __syncthreads();   // keeps the CTA's warps in the same phase of the code
@@ -370,7 +391,7 @@ __device__ __forceinline__ void warp_acc_finish(const double* __restrict__ wacc,
 template <int N, int MODEL>
 __global__ void __launch_bounds__(reg_cta_threads(N, false), reg_cta_min_blocks(N, false)) fidelity_stats_reg_warp_kernel(FusedArgs g) {
     constexpr int K = draws_per_site(MODEL) * N;
-    constexpr int KP = K | 1;
+    constexpr int KP = reg_row_doubles(MODEL, N);
     extern __shared__ __align__(16) double smem_raw[];
     const FidArgs& a = g.f;
     const ZigEntry* kw = reinterpret_cast<const ZigEntry*>(smem_raw);
@@ -407,7 +428,7 @@ __global__ void __launch_bounds__(reg_cta_threads(N, false), reg_cta_min_blocks(
 template <int N, int MODEL, bool REPLAY>
 __global__ void __launch_bounds__(reg_cta_threads(N, REPLAY), reg_cta_min_blocks(N, REPLAY)) fidelity_stats_reg_kernel(FusedArgs g) {
     constexpr int K = draws_per_site(MODEL) * N;
-    constexpr int KP = K | 1;
+    constexpr int KP = reg_row_doubles(MODEL, N);
     extern __shared__ __align__(16) double smem_raw[];
     __shared__ double scratch[MAX_CTA_WARPS * PART_DOUBLES];
     const FidArgs& a = g.f;
@@ -428,7 +449,7 @@ __global__ void __launch_bounds__(reg_cta_threads(N, REPLAY), reg_cta_min_blocks
             const long long b = bt + threadIdx.x;
             if (REPLAY) {
                 long long nvalid = b1 - bt < (long long)blockDim.x ? b1 - bt : (long long)blockDim.x;
-                stage_replay_rows<K>(a.replay + (seg * a.B + bt) * K, (int)nvalid, stage);
+                stage_replay_rows<K, KP>(a.replay + (seg * a.B + bt) * K, (int)nvalid, stage);
             }
             if (b < b1) {
                 double f = eval_reg<N, MODEL, REPLAY>(a, s, c, b, stage + threadIdx.x * KP, kw);

@@ -14,10 +14,9 @@ namespace rc {
 template <int MODEL, bool REPLAY>
 static cudaError_t launch_reg(const FidArgs& a, int sm_count, cudaStream_t st) {
     constexpr int N = RC_NSPIN;
-    constexpr int K = draws_per_site(MODEL) * N;
     const int threads = reg_threads_runtime(N, REPLAY);
     // one private row per lane (+ the ziggurat fast-path table in Philox mode)
-    size_t smem = (size_t)threads * (K | 1) * sizeof(double) + (REPLAY ? 0 : sizeof(ZigEntry) * ZIG_LAYERS);
+    size_t smem = (size_t)threads * reg_row_doubles(MODEL, N) * sizeof(double) + (REPLAY ? 0 : sizeof(ZigEntry) * ZIG_LAYERS);
     auto kern = fidelity_reg_kernel<N, MODEL, REPLAY>;
     if (const char* e = getenv("RC_FID_SMEM_PAD")) smem += (size_t)atoi(e) * 1024;  // tuning: limits CTAs/SM
     cudaError_t err;
@@ -42,9 +41,8 @@ static cudaError_t launch_reg(const FidArgs& a, int sm_count, cudaStream_t st) {
 template <int MODEL>
 static cudaError_t launch_fused_reg_warp(const FusedArgs& g, int sm_count, cudaStream_t st) {
     constexpr int N = RC_NSPIN;
-    constexpr int K = draws_per_site(MODEL) * N;
     const int threads = reg_threads_runtime(N, false);
-    size_t smem = (size_t)threads * (K | 1) * sizeof(double) + sizeof(ZigEntry) * ZIG_LAYERS;
+    size_t smem = (size_t)threads * reg_row_doubles(MODEL, N) * sizeof(double) + sizeof(ZigEntry) * ZIG_LAYERS;
     auto kern = fidelity_stats_reg_warp_kernel<N, MODEL>;
     cudaError_t err;
     if (smem > 40 * 1024) {
@@ -68,8 +66,7 @@ static cudaError_t launch_fused_reg_warp(const FusedArgs& g, int sm_count, cudaS
 template <int MODEL, bool REPLAY>
 static cudaError_t launch_fused_reg(const FusedArgs& g, int threads, int sm_count, cudaStream_t st) {
     constexpr int N = RC_NSPIN;
-    constexpr int K = draws_per_site(MODEL) * N;
-    size_t smem = (size_t)threads * (K | 1) * sizeof(double) + (REPLAY ? 0 : sizeof(ZigEntry) * ZIG_LAYERS);
+    size_t smem = (size_t)threads * reg_row_doubles(MODEL, N) * sizeof(double) + (REPLAY ? 0 : sizeof(ZigEntry) * ZIG_LAYERS);
     auto kern = fidelity_stats_reg_kernel<N, MODEL, REPLAY>;
     cudaError_t err;
     if (smem > 40 * 1024) {

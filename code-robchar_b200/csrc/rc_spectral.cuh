@@ -241,4 +241,181 @@ RC_HD bool amplitude_spectral_strided(double* d, double* e, int ld, int n, doubl
 
 #undef RC_AT
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident variant for the short chains (N <= 8): same single-body compact QL as
+// fidelity_reg_compact (active block pinned at index 0, deflation = register shift), without the two
+// eigenvector rows — 21 instead of 29 FP64 per rotation slot, half the shift moves, 2N fewer live
+// registers — then the spectral weights from the eigenvalues parked in the lane's scratch row.
+// scratch: >= 3N doubles per lane, element k at scratch[k * sstride]:
+//   [0, N)     eigenvalues (written as they deflate)
+//   [N, 2N)    original diagonal, [2N, 3N-1) original couplings (for the minors and for the recomputation)
+// Returns false when the caller must recompute with fidelity_reg_compact (estimate rejected / QL failure).
+// ---------------------------------------------------------------------------------------------
+template <int N>
+struct QlSweepValues {
+    static RC_HD void run(double (&d)[N], double (&e)[N], int m, double dm, int mend, double tiny, int& rmin) {
+        double g = wilkinson_g(d[0], d[1], e[0], dm);
+        double r;
+        double s = 1.0, c = 1.0, p = 0.0;
+#pragma unroll
+        for (int i = N - 2; i >= 0; --i) {
+            if (i < m) {
+                const double f = s * e[i];
+                const double b = c * e[i];
+                const double h = fma(f, f, fma(g, g, tiny));
+                const double rinv = rc_rsqrt(h);
+                r = h * rinv;
+                e[i + 1] = r;
+                rmin = hi_word(r) < rmin ? hi_word(r) : rmin;
+                s = f * rinv;
+                c = g * rinv;
+                g = d[i + 1] - p;
+                r = fma(d[i] - g, s, (2.0 * c) * b);
+                p = s * r;
+                d[i + 1] = g + p;
+                g = c * r - b;
+            }
+        }
+        d[0] -= p;
+        e[0] = g;
+        if (m != mend) {
+#pragma unroll
+            for (int i = 1; i < N; ++i)
+                if (i == m) e[i] = 0.0;
+        }
+    }
+};
+
+template <int N>
+RC_HD bool amplitude_reg_spectral(double (&d)[N], double (&e)[N], int in, int out, double T, double* scratch, int sstride,
+                                  double& re_out, double& im_out) {
+#define RC_S(k) scratch[(size_t)(k) * sstride]
+    double anorm = 0.0, chk = T;
+    e[N - 1] = 0.0;
+    const int a = in < out ? in : out, b = in < out ? out : in;
+    double pb = 1.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        anorm = fmax(anorm, fabs(d[k]) + fabs(e[k]));
+        chk += d[k] + e[k];
+        RC_S(N + k) = d[k];
+        if (k < N - 1) {
+            RC_S(2 * N + k) = e[k];
+            pb *= (k >= a && k < b) ? e[k] : 1.0;
+        }
+    }
+    re_out = NAN; im_out = NAN;
+    if (!(fabs(chk) <= DBL_MAX)) return true;     // NaN / Inf controller or draw (mcsim.py:369-374)
+    const double tol = DBL_EPSILON * anorm;
+    const int tolhi = threshold_hi(tol);
+    const double tiny = fmin(tol, 1e-280);
+    int nact = N, ndone = 0, it = 0, rmin = 0;
+    while (nact > 1 && it <= QL_MAX_SWEEPS) {
+        if (negligible_hi(e[0], tolhi)) {
+            RC_S(ndone) = d[0];
+            ++ndone; --nact; it = 0;
+#pragma unroll
+            for (int i = 0; i < N - 1; ++i) { d[i] = d[i + 1]; e[i] = e[i + 1]; }
+        }
+        if (nact > 1 && !negligible_hi(e[0], tolhi)) {
+            int m = nact - 1;
+            bool split = false;
+            if (rmin < tolhi) {
+#pragma unroll
+                for (int i = N - 2; i >= 1; --i)
+                    if (i < nact - 1 && negligible_hi(e[i], tolhi)) m = i;
+                split = m != nact - 1;
+            }
+            double dm = d[N - 1];
+#pragma unroll
+            for (int i = N - 2; i >= 1; --i)
+                if (i == m) dm = d[i];
+            ++it;
+            rmin = 0x7fffffff;
+            QlSweepValues<N>::run(d, e, m, dm, nact - 1, tiny, rmin);
+            if (split) rmin = 0;
+        }
+    }
+    if (nact > 1) return false;
+    RC_S(ndone) = d[0];
+    // weights: loops, not unrolled (the hot code of the register kernels has to stay inside the instruction cache)
+    const double cgap = (double)(N - 1) * 4.0 * DBL_EPSILON * anorm;
+    const int na = a, nb = N - 1 - b;
+    double re = 0.0, im = 0.0, est = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = 0; k < N; ++k) {
+        const double lk = RC_S(k);
+        double P0 = 1.0, P1 = 1.0;
+        int mh = 0x7fffffff;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < N; ++j) {
+            const double df = lk - RC_S(j);
+            const bool self = j == k;
+            const int h = self ? 0x7fffffff : (hi_word(df) & 0x7fffffff);
+            mh = h < mh ? h : mh;
+            const double fct = self ? 1.0 : df;
+            if (j & 1) P1 *= fct; else P0 *= fct;
+        }
+        const double Pk = P0 * P1;
+        double num = pb, mag = fabs(pb);
+        if (na > 0) {
+            double p0 = 1.0, p1 = lk - RC_S(N), a0 = 1.0, a1 = fabs(p1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int j = 1; j < na; ++j) {
+                const double x = lk - RC_S(N + j), b2 = RC_S(2 * N + j - 1) * RC_S(2 * N + j - 1);
+                const double t = fma(x, p1, -(b2 * p0)), at = fma(fabs(x), a1, b2 * a0);
+                p0 = p1; p1 = t; a0 = a1; a1 = at;
+            }
+            num *= p1; mag *= a1;
+        }
+        if (nb > 0) {
+            double p0 = 1.0, p1 = lk - RC_S(N + N - 1), a0 = 1.0, a1 = fabs(p1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int j = N - 2; j > b; --j) {
+                const double x = lk - RC_S(N + j), b2 = RC_S(2 * N + j) * RC_S(2 * N + j);
+                const double t = fma(x, p1, -(b2 * p0)), at = fma(fabs(x), a1, b2 * a0);
+                p0 = p1; p1 = t; a0 = a1; a1 = at;
+            }
+            num *= p1; mag *= a1;
+        }
+        const double y = rc_rcp_full(Pk);
+        double w = num * y;
+        w = fma(fma(-w, Pk, num), y, w);
+        est = fma(fabs(w) * cgap, rc_rcp_seed(hi_as_double(mh)), est);
+        est = fma(8.0 * DBL_EPSILON * mag, fabs(y), est);
+        double sn, cs;
+        rc_sincos_tab(lk * T, &sn, &cs);
+        re = fma(w, cs, re);
+        im = fma(-w, sn, im);
+    }
+    re_out = re; im_out = im;
+    return est <= SPEC_EST_THR;
+#undef RC_S
+}
+
+// Fidelity with the in-line recomputation: d / e are restored from the scratch row and handed to the
+// eigenvector-accumulating solver when the spectral result is rejected.
+template <int N>
+RC_HD double fidelity_reg_spectral(double (&d)[N], double (&e)[N], int in, int out, double T, double* scratch, int sstride,
+                                   int* fail, int* recomputed) {
+    double re, im;
+    *fail = 0;
+    if (amplitude_reg_spectral<N>(d, e, in, out, T, scratch, sstride, re, im)) return fma(re, re, im * im);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        d[k] = scratch[(size_t)(N + k) * sstride];
+        e[k] = k < N - 1 ? scratch[(size_t)(2 * N + k) * sstride] : 0.0;
+    }
+    *recomputed = 1;
+    return fidelity_reg_compact<N>(d, e, in, out, T, scratch, sstride, fail);
+}
+
 }  // namespace rc

@@ -11,11 +11,43 @@
 #include "rc_spectral.cuh"
 using namespace rc;
 
+template <int N>
+static void run_reg(FILE* fi, int in, int out, int count) {
+    std::vector<double> buf(2 * N);
+    double maxdiff = 0;
+    long nre = 0;
+    for (int k = 0; k < count; ++k) {
+        if (fread(buf.data(), sizeof(double), 2 * N, fi) != (size_t)(2 * N)) exit(1);
+        double d[N], e[N], d2[N], e2[N], scr[3 * N], scr2[3 * N];
+        for (int i = 0; i < N; ++i) { d[i] = d2[i] = buf[i]; e[i] = e2[i] = i < N - 1 ? buf[N + i] : 0.0; }
+        const double T = buf[2 * N - 1];
+        int fail = 0, re = 0;
+        const double f = fidelity_reg_spectral<N>(d, e, in, out, T, scr, 1, &fail, &re);
+        int fail2 = 0;
+        const double fref = fidelity_reg_compact<N>(d2, e2, in, out, T, scr2, 1, &fail2);
+        nre += re;
+        const double diff = fabs(f - fref);
+        if (!(diff <= maxdiff)) maxdiff = diff;
+    }
+    printf("REG N=%d %d->%d count=%d maxdiff=%.3e recomputed=%.5f\n", N, in, out, count, maxdiff, (double)nre / count);
+}
+
 int main(int argc, char** argv) {
     FILE* fi = fopen(argv[1], "rb");
     int hdr[4];
     if (!fi || fread(hdr, sizeof(int), 4, fi) != 4) return 1;
     const int N = hdr[0], in = hdr[1], out = hdr[2], count = hdr[3];
+    if (argc > 2 && !strcmp(argv[2], "reg")) {
+        switch (N) {
+            case 4: run_reg<4>(fi, in, out, count); break;
+            case 5: run_reg<5>(fi, in, out, count); break;
+            case 6: run_reg<6>(fi, in, out, count); break;
+            case 7: run_reg<7>(fi, in, out, count); break;
+            case 8: run_reg<8>(fi, in, out, count); break;
+            default: fprintf(stderr, "reg variant: N = 4..8\n"); return 2;
+        }
+        return 0;
+    }
     std::vector<double> buf(2 * N);
     double maxdiff = 0, maxdiff_all = 0;
     long nfallback = 0, nbad = 0;
