@@ -338,7 +338,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    launches0 = eng.LAUNCHES
+    launches0 = eng.launch_count()
     barrier()
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_end = torch.cuda.Event(enable_timing=True)
@@ -354,7 +354,7 @@ def run_ours(args):
     ms = marks[0].elapsed_time(t_end)
     step_ms = [marks[k].elapsed_time(marks[k + 1]) for k in range(args.steps)]
     tail_ms = marks[args.steps].elapsed_time(t_end)
-    launches = eng.LAUNCHES - launches0
+    launches = eng.launch_count() - launches0
     fid_ms = float(np.mean([a.elapsed_time(b) for a, b in fid_events])) if fid_events else None
 
     # ---- e2e: host buffers through the public API, copies and the exchange inside the timed region ------------

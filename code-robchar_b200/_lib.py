@@ -34,6 +34,7 @@ _i64, _i32, _u64, _f64, _vp, _sz = C.c_int64, C.c_int, C.c_uint64, C.c_double, C
 _SIGNATURES = {
     "rc_version": (C.c_int, []),
     "rc_last_error": (C.c_char_p, []),
+    "rc_launch_count": (C.c_ulonglong, []),
     "rc_device_info": (C.c_int, [_vp, _vp, _vp]),
     "rc_fidelity_mc": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64, _vp, _vp,
                                  _vp, _vp]),

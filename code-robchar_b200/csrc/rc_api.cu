@@ -92,7 +92,7 @@ extern "C" int rc_fp64_peak_tflops(double* tflops, void* stream) {
     double best = 0.0;
     for (int rep = 0; rep < 4; ++rep) {
         RC_CUDA_TRY(cudaEventRecord(e0, st));
-        dfma_peak_kernel<<<blocks, threads, 0, st>>>(out.as<double>(), iters, 0.999999, 1e-7);
+        dfma_peak_kernel<<<blocks, threads, 0, st>>>(out.as<double>(), iters, 0.999999, 1e-7); rc::note_launch();
         RC_CUDA_TRY(cudaEventRecord(e1, st));
         RC_CUDA_TRY(cudaEventSynchronize(e1));
         float ms = 0.f;

@@ -10,6 +10,7 @@ namespace rc {
 char* last_error_buffer();            // thread local, 512 bytes
 int set_error(int code, const char* fmt, ...);
 int device_sm_count();                // SMs of the current device (cached per device)
+void note_launch();                   // one kernel of this library was launched (process-wide counter, rc_launch_count)
 // rc_fidelity.cu: shared implementation of rc_fidelity_mc, also launched per sigma chunk by the host sweep
 int fidelity_mc_impl(const char* who, const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
                      const double* sigma_dev, int S, int64_t B, int model, int zz, uint64_t seed, int64_t c_offset,

@@ -178,7 +178,7 @@ extern "C" int rc_expm_batch(const double* A_dev, int64_t batch, int M, double* 
     if (occ < 1) occ = 1;
     long long grid = (long long)device_sm_count() * occ;
     if (grid > batch) grid = batch;
-    expm_pade13_kernel<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>((const cplx*)A_dev, batch, M, (cplx*)out_dev);
+    expm_pade13_kernel<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>((const cplx*)A_dev, batch, M, (cplx*)out_dev); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }

@@ -17,6 +17,10 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+static unsigned long long g_launches = 0;
+void note_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+unsigned long long launches_so_far() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int device_sm_count() {
     static int cached[64] = {0};
     int dev = 0;
@@ -162,6 +166,7 @@ static cudaError_t launch_persistent(Kern kern, int threads, size_t smem, long l
     if (grid > need_blocks) grid = need_blocks;
     if (grid < 1) return cudaSuccess;
     void* args[1] = {const_cast<void*>(arg)};
+    note_launch();
     return cudaLaunchKernel((const void*)kern, dim3((unsigned)grid), dim3(threads), args, smem, st);
 }
 
@@ -428,6 +433,8 @@ __global__ void philox_normals_kernel(long long C, long long B, int S, int n, in
 using namespace rc;
 
 extern "C" int rc_version(void) { return 200; }
+namespace rc { unsigned long long launches_so_far(); }
+extern "C" unsigned long long rc_launch_count(void) { return rc::launches_so_far(); }
 
 // Name of the evolution kernel the launcher picks for a sweep of this shape (bench.py labels its roofline with it).
 extern "C" int rc_evolution_kernel_name(int nspin, int replay, int fused, char* buf, size_t buf_bytes) {
@@ -526,7 +533,7 @@ extern "C" int rc_philox_normals(int64_t C, int nspin, int S, int64_t B, int mod
     RC_CUDA_TRY(zig_tables_device(&zig));
     philox_normals_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(C, B, S, nspin, model, (uint32_t)seed,
                                                                               (uint32_t)(seed >> 32), c_offset, b_offset,
-                                                                              zig, normals_dev);
+                                                                              zig, normals_dev); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }
@@ -574,7 +581,7 @@ extern "C" int rc_fidelity_stats(const double* ctrl_dev, int64_t C, int nspin, i
     RC_CUDA_TRY(launch_fused(g, st));
     long long blocks = (nseg + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    fused_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(g.partials, nseg, g.nchunks, B, dkw_eps, stats_dev);
+    fused_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(g.partials, nseg, g.nchunks, B, dkw_eps, stats_dev); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }
@@ -642,7 +649,7 @@ extern "C" int rc_fidelity_stats_blocks(const double* ctrl_dev, int64_t C, int n
         RC_CUDA_TRY(launch_fused(g, st));
     }
     block_merge_kernel<<<(unsigned)blocks, 256, 0, st>>>(g.partials, nseg, g.nchunks, b_lo / chunk, nchunks_total, v_lo, v_hi,
-                                                         blocks_dev);
+                                                         blocks_dev); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }
@@ -654,7 +661,7 @@ extern "C" int rc_stats_from_blocks(const double* blocks_dev, int64_t nseg, int6
     if (!blocks_dev || !stats_dev) return set_error(RC_ERR_NULL, "rc_stats_from_blocks: null pointer");
     long long blocks = (nseg + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    blocks_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(blocks_dev, nseg, B, dkw_eps, stats_dev);
+    blocks_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(blocks_dev, nseg, B, dkw_eps, stats_dev); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }

@@ -53,7 +53,7 @@ __host__ __device__ constexpr int draws_per_site(int model) { return model == MO
 // Doubles of the private shared-memory row of one lane in the register kernels: the K normals of the evaluation,
 // reused as eigensolver scratch (2N for the eigenvector solver, 3N - 1 for the spectral one); odd => conflict-free.
 __host__ __device__ constexpr int reg_row_doubles(int model, int n) {
-    return ((draws_per_site(model) * n > 3 * n ? draws_per_site(model) * n : 3 * n)) | 1;
+    return (RC_REG_SPECTRAL && draws_per_site(model) * n < 3 * n ? 3 * n : draws_per_site(model) * n) | 1;
 }
 
 // Heisenberg / Z diagonal of qnewton.py:148-150 for the open chain: t_i = (N-1)/2 - deg_i.
@@ -769,6 +769,8 @@ __global__ void __launch_bounds__(SMEM_FUSED_MAX_THREADS) fidelity_stats_smem_ke
     }
 }
 #endif  // __CUDACC__
+
+void note_launch();   // rc_fidelity.cu: one kernel of this library was launched (rc_launch_count)
 
 // launchers implemented in rc_fidelity_n.cu (one translation unit per N) / rc_fidelity.cu
 typedef cudaError_t (*fid_launch_fn)(const FidArgs&, int sm_count, cudaStream_t);

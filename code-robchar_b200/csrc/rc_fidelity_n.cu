@@ -33,7 +33,7 @@ static cudaError_t launch_reg(const FidArgs& a, int sm_count, cudaStream_t st) {
     long long grid = (long long)sm_count * occ;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, threads, smem, st>>>(a);
+    kern<<<(unsigned)grid, threads, smem, st>>>(a); rc::note_launch();
     return cudaGetLastError();
 }
 
@@ -59,7 +59,7 @@ static cudaError_t launch_fused_reg_warp(const FusedArgs& g, int sm_count, cudaS
     const long long need = (nitems + wpc - 1) / wpc;
     if (grid > need) grid = need;
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, threads, smem, st>>>(g);
+    kern<<<(unsigned)grid, threads, smem, st>>>(g); rc::note_launch();
     return cudaGetLastError();
 }
 
@@ -81,7 +81,7 @@ static cudaError_t launch_fused_reg(const FusedArgs& g, int threads, int sm_coun
     long long grid = (long long)sm_count * occ;
     if (grid > nitems) grid = nitems;
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, threads, smem, st>>>(g);
+    kern<<<(unsigned)grid, threads, smem, st>>>(g); rc::note_launch();
     return cudaGetLastError();
 }
 

@@ -198,7 +198,7 @@ extern "C" int rc_fidelity_grad(const double* x_dev, int64_t C, int nspin, int i
     long long blocks = (C + GRAD_WARPS - 1) / GRAD_WARPS;
     const long long cap = (long long)device_sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    fidelity_grad_kernel<<<(unsigned)blocks, 32 * GRAD_WARPS, smem, (cudaStream_t)stream>>>(a);
+    fidelity_grad_kernel<<<(unsigned)blocks, 32 * GRAD_WARPS, smem, (cudaStream_t)stream>>>(a); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }

@@ -285,6 +285,7 @@ static int objective_host_fast(const double* x_host, int nspin, int inspin, int 
     }
     if (mi == 0) objective_kernel<MODEL_COMPLEX3><<<1, threads, smem, st>>>(q);
     else objective_kernel<MODEL_REAL2><<<1, threads, smem, st>>>(q);
+    rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     // spin on the mapped flag; fall back to a stream synchronisation (which also surfaces launch failures) after 2 s
     const double t0 = now_s();

@@ -118,7 +118,7 @@ extern "C" int rc_peer_signal(void* const* peer_flags, int world, int rank, uint
         if (!peer_flags[k]) return set_error(RC_ERR_NULL, "rc_peer_signal: null flag array %d", k);
         f.p[k] = (unsigned long long*)peer_flags[k];
     }
-    peer_signal_kernel<<<1, PEER_MAX_WORLD, 0, (cudaStream_t)stream>>>(f, world, rank, seq);
+    peer_signal_kernel<<<1, PEER_MAX_WORLD, 0, (cudaStream_t)stream>>>(f, world, rank, seq); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }
@@ -130,7 +130,7 @@ extern "C" int rc_peer_wait(const void* local_flags, int world, uint64_t seq, do
     if (!(timeout_s > 0.0)) timeout_s = 10.0;
     peer_wait_kernel<<<1, PEER_MAX_WORLD, 0, (cudaStream_t)stream>>>((const unsigned long long*)local_flags, world, seq,
                                                                    (unsigned long long)(timeout_s * 1e9),
-                                                                   (unsigned long long*)timed_out_dev);
+                                                                   (unsigned long long*)timed_out_dev); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }

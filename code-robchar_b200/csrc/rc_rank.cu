@@ -140,10 +140,10 @@ static cudaError_t launch_clustered_walk(const double* values, const int* perm, 
         if (err != cudaSuccess) return err;
         long long blocks = (R + CW_WARPS - 1) / CW_WARPS;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        clustered_walk_warp_kernel<<<(unsigned)blocks, CW_WARPS * 32, smem, st>>>(values, perm, R, (int)n, alpha, r_fixed, out);
+        clustered_walk_warp_kernel<<<(unsigned)blocks, CW_WARPS * 32, smem, st>>>(values, perm, R, (int)n, alpha, r_fixed, out); rc::note_launch();
     } else {
         const long long blocks = (R + 31) / 32;
-        clustered_walk_kernel<<<(unsigned)blocks, 32, 0, st>>>(values, perm, R, n, alpha, r_fixed, out);
+        clustered_walk_kernel<<<(unsigned)blocks, 32, 0, st>>>(values, perm, R, n, alpha, r_fixed, out); rc::note_launch();
     }
     return cudaGetLastError();
 }
@@ -334,7 +334,7 @@ static int argsort_rows(const double* values, long long R, long long n, void* ws
         if (smem > 40 * 1024)
             RC_CUDA_TRY(cudaFuncSetAttribute(argsort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         long long grid = R < (long long)sm * 8 ? R : (long long)sm * 8;
-        argsort_small_kernel<<<(unsigned)grid, threads, smem, st>>>(values, R, (int)n, P, perm);
+        argsort_small_kernel<<<(unsigned)grid, threads, smem, st>>>(values, R, (int)n, P, perm); rc::note_launch();
         RC_CUDA_TRY(cudaGetLastError());
         return RC_OK;
     }
@@ -345,7 +345,7 @@ static int argsort_rows(const double* values, long long R, long long n, void* ws
     int* i_in = (int*)p; p += align256((size_t)R * n * 4);
     size_t tb = rank_cub_temp(R, n);
     if ((size_t)(p - (char*)ws) + tb > ws_bytes) return set_error(RC_ERR_WORKSPACE, "rank: workspace too small");
-    build_keys_kernel<<<sm * 8, 256, 0, st>>>(values, R * n, (int)n, k_in, i_in);
+    build_keys_kernel<<<sm * 8, 256, 0, st>>>(values, R * n, (int)n, k_in, i_in); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     auto off = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), RowOffset{(int)n});
     RC_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortPairs(p, tb, k_in, k_out, i_in, perm, (int)(R * n), (int)R, off, off + 1,
@@ -380,7 +380,7 @@ extern "C" int rc_ranks(const double* values_dev, int64_t R, int64_t n, int64_t*
     long long total = R * n;
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    scatter_ranks_kernel<<<(unsigned)blocks, 256, 0, st>>>((const int*)workspace_dev, R, n, (long long*)ranks_dev);
+    scatter_ranks_kernel<<<(unsigned)blocks, 256, 0, st>>>((const int*)workspace_dev, R, n, (long long*)ranks_dev); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }
@@ -411,10 +411,10 @@ extern "C" int rc_kendall_tau_b_batched(const double* x_dev, const int64_t* y_de
     if (n >= 2) {
         dim3 grid((unsigned)((n + KT_THREADS - 1) / KT_THREADS), (unsigned)(Rx * Ry), (unsigned)G);
         kendall_count_kernel<<<grid, KT_THREADS, 0, st>>>(x_dev, Rx, (const long long*)y_dev, Ry, n,
-                                                         (unsigned long long*)counts_dev);
+                                                         (unsigned long long*)counts_dev); rc::note_launch();
         RC_CUDA_TRY(cudaGetLastError());
     }
-    kendall_finalize_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>((const unsigned long long*)counts_dev, np, n, tau_dev);
+    kendall_finalize_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>((const unsigned long long*)counts_dev, np, n, tau_dev); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }
@@ -462,11 +462,11 @@ extern "C" int rc_rank_consistency(const double* W_dev, int64_t S, int64_t G, in
     RC_CUDA_TRY(cudaMemsetAsync(mark, 0, (size_t)G * Cg, st));
     long long blocks = (G * k + 255) / 256;
     if (blocks > sm * 8) blocks = sm * 8;
-    mark_topk_kernel<<<(unsigned)blocks, 256, 0, st>>>((const int*)sortws, G, Cg, k, mark);
-    compact_topk_kernel<<<(unsigned)G, 256, 0, st>>>(mark, Cg, k, (long long*)sel_dev);
+    mark_topk_kernel<<<(unsigned)blocks, 256, 0, st>>>((const int*)sortws, G, Cg, k, mark); rc::note_launch();
+    compact_topk_kernel<<<(unsigned)G, 256, 0, st>>>(mark, Cg, k, (long long*)sel_dev); rc::note_launch();
     blocks = (G * S * k + 255) / 256;
     if (blocks > sm * 8) blocks = sm * 8;
-    gather_topk_kernel<<<(unsigned)blocks, 256, 0, st>>>(W_dev, S, G, Cg, k, (const long long*)sel_dev, Wsel_dev);
+    gather_topk_kernel<<<(unsigned)blocks, 256, 0, st>>>(W_dev, S, G, Cg, k, (const long long*)sel_dev, Wsel_dev); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     // 2. clustered ranks (radius alpha*(max-min) per row) and ordinal ranks + 1 of every selected row
     rcode = argsort_rows(Wsel_dev, G * S, k, sortws, ws_sort, st);
@@ -474,7 +474,7 @@ extern "C" int rc_rank_consistency(const double* W_dev, int64_t S, int64_t G, in
     RC_CUDA_TRY(launch_clustered_walk(Wsel_dev, (const int*)sortws, G * S, k, alpha, 0.0, cr, st));
     blocks = (G * S * k + 255) / 256;
     if (blocks > sm * 8) blocks = sm * 8;
-    scatter_ranks_kernel<<<(unsigned)blocks, 256, 0, st>>>((const int*)sortws, G * S, k, rk, 1);
+    scatter_ranks_kernel<<<(unsigned)blocks, 256, 0, st>>>((const int*)sortws, G * S, k, rk, 1); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     // 3. S x S Kendall tau-b per group
     return rc_kendall_tau_b_batched(cr, (const int64_t*)rk, G, S, S, k, tau_dev, counts, stream);
@@ -491,7 +491,7 @@ extern "C" int rc_arim_bootstrap(const double* rims_dev, int64_t R, int64_t k, i
         RC_CUDA_TRY(cudaFuncSetAttribute(arim_bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = R < (long long)device_sm_count() * 8 ? R : (long long)device_sm_count() * 8;
     arim_bootstrap_kernel<<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(rims_dev, R, (int)k, nboot, (uint32_t)seed,
-                                                                               (uint32_t)(seed >> 32), arim_dev, std_dev);
+                                                                               (uint32_t)(seed >> 32), arim_dev, std_dev); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }

@@ -433,7 +433,7 @@ static cudaError_t launch_stats_unsorted_warp(const double* fids, long long nseg
     long long grid = (long long)sm * occ;
     const long long need = (nseg + 7) / 8;
     if (grid > need) grid = need;
-    stats_unsorted_warp_kernel<E><<<(unsigned)grid, 256, 0, st>>>(fids, nseg, B, eps, stride, stats, illegal);
+    stats_unsorted_warp_kernel<E><<<(unsigned)grid, 256, 0, st>>>(fids, nseg, B, eps, stride, stats, illegal); rc::note_launch();
     return cudaGetLastError();
 }
 
@@ -447,7 +447,7 @@ int stats_unsorted_impl(const double* fids_dev, int64_t nseg, int64_t B, double 
     const int b = (int)(B <= 512 ? B : 0);
     if (B > 512) {
         long long grid = nseg < (long long)sm * 8 ? nseg : (long long)sm * 8;
-        stats_unsorted_block_kernel<<<(unsigned)grid, 256, 0, st>>>(fids_dev, nseg, B, dkw_eps, stat_stride, stats_dev, illegal_dev);
+        stats_unsorted_block_kernel<<<(unsigned)grid, 256, 0, st>>>(fids_dev, nseg, B, dkw_eps, stat_stride, stats_dev, illegal_dev); rc::note_launch();
         err = cudaGetLastError();
     } else if (b <= 32) err = launch_stats_unsorted_warp<1>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);
     else if (b <= 64) err = launch_stats_unsorted_warp<2>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);
@@ -468,7 +468,7 @@ static cudaError_t launch_sort_stats_warp(const double* fids, long long nseg, in
     long long grid = (long long)sm * occ;
     const long long need = (nseg + 3) / 4;
     if (grid > need) grid = need;
-    sort_stats_warp_kernel<E><<<(unsigned)grid, 128, 0, st>>>(fids, nseg, B, eps, stats, sorted_out, illegal);
+    sort_stats_warp_kernel<E><<<(unsigned)grid, 128, 0, st>>>(fids, nseg, B, eps, stats, sorted_out, illegal); rc::note_launch();
     return cudaGetLastError();
 }
 
@@ -587,7 +587,7 @@ extern "C" int rc_stats(const double* fids_dev, int64_t nseg, int64_t B, double 
         long long grid = (long long)sm * occ;
         if (grid > nseg) grid = nseg;
         sort_stats_small_kernel<<<(unsigned)grid, threads, smem, st>>>(fids_dev, nseg, (int)B, P, dkw_eps, stats_dev,
-                                                                        sorted_dev, illegal_dev);
+                                                                        sorted_dev, illegal_dev); rc::note_launch();
         RC_CUDA_TRY(cudaGetLastError());
         return RC_OK;
     }
@@ -606,7 +606,7 @@ extern "C" int rc_stats(const double* fids_dev, int64_t nseg, int64_t B, double 
         RC_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(tmp, tb, fids_dev + s0 * B, chunk, (int)(ns * B), (int)ns,
                                                             off, off + 1, 0, 64, st));
         long long grid = ns < (long long)sm * 4 ? ns : (long long)sm * 4;
-        stats_sorted_kernel<<<(unsigned)grid, 512, 0, st>>>(chunk, s0, ns, nseg, B, dkw_eps, stats_dev, illegal_dev);
+        stats_sorted_kernel<<<(unsigned)grid, 512, 0, st>>>(chunk, s0, ns, nseg, B, dkw_eps, stats_dev, illegal_dev); rc::note_launch();
         RC_CUDA_TRY(cudaGetLastError());
         if (sorted_dev)
             RC_CUDA_TRY(cudaMemcpyAsync(sorted_dev + s0 * B, chunk, (size_t)ns * B * sizeof(double),
@@ -653,7 +653,7 @@ extern "C" int rc_rim_p(const double* fids_dev, int64_t nseg, int64_t B, double 
     if (!fids_dev || !out_dev) return rc::set_error(RC_ERR_NULL, "rc_rim_p: null pointer");
     long long blocks = (nseg + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    rc::rim_p_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(fids_dev, nseg, B, p, out_dev, illegal_dev);
+    rc::rim_p_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(fids_dev, nseg, B, p, out_dev, illegal_dev); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
     return RC_OK;
 }

@@ -20,13 +20,14 @@ METRIC_NAMES = [METRIC_W, "Q th. 0.95", "Q th. 0.98", "std", "worst case fid"]
 STAT_KEYS = [m + s for m in METRIC_NAMES for s in ("", " upper", " lower")]
 
 
-# kernels launched by this process through the C-ABI (bench.py reports it as gpu_launches)
-LAUNCHES = 0
+def launch_count() -> int:
+    """Kernels of librobchar_b200.so launched by this process so far, counted at the launch sites inside the library
+    (rc_launch_count; bench.py reports the difference over its timed region as gpu_launches)."""
+    return int(lib().rc_launch_count())
 
 
 def _count(n: int) -> None:
-    global LAUNCHES
-    LAUNCHES += n
+    """(kept as a no-op: launches are counted inside the library)"""
 
 
 def require_cuda() -> torch.device:

@@ -46,6 +46,9 @@ extern "C" {
 
 int rc_version(void);
 const char* rc_last_error(void);
+/* Number of kernels of THIS library launched by the process so far (counted at the launch sites; library kernels
+ * such as the CUB segmented sort of the B > 4096 statistics path are not included). */
+unsigned long long rc_launch_count(void);
 /* SM count and compute capability of the current device. */
 int rc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -27,12 +27,16 @@ def rb():
     return robchar_b200
 
 
+NEAR_TIE_SWAPS = []      # (rows compared, rows whose device ranking differs from the reference's only by near ties)
+
+
 def assert_same_ranking_modulo_near_ties(dev_ranks, ref_values, tol=RIM_TOL):
     """Rankings from the device's own RIMs vs the reference's RIMs: identical except where the
     reference values are tied to within the RIM tolerance (duplicate / mirror-equivalent controllers
     give RIMs equal to ~1e-16, whose order is implementation-defined in the reference itself).
     Any such near-tie swap is checked explicitly, not hidden: the reference values taken in the
     device's order must be ascending to within `tol`."""
+    swapped = 0
     for r in range(ref_values.shape[0]):
         ref_rank = orc.get_ranks(ref_values[r])
         if np.array_equal(dev_ranks[r], ref_rank):
@@ -40,6 +44,9 @@ def assert_same_ranking_modulo_near_ties(dev_ranks, ref_values, tol=RIM_TOL):
         order = np.empty_like(dev_ranks[r])
         order[dev_ranks[r]] = np.arange(dev_ranks[r].size)
         assert np.all(np.diff(ref_values[r][order]) >= -tol), f"row {r}: ranking differs beyond near ties"
+        swapped += 1
+    NEAR_TIE_SWAPS.append((ref_values.shape[0], swapped))
+    print(f"[ranking] {ref_values.shape[0]} rows compared, {swapped} differ from the reference only by near ties (< {tol})")
 
 
 def nominal(rb, ctrl, n, i, o, **kw):
@@ -590,8 +597,8 @@ def test_full_size_properties_nspin7(rb):
     assert torch.equal(f, f2)                                           # deterministic
     assert bool(((f >= 0) & (f <= 1 + 1e-12)).all())
     assert bool((f[0] == f[0, :, :1]).all())                            # sigma = 0: all draws identical
-    sub = np.arange(0, C, 997)
-    assert np.abs(f[0, sub, 0].cpu().numpy() - orc.fidelity_batch(ctrl[sub], n, 0, 6)).max() < FID_TOL
+    # the whole sigma = 0 column (all 19 000 controllers) against the oracle's expm
+    assert np.abs(f[0, :, 0].cpu().numpy() - orc.fidelity_batch(ctrl, n, 0, 6)).max() < FID_TOL
     st = rb.engine.stats(f, eps)
     fe, ste = rb.engine.fidelity_mc_stats(ctrl, sig, B, n, 0, 6, dkw_eps=eps, seed=1)   # sort-free statistics
     assert torch.equal(fe, f)
