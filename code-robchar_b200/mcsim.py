@@ -1,9 +1,9 @@
 """Cachable Monte-Carlo simulation class with the reference's API; the sweep runs on the GPU.
 
 Mirrors upstream ``mcsim.py``: ``MCDataSim`` (:200-660) with the same constructor, attributes,
-file-name grammar and JSON layouts, the metric registry (:144-183) and the helpers ``get_cdf``,
-``get_supcdf``, ``vn_test`` (:42-123).  Plotting / TSNE parts are not part of the compute path and
-are omitted.
+file-name grammar and JSON layouts, the metric registry (:144-183) and the small helpers ``get_cdf``,
+``get_supcdf``, ``vn_test`` (:42-123, restated).  Plotting / TSNE parts and the controller-file merge
+utilities (:594-649) are not part of the compute path and are omitted.
 
 Differences that are deliberate and documented:
 * noise: by default drawn in-kernel with counter-based Philox (``seed``); ``rng_mode="numpy"``
@@ -46,43 +46,40 @@ def get_cdf(arrays):
 
 @check_numpytype
 def get_supcdf(cdf):
-    """mcsim.py:50-57."""
-    sup = np.zeros_like(cdf)
-    n = len(cdf)
-    for i in range(n):
-        sup[i] = sum(cdf[i:]) / (n - i)
-    return sup
+    """Tail averages of a cdf vector: out[i] = mean(cdf[i:]) (what mcsim.py:50-57 computes with a loop)."""
+    tail_sums = np.cumsum(cdf[::-1])[::-1]
+    return tail_sums / np.arange(cdf.size, 0, -1)
 
 
 @check_numpytype
 def vn_test(obs_v, alpha=0.95, verbose=True, bartels=True):
-    """Von Neumann successive-difference randomness test (mcsim.py:59-123)."""
-    from scipy.stats import norm
+    """Von Neumann ratio test of serial independence (same decision rule and return shape as mcsim.py:59-123):
+    statistic = mean squared successive difference / population variance, ~2 for independent samples.
+    bartels=True uses the fixed cut 1.1; otherwise the normal quantile at 1 - alpha with the ratio's exact mean
+    2n/(n-1) and variance 4 n^2 (n-2) / ((n+1)(n-1)^3)."""
     n = obs_v.size
     if n < 40:
         raise Exception("{} nobs are insufficient for the test.".format(n))
-    mean = 2 * n / (n - 1)
-    sigma = 4 * n * n * (n - 2) / ((n + 1) * pow((n - 1), 3))
-    sdiff = np.diff(obs_v)
-    sdiff = sdiff * sdiff
-    VN_statistic = sdiff.mean() / obs_v.var()
+    ratio = np.mean(np.square(obs_v[1:] - obs_v[:-1])) / np.var(obs_v)
     if bartels:
         if verbose:
-            print(VN_statistic)
-        return (True, VN_statistic) if VN_statistic > 1.1 else (False, VN_statistic)
-    phi = norm.ppf(1 - alpha, loc=mean, scale=np.sqrt(sigma))
-    return (True, phi) if VN_statistic > phi else (False, phi)
+            print(ratio)
+        return (bool(ratio > 1.1), ratio)
+    from scipy.stats import norm
+    centre = 2.0 * n / (n - 1)
+    spread = np.sqrt(4.0 * n * n * (n - 2) / ((n + 1) * (n - 1) ** 3))
+    cut = norm.ppf(1 - alpha, loc=centre, scale=spread)
+    return (bool(ratio > cut), cut)
 
 
 def ovlen(obj):
-    """mcsim.py:133-142."""
-    import pandas as pd
-    if isinstance(obj, (list, np.ndarray, pd.Series)):
-        return len(obj)
-    if isinstance(obj, dict):
-        return len(obj.keys())
+    """Number of entries of a container, 1 for a scalar (mcsim.py:133-142)."""
     if isinstance(obj, (int, float)):
         return 1
+    if isinstance(obj, dict):
+        return len(obj)
+    if hasattr(obj, "__len__") and not isinstance(obj, str):
+        return len(obj)
     raise TypeError("unknown data type encountered")
 
 
@@ -408,54 +405,16 @@ class MCDataSim:
         idx = np.ix_(np.ones(wd_data_c.shape[0], dtype=bool), filmask)
         return wd_data_c[idx], np.array(wd_data_u)[idx], np.array(wd_data_l)[idx]
 
-    def get_wd_data_c(self):
-        "mcsim.py:317-333"
-        noise_keys = list(self.controllers["ppo"].keys())
-        all_wd_data_c = []
-        for alg in range(len(noise_keys) + 1):
-            if alg == 11:
-                wd_data = self.get_metrics_dict(None, self.noises, algoname="lbfgs")["lbfgs"]
-            else:
-                wd_data = self.get_metrics_dict(noise_keys[alg], self.noises, algoname="ppo")["ppo"]
-            wd_data_c = np.array(wd_data[engine.METRIC_W])
-            if self.topk:
-                wd_data_c = wd_data_c[self.get_top_k_by_fid_idx(wd_data_c, self.topk)]
-            all_wd_data_c.append(wd_data_c)
-        return all_wd_data_c
-
-    @staticmethod
-    def sort_fids_by(fids: np.ndarray, by_metric: np.ndarray, best_k: int = 100):
-        return fids[np.argsort(by_metric, axis=-1, kind="stable")[:best_k]]
-
-    # ---- file utilities (mcsim.py:572-649) -----------------------------------------------------------
+    # ---- locating an experiment's files (mcsim.py:572-592) ---------------------------------------------
     def get_path(self, directory_exportable, of: str = "controllers"):
-        rootpath = self.global_experiments_directory + directory_exportable
-        if not os.path.exists(rootpath):
+        """Controller file of another experiment directory, or the list of its .mc / .mcm caches."""
+        if not os.path.exists(self.global_experiments_directory + directory_exportable):
             raise DirectoryDoesNotExistError(self.global_experiments_directory)
-        controller_dict_path = self.get_experiment_name(directory_exportable)()
-        if self.filemarker is not None:
-            controller_dict_path += self.filemarker
-        if not os.path.exists(controller_dict_path):
-            raise DirectoryDoesNotExistError(controller_dict_path)
+        stem = self.get_experiment_name(directory_exportable)() + (self.filemarker or "")
+        if not os.path.exists(stem):
+            raise DirectoryDoesNotExistError(stem)
         if of == "controllers":
-            return controller_dict_path
-        if of == "mcm":
-            return glob.glob(controller_dict_path + "**.mcm")
-        if of == "mc":
-            return glob.glob(controller_dict_path + "**.mc")
+            return stem
+        if of in ("mc", "mcm"):
+            return glob.glob(f"{stem}**.{of}")
         raise Exception("No such object type exists. Please specify a correct .description.")
-
-    def load_controllers_in_dir(self, directory_exportable):
-        return self.load_controllers(self.get_path(directory_exportable, of="controllers"))
-
-    def merge_controller_files(self, directory_exportable: str) -> None:
-        "file names must be identical but located in a different `directory_exportable` (mcsim.py:626-649)"
-        alt_controllers = self.load_controllers_in_dir(directory_exportable)
-        for algo in self.ctrlnames(alt_controllers):
-            if algo not in self.controllers:
-                self.controllers[algo] = alt_controllers[algo]
-            elif algo != "lbfgs":
-                for noise in list(alt_controllers[algo].keys()):
-                    if noise not in self.controllers[algo]:
-                        self.controllers[algo][noise] = alt_controllers[algo][noise]
-        json.dump(self.controllers, open(self.get_controller_name, "w"))
