@@ -67,6 +67,8 @@ _SIGNATURES = {
     "rc_clustered_ranks": (C.c_int, [_vp, _i64, _i64, _f64, _f64, _vp, _vp, _sz, _vp]),
     "rc_kendall_tau_b": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
     "rc_kendall_tau_b_batched": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "rc_kendall_large_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
+    "rc_kendall_tau_b_large": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "rc_rank_consistency_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "rc_rank_consistency": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _f64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rc_robustness_sweep_host": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64,

@@ -328,6 +328,8 @@ def kendall_tau_b(x, y) -> torch.Tensor:
     Ry = y2.shape[0]
     if y2.shape[1] != n:
         raise ValueError("x and y rows must have the same length")
+    if n > KENDALL_PAIRCOUNT_MAX_N:
+        return kendall_tau_b_batched(x2[None], y2[None])[0]
     tau = torch.empty((Rx, Ry), dtype=torch.float64, device=dev)
     counts = torch.empty((Rx, Ry, 4), dtype=torch.int64, device=dev)
     check(lib().rc_kendall_tau_b(_ptr(x2), Rx, _ptr(y2), Ry, n, _ptr(tau), _ptr(counts), _stream()))
@@ -335,8 +337,12 @@ def kendall_tau_b(x, y) -> torch.Tensor:
     return tau
 
 
-def kendall_tau_b_batched(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """x [G][Rx][n] double ranks, y [G][Ry][n] int64 ranks -> tau [G][Rx][Ry] (one launch for all groups)."""
+KENDALL_PAIRCOUNT_MAX_N = 4096     # above: rc_kendall_tau_b_large (O(n log^2 n)) instead of the O(n^2) pair count
+
+
+def kendall_tau_b_batched(x: torch.Tensor, y: torch.Tensor, force_large: bool = False) -> torch.Tensor:
+    """x [G][Rx][n] double ranks, y [G][Ry][n] int64 ranks -> tau [G][Rx][Ry] (one launch for all groups; long rank
+    vectors, n > 4096, take the sort + merge-pass path, bit-identical integer counts)."""
     dev = require_cuda()
     x = _f64(x, dev)
     y = y.to(device=dev, dtype=torch.int64).contiguous()
@@ -346,6 +352,13 @@ def kendall_tau_b_batched(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         raise ValueError("x and y must share group count and row length")
     tau = torch.empty((G, Rx, Ry), dtype=torch.float64, device=dev)
     counts = torch.empty((G, Rx, Ry, 4), dtype=torch.int64, device=dev)
+    if n > KENDALL_PAIRCOUNT_MAX_N or force_large:      # long rank vectors: sort + merge-pass inversion count
+        wb = lib().rc_kendall_large_workspace_bytes(G, Rx, Ry, n)
+        if wb == 0:
+            raise ValueError("Kendall problem too large (more than 2^31 elements)")
+        ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+        check(lib().rc_kendall_tau_b_large(_ptr(x), _ptr(y), G, Rx, Ry, n, _ptr(tau), _ptr(counts), _ptr(ws), wb, _stream()))
+        return tau
     check(lib().rc_kendall_tau_b_batched(_ptr(x), _ptr(y), G, Rx, Ry, n, _ptr(tau), _ptr(counts), _stream()))
     _count(2)
     return tau

@@ -191,6 +191,15 @@ int rc_kendall_tau_b(const double* x_dev, int64_t Rx, const int64_t* y_dev, int6
 int rc_kendall_tau_b_batched(const double* x_dev, const int64_t* y_dev, int64_t G, int64_t Rx, int64_t Ry,
                              int64_t n, double* tau_dev, long long* counts_dev, void* stream);
 
+/* The same matrices for LONG rank vectors (top-k up to 1e5) in O(n log^2 n): dense labels by segmented
+ * radix sort, tie counts from the sorted runs, discordant pairs = inversions counted by parallel merge passes
+ * (Knight's algorithm, what SciPy itself uses).  Integer counts => bit-identical to rc_kendall_tau_b_batched.
+ * workspace: rc_kendall_large_workspace_bytes(G, Rx, Ry, n) (0 = more than 2^31 elements). */
+size_t rc_kendall_large_workspace_bytes(int64_t G, int64_t Rx, int64_t Ry, int64_t n);
+int rc_kendall_tau_b_large(const double* x_dev, const int64_t* y_dev, int64_t G, int64_t Rx, int64_t Ry, int64_t n,
+                           double* tau_dev, long long* counts_dev, void* workspace_dev, size_t workspace_bytes,
+                           void* stream);
+
 /* The paper's fig-4 rank-consistency analysis for G controller groups in one call.
  * W_dev: RIM matrix [S][G*Cg] (row 0 of the statistics tensor).  Per group: keep the topk
  * controllers with the smallest RIM at sigma index 0, in their original column order

@@ -1084,3 +1084,30 @@ def test_analytic_gradient_from_eigendecomposition(rb):
     e_n, g_n = rb.engine.fidelity_grad(np.stack([x, xn]), n, 0, 5)
     assert np.isfinite(e_n[0]) and np.isnan(e_n[1]) and np.isnan(g_n[1]).all() and np.abs(g_n[0] - grad).max() < 1e-14
     assert rb.engine.fidelity_grad(np.zeros((0, n + 1)), n, 0, 5)[0].shape == (0,)
+
+
+@pytest.mark.parametrize("n", [2, 3, 100, 4097, 20000])
+def test_kendall_large_path_equals_pair_count_and_scipy(rb, n):
+    """rc_kendall_tau_b_large (sort + merge-pass inversion count, for top-k up to 1e5) gives the same integer counts
+    as the O(n^2) pair count and scipy.stats.kendalltau: ties in x (clustered ranks), ties in y, all-tied rows."""
+    rs = np.random.RandomState(n)
+    G, Rx, Ry = 2, 3, 2
+    x = rs.randint(0, max(2, n // 7), size=(G, Rx, n)).astype(np.float64)      # heavily tied (clustered ranks)
+    x[0, 1] = rs.permutation(n)                                                  # no ties
+    x[1, 2] = 5.0                                                                # all tied -> NaN
+    y = np.stack([np.stack([rs.permutation(n) for _ in range(Ry)]) for _ in range(G)]).astype(np.int64)
+    y[1, 0] = rs.randint(0, 3, size=n)                                           # tied y
+    xt, yt = torch.as_tensor(x).cuda(), torch.as_tensor(y).cuda()
+    big = rb.engine.kendall_tau_b_batched(xt, yt, force_large=True).cpu().numpy()
+    if n <= 4096:
+        small = rb.engine.kendall_tau_b_batched(xt, yt).cpu().numpy()
+        assert np.array_equal(big, small, equal_nan=True)
+    for g in range(G):
+        for j in range(Rx):
+            for i in range(Ry):
+                want = scipy.stats.kendalltau(x[g, j], y[g, i]).correlation if n >= 2 else np.nan
+                got = big[g, j, i]
+                assert (np.isnan(want) and np.isnan(got)) or got == want, (g, j, i, got, want)
+    if n > 4096:                                                                 # the public call picks the large path itself
+        one = rb.engine.kendall_tau_b(xt[0], yt[0]).cpu().numpy()
+        assert np.array_equal(one, big[0], equal_nan=True)
