@@ -12,7 +12,7 @@ cmds=()
 for n in $(seq 2 16); do
   cmds+=("$NVCC $FLAGS -DRC_NSPIN=$n -c rc_fidelity_n.cu -o $OBJ/rc_fidelity_$n.o")
 done
-for f in rc_fidelity rc_stats rc_rank rc_api rc_expm rc_peer rc_objective rc_grad rc_kendall_large; do
+for f in rc_fidelity rc_stats rc_rank rc_api rc_expm rc_peer rc_objective rc_grad rc_kendall_large rc_dense_mc; do
   cmds+=("$NVCC $FLAGS -c $f.cu -o $OBJ/$f.o")
 done
 printf '%s\n' "${cmds[@]}" | xargs -P "$JOBS" -I{} bash -c "{}"

@@ -432,7 +432,13 @@ extern "C" size_t rc_rank_consistency_workspace_bytes(int64_t S, int64_t G, int6
     size_t a = rc_ranks_workspace_bytes(G, Cg), b = rc_ranks_workspace_bytes(G * S, k);
     if (a == 0 || b == 0) return 0;
     size_t ws = a > b ? a : b;
-    return align256(ws) + align256((size_t)G * Cg) + 2 * align256((size_t)G * S * k * 8) + align256((size_t)G * S * S * 4 * 8) + 256;
+    size_t kl = 0;
+    if (k > RANK_SMEM_MAX) {          // long rank vectors: the sort + merge-pass Kendall (rc_kendall_tau_b_large)
+        kl = rc_kendall_large_workspace_bytes(G, S, S, k);
+        if (kl == 0) return 0;
+    }
+    return align256(ws) + align256((size_t)G * Cg) + 2 * align256((size_t)G * S * k * 8) + align256((size_t)G * S * S * 4 * 8) +
+           align256(kl) + 256;
 }
 
 extern "C" int rc_rank_consistency(const double* W_dev, int64_t S, int64_t G, int64_t Cg, int64_t topk, double alpha,
@@ -454,7 +460,8 @@ extern "C" int rc_rank_consistency(const double* W_dev, int64_t S, int64_t G, in
     unsigned char* mark = (unsigned char*)p; p += align256((size_t)G * Cg);
     double* cr = (double*)p; p += align256((size_t)G * S * k * 8);
     long long* rk = (long long*)p; p += align256((size_t)G * S * k * 8);
-    long long* counts = (long long*)p;
+    long long* counts = (long long*)p; p += align256((size_t)G * S * S * 4 * 8);
+    void* klws = p;
     const int sm = device_sm_count();
     // 1. ranks of the sigma-index-0 row inside every group (W row 0 is [G][Cg] contiguous)
     int rcode = argsort_rows(W_dev, G, Cg, sortws, ws_sort, st);
@@ -476,7 +483,10 @@ extern "C" int rc_rank_consistency(const double* W_dev, int64_t S, int64_t G, in
     if (blocks > sm * 8) blocks = sm * 8;
     scatter_ranks_kernel<<<(unsigned)blocks, 256, 0, st>>>((const int*)sortws, G * S, k, rk, 1); rc::note_launch();
     RC_CUDA_TRY(cudaGetLastError());
-    // 3. S x S Kendall tau-b per group
+    // 3. S x S Kendall tau-b per group (O(k^2) pair count for the paper's k = 100; sort + merge passes for long vectors)
+    if (k > RANK_SMEM_MAX)
+        return rc_kendall_tau_b_large(cr, (const int64_t*)rk, G, S, S, k, tau_dev, counts, klws,
+                                      rc_kendall_large_workspace_bytes(G, S, S, k), stream);
     return rc_kendall_tau_b_batched(cr, (const int64_t*)rk, G, S, S, k, tau_dev, counts, stream);
 }
 

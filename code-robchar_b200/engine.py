@@ -83,8 +83,14 @@ class Counters:
 
 def fidelity_mc(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, *, model: int = MODEL_COMPLEX3,
                 zz: bool = False, seed: int = 0, c_offset: int = 0, b_offset: int = 0, replay=None, out=None,
-                counters: Counters | None = None, check_convergence: bool = True) -> torch.Tensor:
-    """Fidelity tensor [S][C][B] (mcsim.py:422-456).  replay: standard normals [S][C][B][K] or None (Philox)."""
+                counters: Counters | None = None, check_convergence: bool = True, topo: str = "chain") -> torch.Tensor:
+    """Fidelity tensor [S][C][B] (mcsim.py:422-456).  replay: standard normals [S][C][B][K] or None (Philox).
+    topo="ring" (noise_model.py:83-85): the batched dense path (rc_dense_fidelity_mc), same layout and draws."""
+    if topo not in ("chain", "linear", "ring"):
+        raise ValueError(f"unknown topology {topo!r}")
+    if topo == "ring":
+        return dense_fidelity_mc(ctrl, sigmas, B, nspin, inspin, outspin, model=model, zz=zz, seed=seed, c_offset=c_offset,
+                                 b_offset=b_offset, replay=replay, out=out, ring=True)
     dev = require_cuda()
     ctrl = _f64(ctrl, dev)
     sigmas = _f64(sigmas, dev).reshape(-1)
@@ -107,6 +113,32 @@ def fidelity_mc(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, *, 
     _count(1)
     if own and check_convergence:
         counters.raise_if_set()
+    return out
+
+
+def dense_fidelity_mc(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, *, model: int = MODEL_COMPLEX3,
+                      zz: bool = False, seed: int = 0, c_offset: int = 0, b_offset: int = 0, replay=None, out=None,
+                      ring: bool = True, tile: int = 1 << 17) -> torch.Tensor:
+    """Fidelity tensor [S][C][B] of a sweep through the dense path (rc_dense_fidelity_mc): ring topology under the
+    structured perturbation, `tile` evaluations per pass of the batched matrix exponential."""
+    dev = require_cuda()
+    ctrl = _f64(ctrl, dev)
+    sigmas = _f64(sigmas, dev).reshape(-1)
+    if ctrl.dim() != 2 or ctrl.shape[1] != nspin + 1:
+        raise ValueError(f"ctrl must be [C][{nspin + 1}], got {tuple(ctrl.shape)}")
+    Cn, S = ctrl.shape[0], sigmas.shape[0]
+    if replay is not None:
+        replay = _f64(replay, dev)
+        if replay.numel() != S * Cn * B * draws_per_eval(nspin, model):
+            raise ValueError("replay must hold S*C*B*K standard normals")
+    if out is None:
+        out = torch.empty((S, Cn, B), dtype=torch.float64, device=dev)
+    total = S * Cn * B
+    wb = lib().rc_dense_fidelity_mc_workspace_bytes(nspin, max(1, min(tile, total)))
+    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+    check(lib().rc_dense_fidelity_mc(_ptr(ctrl), Cn, nspin, inspin, outspin, _ptr(sigmas), S, B, model, int(bool(zz)),
+                                     int(bool(ring)), C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, _ptr(replay),
+                                     _ptr(out), _ptr(ws), wb, _stream()))
     return out
 
 

@@ -302,6 +302,19 @@ int rc_fidelity_grad_host(const double* x_host, int64_t C, int nspin, int inspin
  * Scaling and squaring with the [13/13] Pade approximant; NaN/Inf input gives NaN output. */
 int rc_expm_batch(const double* A_dev, int64_t batch, int M, double* out_dev, void* stream);
 
+/* Batched Monte-Carlo sweep for the ring topology (noise_model.py:83-85, qnewton.py:145-147: unit couplings between
+ * sites 0 and N-1 on top of the chain) under the structured perturbation, which the reference evaluates one call at a
+ * time with scipy.linalg.expm (noise_model.py:98-109).  Same arguments, Philox counters, replay layout and fids
+ * [S][C][B] output as rc_fidelity_mc; ring = 0 evaluates the open chain through the same dense path (cross-check).
+ * Each tile of evaluations gets its dense -iTH built on the device, goes through rc_expm_batch and |U[out,in]|^2 is
+ * extracted.  workspace: any size >= one matrix pair; rc_dense_fidelity_mc_workspace_bytes(nspin, tile) for a
+ * tile of `tile` evaluations per pass. */
+size_t rc_dense_fidelity_mc_workspace_bytes(int nspin, int64_t tile);
+int rc_dense_fidelity_mc(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin, const double* sigma_dev,
+                         int S, int64_t B, int model, int zz, int ring, uint64_t seed, int64_t c_offset, int64_t b_offset,
+                         const double* replay_dev, double* fids_dev, void* workspace_dev, size_t workspace_bytes,
+                         void* stream);
+
 /* FP64 FMA throughput micro-benchmark of the current device (TFLOP/s, 2 flops per DFMA); used as
  * the roofline denominator of the evolution kernel. */
 int rc_fp64_peak_tflops(double* tflops, void* stream);

@@ -1111,3 +1111,46 @@ def test_kendall_large_path_equals_pair_count_and_scipy(rb, n):
     if n > 4096:                                                                 # the public call picks the large path itself
         one = rb.engine.kendall_tau_b(xt[0], yt[0]).cpu().numpy()
         assert np.array_equal(one, big[0], equal_nan=True)
+
+
+def test_rank_consistency_with_long_rank_vectors(rb):
+    """The one-call fig-4 analysis with top-k = 6000 > 4096 (scaled rank sizes): selection, clustered /
+    ordinal ranks through the segmented-sort path and the Kendall matrix through the sort + merge-pass path, against
+    the oracle's restatement of the reference functions."""
+    rs = np.random.RandomState(4)
+    S, Cg, topk = 3, 7000, 6000
+    W = rs.uniform(0, 1, (S, Cg))
+    W[1] = W[0] + 0.01 * rs.standard_normal(Cg)
+    tau, sel, Wsel = rb.engine.grouped_rank_consistency(torch.as_tensor(W).cuda(), 1, topk=topk, alpha=0.05)
+    mask = orc.get_top_k_mask(W[0], topk)
+    assert np.array_equal(np.nonzero(mask)[0], sel[0].cpu().numpy())
+    assert np.array_equal(tau[0].cpu().numpy(), orc.kendall_matrix(W[:, mask]), equal_nan=True)
+
+
+@pytest.mark.parametrize("n,model,zz", [(3, 0, False), (6, 0, False), (7, 1, True), (12, 0, True)])
+def test_batched_ring_topology_sweep(rb, n, model, zz):
+    """topo="ring" as a batched Monte-Carlo sweep (rc_dense_fidelity_mc): replay parity with the oracle's dense
+    expm on the ring Hamiltonian (noise_model.py:83-85, qnewton.py:145-150 for the Heisenberg diagonal), Philox mode ==
+    replay of its own normals, the open chain through the same dense path == the tridiagonal kernels, tiling."""
+    rs = np.random.RandomState(n)
+    C, B, S = 5, 9, 3
+    ctrl = orc.synthetic_controllers(C, n, seed=n)
+    ctrl[:, :n] *= 0.2
+    sig = np.array([0.0, 0.05, 0.1])
+    K = (3 if model == 0 else 2) * n
+    nrm = rs.standard_normal((S, C, B, K))
+    f = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, n // 2, model=model, zz=zz, replay=nrm, topo="ring").cpu().numpy()
+    ref = orc.fidelity_mc_replay(ctrl, sig, nrm, n, 0, n // 2, model=model, zz=zz, topo="ring")
+    assert np.abs(f - ref).max() < FID_TOL
+    kw = dict(model=model, zz=zz, seed=8, c_offset=1, b_offset=2)
+    z = rb.engine.philox_normals(C, n, S, B, model=model, seed=8, c_offset=1, b_offset=2)
+    fa = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, n // 2, topo="ring", **kw)
+    fb = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, n // 2, model=model, zz=zz, replay=z, topo="ring")
+    assert torch.equal(fa, fb)
+    small_tiles = rb.engine.dense_fidelity_mc(ctrl, sig, B, n, 0, n // 2, ring=True, tile=7, **kw)
+    assert torch.equal(small_tiles, fa)
+    chain_dense = rb.engine.dense_fidelity_mc(ctrl, sig, B, n, 0, n // 2, ring=False, **kw).cpu().numpy()
+    chain_fast = rb.engine.fidelity_mc(ctrl, sig, B, n, 0, n // 2, **kw).cpu().numpy()
+    assert np.abs(chain_dense - chain_fast).max() < FID_TOL
+    if n > 2:
+        assert np.abs(fa.cpu().numpy() - chain_fast).max() > 1e-6       # the corner couplings do change the answer
