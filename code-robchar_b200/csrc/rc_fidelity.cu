@@ -181,6 +181,16 @@ static cudaError_t launch_smem(const FidArgs& a0, int sm_count, cudaStream_t st)
     const long long nblk = (total + threads - 1) / threads;
     if (algo == ALGO_SPECTRAL) {
         a.respec = respec_counter_device();
+        // the CTA sizes the launcher picks (768 lanes for N <= 18, 640 to N = 22, 512 to N = 28, 384 above) have the stride
+        // compiled in (Philox mode): shared-memory offsets become immediates
+        if (!REPLAY && !AMPS && threads == 768)
+            return launch_persistent(fidelity_smem_kernel<MODEL, false, false, ALGO_SPECTRAL, SMEM_MAX_THREADS, 768>, threads, smem, nblk, sm_count, st, &a);
+        if (!REPLAY && !AMPS && threads == 640)
+            return launch_persistent(fidelity_smem_kernel<MODEL, false, false, ALGO_SPECTRAL, SMEM_MAX_THREADS, 640>, threads, smem, nblk, sm_count, st, &a);
+        if (!REPLAY && !AMPS && threads == 512)
+            return launch_persistent(fidelity_smem_kernel<MODEL, false, false, ALGO_SPECTRAL, SMEM_WIDE_THREADS, 512>, threads, smem, nblk, sm_count, st, &a);
+        if (!REPLAY && !AMPS && threads == 384)
+            return launch_persistent(fidelity_smem_kernel<MODEL, false, false, ALGO_SPECTRAL, SMEM_WIDE_THREADS, 384>, threads, smem, nblk, sm_count, st, &a);
         if (threads <= SMEM_WIDE_THREADS)
             return launch_persistent(fidelity_smem_kernel<MODEL, REPLAY, AMPS, ALGO_SPECTRAL, SMEM_WIDE_THREADS>, threads, smem, nblk, sm_count, st, &a);
         return launch_persistent(fidelity_smem_kernel<MODEL, REPLAY, AMPS, ALGO_SPECTRAL>, threads, smem, nblk, sm_count, st, &a);
@@ -227,6 +237,14 @@ static cudaError_t launch_fused_smem_warp(const FusedArgs& g0, int sm_count, cud
     const long long need = (nitems + wpc - 1) / wpc;
     if (algo == ALGO_SPECTRAL) {
         g.f.respec = respec_counter_device();
+        if (threads == 768)
+            return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL, SMEM_MAX_THREADS, 768>, threads, smem, need, sm_count, st, &g);
+        if (threads == 640)
+            return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL, SMEM_MAX_THREADS, 640>, threads, smem, need, sm_count, st, &g);
+        if (threads == 512)
+            return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL, SMEM_WIDE_THREADS, 512>, threads, smem, need, sm_count, st, &g);
+        if (threads == 384)
+            return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL, SMEM_WIDE_THREADS, 384>, threads, smem, need, sm_count, st, &g);
         if (threads <= SMEM_WIDE_THREADS)
             return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL, SMEM_WIDE_THREADS>, threads, smem, need, sm_count, st, &g);
         return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL>, threads, smem, need, sm_count, st, &g);

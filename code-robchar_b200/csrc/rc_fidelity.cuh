@@ -535,16 +535,17 @@ __host__ __device__ inline int spec_outer_sites(int n, int in, int out) {
     const int lo = in < out ? in : out, hi = in < out ? out : in;
     return lo + (n - 1 - hi);
 }
-__host__ __device__ inline int spec_lane_doubles(int n, int in, int out) { return 2 * n + 2 * spec_outer_sites(n, in, out); }
+// + 1: the pad row in front of d that the unconditional operand prefetch of the chase may read (rc_spectral.cuh)
+__host__ __device__ inline int spec_lane_doubles(int n, int in, int out) { return 2 * n + 2 * spec_outer_sites(n, in, out) + 1; }
 
 // d / e of the gauge-transformed Hamiltonian of one evaluation into this lane's columns (same arithmetic, same
 // rounding order as build_tridiagonal / eval_smem).  Philox mode, complex model: three draws per site but two
 // columns — the imaginary coupling draw nn2_i is parked in the spare slot e[n-1] and folded into
 // e[i-1] = |1 + sigma nn_i + i sigma nn2_i| as soon as its Philox block is complete (a block holds at most one).
-template <int MODEL, bool REPLAY>
+template <int MODEL, bool REPLAY, int LD = 0>
 __device__ __noinline__ void build_spec(const FidArgs& a, long long s, long long c, long long b, const double* row,
-                                        double* d, double* e, int ld) {
-    const int n = a.N;
+                                        double* d, double* e, int ld_rt) {
+    const int n = a.N, ld = LD ? LD : ld_rt;
     constexpr int P = draws_per_site(MODEL);
     const double* x = a.ctrl + c * (n + 1);
     const double sigma = __ldg(a.sigma + s);
@@ -620,7 +621,7 @@ template <int MODEL, bool REPLAY>
 __device__ __noinline__ double2 spec_recompute(const FidArgs& a, bool mine, long long s, long long c, long long b,
                                                const double* row, double* sm, double T) {
     const int n = a.N, ld = blockDim.x, lane = threadIdx.x & 31;
-    double* d = sm + threadIdx.x;
+    double* d = sm + ld + threadIdx.x;            // row 0 of the lane's column is the pad row
     double* e = d + (size_t)n * ld;
     double re = NAN, im = NAN;
 #pragma unroll 1
@@ -628,7 +629,7 @@ __device__ __noinline__ double2 spec_recompute(const FidArgs& a, bool mine, long
         __syncwarp();
         if (mine && (lane & 1) == par) {
             build_spec<MODEL, REPLAY>(a, s, c, b, row, d, e, ld);
-            double* zi = sm + (threadIdx.x ^ 1);
+            double* zi = sm + ld + (threadIdx.x ^ 1);
             double* zo = zi + (size_t)n * ld;
             for (int i = 0; i < n; ++i) {
                 zi[(size_t)i * ld] = (i == a.in) ? 1.0 : 0.0;
@@ -646,13 +647,13 @@ __device__ __noinline__ double2 spec_recompute(const FidArgs& a, bool mine, long
 
 // One evaluation per lane; ALL 32 lanes of the warp must call it converged (`valid` = this lane has work): the
 // rare evaluations whose spectral error estimate is rejected are recomputed inside the call (spec_recompute).
-template <int MODEL, bool REPLAY, bool AMPS = false>
+template <int MODEL, bool REPLAY, bool AMPS = false, int LD = 0>
 __device__ __forceinline__ double eval_spec(const FidArgs& a, bool valid, long long s, long long c, long long b,
                                             const double* row /* global replay row */, double* sm) {
-    const int n = a.N, ld = blockDim.x;
+    const int n = a.N, ld = LD ? LD : (int)blockDim.x;   // LD: compile-time CTA size (immediate shared-memory offsets)
     const int lo = a.in < a.out ? a.in : a.out, hi = a.in < a.out ? a.out : a.in;
     const int nx = lo + (n - 1 - hi);
-    double* d = sm + threadIdx.x;
+    double* d = sm + ld + threadIdx.x;                    // row 0 of the lane's column is the pad row
     double* e = d + (size_t)n * ld;
     double* xd = e + (size_t)n * ld;
     double* xe = xd + (size_t)nx * ld;
@@ -660,7 +661,7 @@ __device__ __forceinline__ double eval_spec(const FidArgs& a, bool valid, long l
     bool ok = true;
     if (valid) {
         T = fabs(__ldg(a.ctrl + c * (n + 1) + n));
-        build_spec<MODEL, REPLAY>(a, s, c, b, row, d, e, ld);
+        build_spec<MODEL, REPLAY, LD>(a, s, c, b, row, d, e, ld);
         SpecBlocks xb;
         xb.xd = xd; xb.xe = xe; xb.na = lo; xb.nb = n - 1 - hi;
         for (int j = 0; j < lo; ++j) { xd[(size_t)j * ld] = d[(size_t)j * ld]; xe[(size_t)j * ld] = e[(size_t)j * ld]; }
@@ -670,7 +671,7 @@ __device__ __forceinline__ double eval_spec(const FidArgs& a, bool valid, long l
         }
         double pb = 1.0;
         for (int i = lo; i < hi; ++i) pb *= e[(size_t)i * ld];
-        ok = amplitude_spectral_strided(d, e, ld, n, T, pb, xb, re, im);
+        ok = amplitude_spectral_strided<LD>(d, e, ld, n, T, pb, xb, re, im);
     }
     const unsigned redo = __ballot_sync(0xffffffffu, valid && !ok);
     if (redo) {
@@ -685,7 +686,7 @@ __device__ __forceinline__ double eval_spec(const FidArgs& a, bool valid, long l
     return fma(re, re, im * im);
 }
 
-template <int MODEL, bool REPLAY, bool AMPS = false, int ALGO = ALGO_VECTORS, int MAXT = SMEM_MAX_THREADS>
+template <int MODEL, bool REPLAY, bool AMPS = false, int ALGO = ALGO_VECTORS, int MAXT = SMEM_MAX_THREADS, int LD = 0>
 __global__ void __launch_bounds__(MAXT, 1) fidelity_smem_kernel(FidArgs a) {
     extern __shared__ double sm[];
     const long long K = (long long)draws_per_site(MODEL) * a.N;
@@ -697,7 +698,7 @@ __global__ void __launch_bounds__(MAXT, 1) fidelity_smem_kernel(FidArgs a) {
         EvalIndex ix = decode_eval(valid ? ev : 0, a.C, a.B);
         const double* row = REPLAY ? a.replay + (valid ? ev : 0) * K : nullptr;
         if (ALGO == ALGO_SPECTRAL) {
-            const double f = eval_spec<MODEL, REPLAY, AMPS>(a, valid, ix.s, ix.c, ix.b, row, sm);
+            const double f = eval_spec<MODEL, REPLAY, AMPS, LD>(a, valid, ix.s, ix.c, ix.b, row, sm);
             if (valid) a.fids[ev] = f;
         } else if (valid) {
             a.fids[ev] = eval_smem<MODEL, REPLAY, AMPS>(a, ix.s, ix.c, ix.b, row, sm);
@@ -706,7 +707,7 @@ __global__ void __launch_bounds__(MAXT, 1) fidelity_smem_kernel(FidArgs a) {
 }
 
 // Warp-autonomous fused variant of the shared-memory kernel (Philox mode): see fidelity_stats_reg_warp_kernel.
-template <int MODEL, int ALGO = ALGO_VECTORS, int MAXT = SMEM_MAX_THREADS>
+template <int MODEL, int ALGO = ALGO_VECTORS, int MAXT = SMEM_MAX_THREADS, int LD = 0>
 __global__ void __launch_bounds__(MAXT, 1) fidelity_stats_smem_warp_kernel(FusedArgs g) {
     extern __shared__ double sm[];
     __shared__ double wacc_all[(SMEM_MAX_THREADS / 32) * WACC_DOUBLES];
@@ -724,7 +725,7 @@ __global__ void __launch_bounds__(MAXT, 1) fidelity_stats_smem_warp_kernel(Fused
             const long long b = bt + lane;
             const bool valid = b < b1;
             double f = 0.0;
-            if (ALGO == ALGO_SPECTRAL) f = eval_spec<MODEL, false>(a, valid, s, c, b, nullptr, sm);
+            if (ALGO == ALGO_SPECTRAL) f = eval_spec<MODEL, false, false, LD>(a, valid, s, c, b, nullptr, sm);
             else if (valid) f = eval_smem<MODEL, false>(a, s, c, b, nullptr, sm);
             warp_acc_pass(wacc, bt == b0, valid, f, g.eps);
         }

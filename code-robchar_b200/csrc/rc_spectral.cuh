@@ -35,7 +35,13 @@ constexpr double SPEC_EST_THR = 1e-11;   // accepted a-posteriori error estimate
 // Eigenvalues of the symmetric tridiagonal (d, e), in place in d (unordered); e is destroyed.  Same flat
 // deflate / sweep loop and the same `rmin` split test as amplitude_strided, minus the eigenvector rows.
 // Returns 1 when an eigenvalue needed more than QL_MAX_SWEEPS sweeps.
-RC_HD int ql_eigenvalues_strided(double* d, double* e, int ld, int n, int tolhi, double tiny) {
+// LD > 0: the column stride is the compile-time constant LD (it becomes an immediate offset of the shared-memory
+// loads / stores of the chase: no address arithmetic per rotation); LD = 0: run-time stride ld_rt.
+// The operands of rotation i-1 are fetched unconditionally while rotation i computes: for i = l = 0 that reads one
+// row BEFORE the arrays, so the caller keeps one pad row in front of d (e follows d, so its row -1 is d's last row).
+template <int LD = 0>
+RC_HD int ql_eigenvalues_strided(double* d, double* e, int ld_rt, int n, int tolhi, double tiny) {
+    const int ld = LD ? LD : ld_rt;
     int rmin = 0, l = 0, it = 0;
     while (l < n - 1 && it <= QL_MAX_SWEEPS) {
         if (negligible_hi(RC_AT(e, l), tolhi)) { ++l; it = 0; }
@@ -55,8 +61,7 @@ RC_HD int ql_eigenvalues_strided(double* d, double* e, int ld, int n, int tolhi,
             double ei = *pe, di = *pd;
             rmin = 0x7fffffff;
             for (int i = m - 1; i >= l; --i) {
-                const int back = i > l ? ld : 0;   // operands of rotation i-1, loaded while rotation i computes
-                const double ein = *(pe - back), din = *(pd - back);
+                const double ein = *(pe - ld), din = *(pd - ld);   // operands of rotation i-1 (pad row when i = 0)
                 const double f = s * ei, b = c * ei;
                 const double h = fma(f, f, fma(g, g, tiny));
                 const double rinv = rc_rsqrt(h);
@@ -122,8 +127,10 @@ struct SpecBlocks { const double* xd; const double* xe; int na, nb; };
 
 // amp = sum_k w_k exp(-i lambda_k T) from the eigenvalues in d[0..n); pb = product of the couplings between
 // the two sites; anorm = max_i(|d_i| + |e_i|) of the original matrix.  *est receives the error estimate.
-RC_HD void spectral_phase_sum(const double* d, int ld, int n, double T, double pb, double anorm, const SpecBlocks& xb,
+template <int LD = 0>
+RC_HD void spectral_phase_sum(const double* d, int ld_rt, int n, double T, double pb, double anorm, const SpecBlocks& xb,
                               double& re_out, double& im_out, double* est_out) {
+    const int ld = LD ? LD : ld_rt;
     double re = 0.0, im = 0.0, est = 0.0;
     const double cgap = (double)(n - 1) * 4.0 * DBL_EPSILON * anorm;
     const bool minors = (xb.na + xb.nb) > 0;
@@ -218,12 +225,14 @@ RC_HD void spectral_phase_sum(const double* d, int ld, int n, double T, double p
     re_out = re; im_out = im; *est_out = est;
 }
 
-// Whole evaluation on strided storage.  On entry d[0..n), e[0..n-1) hold the matrix; xb the blocks outside
+// Whole evaluation on strided storage (one pad row in front of d, see ql_eigenvalues_strided).  On entry d[0..n), e[0..n-1) hold the matrix; xb the blocks outside
 // [a, b] (already copied aside by the caller), pb the coupling product.  Returns true when the result is
 // accepted; false = recompute with amplitude_strided (non-finite estimate, estimate above threshold, or
 // eigenvalue non-convergence).  NaN / Inf input: accepted with NaN output, like amplitude_strided.
-RC_HD bool amplitude_spectral_strided(double* d, double* e, int ld, int n, double T, double pb, const SpecBlocks& xb,
+template <int LD = 0>
+RC_HD bool amplitude_spectral_strided(double* d, double* e, int ld_rt, int n, double T, double pb, const SpecBlocks& xb,
                                       double& re_out, double& im_out) {
+    const int ld = LD ? LD : ld_rt;
     double anorm = 0.0, chk = T;
     RC_AT(e, n - 1) = 0.0;
     for (int k = 0; k < n; ++k) {
@@ -233,9 +242,9 @@ RC_HD bool amplitude_spectral_strided(double* d, double* e, int ld, int n, doubl
     re_out = NAN; im_out = NAN;
     if (!(fabs(chk) <= DBL_MAX)) return true;
     const double tol = DBL_EPSILON * anorm;
-    if (ql_eigenvalues_strided(d, e, ld, n, threshold_hi(tol), fmin(tol, 1e-280))) return false;
+    if (ql_eigenvalues_strided<LD>(d, e, ld, n, threshold_hi(tol), fmin(tol, 1e-280))) return false;
     double est;
-    spectral_phase_sum(d, ld, n, T, pb, anorm, xb, re_out, im_out, &est);
+    spectral_phase_sum<LD>(d, ld, n, T, pb, anorm, xb, re_out, im_out, &est);
     return est <= SPEC_EST_THR;   // false for NaN / inf as well
 }
 

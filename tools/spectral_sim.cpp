@@ -57,7 +57,10 @@ int main(int argc, char** argv) {
         std::vector<double> d(buf.begin(), buf.begin() + N), e(N, 0.0), zi(N, 0.0), zo(N, 0.0);
         for (int i = 0; i < N - 1; ++i) e[i] = buf[N + i];
         const double T = buf[2 * N - 1];
-        std::vector<double> d2 = d, e2 = e, xd(N, 0.0), xe(N, 0.0);
+        std::vector<double> de(2 * N + 1, 0.0), xd(N, 0.0), xe(N, 0.0);   // [pad][d][e] contiguous: the chase prefetches row -1
+        double* d2p = de.data() + 1;
+        double* e2p = d2p + N;
+        for (int i = 0; i < N; ++i) { d2p[i] = d[i]; e2p[i] = e[i]; }
         SpecBlocks xb;
         xb.na = a; xb.nb = N - 1 - b; xb.xd = xd.data(); xb.xe = xe.data();
         for (int j = 0; j < a; ++j) { xd[j] = d[j]; xe[j] = e[j]; }
@@ -65,7 +68,7 @@ int main(int argc, char** argv) {
         double pb = 1.0;
         for (int i = a; i < b; ++i) pb *= e[i];
         double re, im;
-        const bool ok = amplitude_spectral_strided(d2.data(), e2.data(), 1, N, T, pb, xb, re, im);
+        const bool ok = amplitude_spectral_strided(d2p, e2p, 1, N, T, pb, xb, re, im);
         zi[in] = 1; zo[out] = 1;
         int fail = 0;
         const double fref = fidelity_strided(d.data(), e.data(), zi.data(), zo.data(), 1, N, T, &fail);
