@@ -244,7 +244,9 @@ static int sweep_host_impl(const double* ctrl_host, int64_t C, int nspin, int in
             copy = async->copy;
         }
         for (int k = 0; k < nch; ++k) {
-            const long long s0 = (long long)S * k / nch, s1 = (long long)S * (k + 1) / nch, Sk = s1 - s0;
+            // ceil-based boundaries: the remainder goes to the FIRST chunks, so the last chunk — whose D2H copy nothing
+            // overlaps — is the smallest (S = 11, 4 chunks: 3, 3, 3, 2 levels; a single-level last chunk measured no better)
+            const long long s0 = ((long long)S * k + nch - 1) / nch, s1 = ((long long)S * (k + 1) + nch - 1) / nch, Sk = s1 - s0;
             const long long e0 = s0 * C * B;
             rcode = fidelity_mc_impl("sweep", ctrl.as<double>(), C, nspin, inspin, outspin, sigma.as<double>() + s0, (int)Sk,
                                      B, model, zz, seed, c_offset, b_offset,
