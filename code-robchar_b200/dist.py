@@ -75,6 +75,10 @@ class _DeviceArray:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """CUDA IPC mapping of the peers' exchange buffers failed on at least one rank (agreed collectively)."""
+
+
 class PeerStatsExchange:
     """Exchange of the per-rank statistics blocks by direct NVLink writes (csrc/rc_peer.cu).
 
@@ -111,15 +115,31 @@ class PeerStatsExchange:
             td.all_gather_object(handles, bytes(handle), group=group)
         else:
             handles[0] = bytes(handle)
-        self.peer_base = []
+        self.peer_base = [0] * self.world
+        self.peer_base[self.rank] = self.base
+        err = None
         for r in range(self.world):
             if r == self.rank:
-                self.peer_base.append(self.base)
-            else:
-                p = C.c_void_p(0)
-                check(self._lib.rc_peer_open((C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(p)))
-                self.peer_base.append(int(p.value))
+                continue
+            p = C.c_void_p(0)
+            code = self._lib.rc_peer_open((C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(p))
+            if code:
+                from ._lib import last_error
+                err = last_error()
+                break
+            self.peer_base[r] = int(p.value)
         if self.world > 1:
+            # the mapping either works on EVERY rank or the exchange is abandoned on every rank (the caller falls back to
+            # the torch.distributed all-gather): agree before anybody pushes
+            okflag = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.dev)
+            td.all_reduce(okflag, op=td.ReduceOp.MIN, group=group)
+            if int(okflag.item()) == 0:
+                for r, b in enumerate(self.peer_base):
+                    if r != self.rank and b:
+                        self._lib.rc_peer_close(C.c_void_p(b))
+                td.barrier(group=group)
+                self._lib.rc_peer_free(C.c_void_p(self.base))
+                raise PeerExchangeUnavailable(err or "a peer could not map this rank's exchange buffer")
             td.barrier(group=group)            # every buffer is mapped (and zeroed) before anyone pushes
         VP = C.c_void_p * self.world
         self._flag_ptrs = VP(*[C.c_void_p(b) for b in self.peer_base])
@@ -214,7 +234,14 @@ class ShardedRobustnessSweep:
                        fused=fused, nboot=nboot)
         self.plan = engine.RobustnessSweepPlan(self.C_local, S, B, nspin, inspin, outspin, **self.kw)
         self.mode = exchange if self.world > 1 else "none"
-        self.xchg = PeerStatsExchange(engine.NUM_STATS * S, C_total, group=group) if self.mode == "peer" else None
+        self.xchg = None
+        if self.mode == "peer":
+            try:
+                self.xchg = PeerStatsExchange(engine.NUM_STATS * S, C_total, group=group)
+            except PeerExchangeUnavailable as e:      # decided by all ranks together: use the collective instead
+                if self.rank == 0:
+                    print(f"[robchar_b200.dist] peer exchange unavailable ({e}); using the torch.distributed all-gather")
+                self.mode = "nccl"
         self.seq = 0
         self._gathered = None
         self._host = None

@@ -50,6 +50,20 @@ if 8 % world == 0:
     ok = ok and same
     if rank == 0:
         print("draw-sharded == single GPU:", same, "W row:", got[0, :, 0].tolist()[:3])
+# uneven shards through the exchange itself: 7 columns over the ranks, 3 pipelined steps
+C7 = 4 * world + 3
+x = rb.dist.PeerStatsExchange(5, C7)
+for k in range(1, 4):
+    blk = x.local_block(k)
+    blk.copy_(torch.arange(5, dtype=torch.float64, device="cuda")[:, None] * 1000 + torch.arange(x.lo, x.hi, dtype=torch.float64, device="cuda")[None, :] + k * 0.5)
+    x.push(k)
+    want = torch.arange(5, dtype=torch.float64, device="cuda")[:, None] * 1000 + torch.arange(C7, dtype=torch.float64, device="cuda")[None, :] + k * 0.5
+    same = torch.equal(x.gathered(k), want)
+    ok = ok and same
+    if rank == 0:
+        print(f"uneven exchange step {k}: {same}")
+x.raise_if_timed_out()
+x.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 td.all_reduce(flag, op=td.ReduceOp.MIN)
 sw.close()
