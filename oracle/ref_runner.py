@@ -1,8 +1,9 @@
 """Runs the UNMODIFIED reference (qyber-black/Code-RobChar) on the host CPU, for timing and cross-checks.
 
 THIS IS TEST / BENCHMARK INFRASTRUCTURE, NOT PRODUCT CODE.  The reference's own .py files are never committed:
-``__graft_entry__.build()`` stages them, where ``/root/reference`` is mounted (the build container), into the
-git-ignored ``oracle/_ref/`` — which travels to the GPU box with the snapshot like the built ``.so`` does.  Only
+``__graft_entry__.build()`` packs them UNMODIFIED, where ``/root/reference`` is mounted (the build container), into
+one archive ``oracle/_ref/reference_modules.zip`` (imported with zipimport) inside the git-ignored ``oracle/_ref/`` —
+which travels to the GPU box with the snapshot like the built ``.so`` does.  Only
 ``bench.py`` (``cpu_baseline`` / ``--impl reference`` legs) and ``tests/`` import this module.
 
 The reference imports plotting / optimiser packages that are not installed here (matplotlib, seaborn, IPython,
@@ -21,21 +22,29 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
+REF_ZIP = os.path.join(REF_DIR, "reference_modules.zip")
 STAGED_DATA = ["noisy_analysis/lbfgs_spin_4_0-2_in", "noisy_analysis/lbfgs_spin_7_0-6_in"]
 _STUBS = ["matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.ticker", "seaborn", "IPython",
           "IPython.display", "skquant", "skquant.opt", "SQSnobFit"]
 
 
 def stage(reference_root: str = "/root/reference") -> bool:
-    """Copy the reference's top-level .py files and two small controller files into oracle/_ref/ (build container
-    only).  Returns True when the staged tree is usable."""
+    """Pack the reference's top-level .py files into oracle/_ref/reference_modules.zip and copy two small controller
+    files next to it (build container only).  Returns True when the staged tree is usable."""
     import shutil
+    import zipfile
     if not os.path.isdir(reference_root):
         return available()
     os.makedirs(os.path.join(REF_DIR, "noisy_analysis"), exist_ok=True)
-    for fn in sorted(os.listdir(reference_root)):
-        if fn.endswith(".py") and fn != "rim_analysis.py":        # rim_analysis.py plots at import; never needed
-            shutil.copyfile(os.path.join(reference_root, fn), os.path.join(REF_DIR, fn))
+    tmp = REF_ZIP + ".tmp"
+    with zipfile.ZipFile(tmp, "w", zipfile.ZIP_DEFLATED) as zf:
+        for fn in sorted(os.listdir(reference_root)):
+            if fn.endswith(".py") and fn != "rim_analysis.py":    # rim_analysis.py plots at import; never needed
+                zf.write(os.path.join(reference_root, fn), fn)
+    os.replace(tmp, REF_ZIP)
+    for fn in os.listdir(REF_DIR):                                 # loose copies of an earlier staging layout
+        if fn.endswith(".py"):
+            os.remove(os.path.join(REF_DIR, fn))
     for rel in STAGED_DATA:
         src = os.path.join(reference_root, rel)
         if os.path.exists(src):
@@ -44,14 +53,14 @@ def stage(reference_root: str = "/root/reference") -> bool:
 
 
 def available() -> bool:
-    return os.path.exists(os.path.join(REF_DIR, "noise_model.py")) and os.path.exists(os.path.join(REF_DIR, "mcsim.py"))
+    return os.path.exists(REF_ZIP)
 
 
 def _import_reference(full: bool = False):
     """noise_model (always) and, with `full`, mcsim / wd_sortof_fast_implementation of the staged reference."""
     sys.dont_write_bytecode = True
-    if REF_DIR not in sys.path:
-        sys.path.insert(0, REF_DIR)
+    if REF_ZIP not in sys.path:
+        sys.path.insert(0, REF_ZIP)
     import noise_model as ref_nm
     if not full:
         return ref_nm, None, None
