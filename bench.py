@@ -382,7 +382,9 @@ def run_ours(args):
                                                     seed=seed, fused=fused, zz=zz, copy=False)
         return obj.step_host(ctrl_pinned, sig_host, seed=seed)
 
-    if not big:
+    if args.skip_e2e:
+        e2e_steps = 0
+    if not big and e2e_steps:
         for k in range(max(1, args.warmup // 2)):
             e2e_step(k)
     sweep.finish()
@@ -410,7 +412,7 @@ def run_ours(args):
 
     evals_step_total = S * C_total * B
     value = evals_step_total * args.steps / (ms * 1e-3)
-    e2e_value = evals_step_total * e2e_steps / (e2e_total_ms * 1e-3)
+    e2e_value = evals_step_total * e2e_steps / (e2e_total_ms * 1e-3) if e2e_steps else None
     if rank != 0:
         sweep.close()
         if world > 1:
@@ -457,8 +459,8 @@ def run_ours(args):
                         "note": "CUDA events at step boundaries on each rank's compute stream; exchange_tail = wait for the "
                                 "last step's peer blocks after the loop (the exchange of the other steps is overlapped)"},
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_total_ms / e2e_steps, "steps": e2e_steps,
-                "step_ms_min_median_max": [float(np.min(e2e_step_ms)), float(np.median(e2e_step_ms)), float(np.max(e2e_step_ms))],
+                "ms_per_step": e2e_total_ms / e2e_steps if e2e_steps else None, "steps": e2e_steps,
+                "step_ms_min_median_max": [float(np.min(e2e_step_ms)), float(np.median(e2e_step_ms)), float(np.max(e2e_step_ms))] if e2e_steps else None,
                 "api": ("robchar_b200.rim_analysis.robustness_sweep -> rc_robustness_sweep_host (one C call, host buffers in/out)"
                         if world == 1 and not args.e2e_sharded_api else
                         "robchar_b200.dist.ShardedRobustnessSweep.step_host -> rc_robustness_sweep_host_keep (one C call per rank, "
@@ -466,7 +468,7 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_value, "unit": "evals/s", "cores": procs, "kind": kind,
                          "sample": cpu_sample_text(kind, procs, args.cpu_evals, nspin) + f", {cpu_wall:.1f} s wall"},
-        "sweep_wall_s": {"device": ms / args.steps * 1e-3, "e2e": e2e_total_ms / e2e_steps * 1e-3},
+        "sweep_wall_s": {"device": ms / args.steps * 1e-3, "e2e": e2e_total_ms / e2e_steps * 1e-3 if e2e_steps else None},
         "spectral_fallbacks": eng.spectral_fallbacks() if nspin >= 11 else None,
     }
     if world == 1 and args.workload == "paper_n7" and not args.no_mcdatasim:
@@ -491,6 +493,7 @@ def main():
     ap.add_argument("--cpu-evals", type=int, default=30000, help="evaluations per CPU worker in the baseline sample")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU exchange of the statistics blocks")
     ap.add_argument("--e2e-sharded-api", action="store_true", help="time ShardedRobustnessSweep.step_host at N=1 as well")
+    ap.add_argument("--skip-e2e", action="store_true", help="table cells of the full-size workloads: skip the second (host-buffer) pass; e2e.value is null")
     ap.add_argument("--no-mcdatasim", action="store_true", help="skip the MCDataSim.get_metrics_dict wall-time leg")
     ap.add_argument("--paper-group", action="store_true", help="also time one paper-size group (11x1000x100) through MCDataSim (~80 s of CPU)")
     args = ap.parse_args()
