@@ -26,10 +26,6 @@ def launch_count() -> int:
     return int(lib().rc_launch_count())
 
 
-def _count(n: int) -> None:
-    """(kept as a no-op: launches are counted inside the library)"""
-
-
 def require_cuda() -> torch.device:
     if not torch.cuda.is_available():
         raise _lib.RobcharLibraryError("robchar_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
@@ -110,7 +106,6 @@ def fidelity_mc(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, *, 
     check(lib().rc_fidelity_mc(_ptr(ctrl), Cn, nspin, inspin, outspin, _ptr(sigmas), S, B, model, int(bool(zz)),
                                C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, _ptr(replay), _ptr(out),
                                counters.nonconv_ptr, _stream()))
-    _count(1)
     if own and check_convergence:
         counters.raise_if_set()
     return out
@@ -168,7 +163,6 @@ def fidelity_mc_stats(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: in
                                           int(bool(zz)), C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, _ptr(replay),
                                           float(dkw_eps), _ptr(out), _ptr(st), counters.nonconv_ptr, counters.illegal_ptr,
                                           _stream()))
-    _count(2)
     if own and check:
         counters.raise_if_set()
     return out, st
@@ -185,7 +179,6 @@ def stats_unsorted(fids: torch.Tensor, dkw_eps: float = 0.0, *, check_legal: boo
     out = torch.empty((NUM_STATS,) + lead, dtype=torch.float64, device=dev)
     cnt = Counters(dev)
     _lib.check(lib().rc_stats_unsorted(_ptr(fids), nseg, B, float(dkw_eps), _ptr(out), cnt.illegal_ptr, _stream()))
-    _count(1)
     if check_legal:
         cnt.raise_if_set()
     return out
@@ -216,7 +209,6 @@ def rim_p(fids, p: float = 2, *, check_legal: bool = True) -> torch.Tensor:
     out = torch.empty(lead if lead else (1,), dtype=torch.float64, device=dev)
     cnt = Counters(dev)
     check(lib().rc_rim_p(_ptr(fids), nseg, B, float(p), _ptr(out), cnt.illegal_ptr, _stream()))
-    _count(1)
     if check_legal:
         cnt.raise_if_set()
     return out if lead else out.reshape(())
@@ -248,7 +240,6 @@ def stats(fids: torch.Tensor, dkw_eps: float = 0.0, *, sort_inplace: bool = Fals
     cnt = Counters(dev)
     check(lib().rc_stats(_ptr(fids), nseg, B, float(dkw_eps), _ptr(out), _ptr(fids) if sort_inplace else C.c_void_p(0),
                          cnt.illegal_ptr, _ptr(ws), wb, _stream()))
-    _count(1 if B <= 4096 else 2 * max(1, -(-nseg // max(1, (1 << 28) // B))))
     if check_legal:
         cnt.raise_if_set()
     return out
@@ -271,7 +262,6 @@ def fidelity_stats(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, 
     check(lib().rc_fidelity_stats(_ptr(ctrl), Cn, nspin, inspin, outspin, _ptr(sigmas), S, B, model, int(bool(zz)),
                                   C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, _ptr(replay), float(dkw_eps),
                                   _ptr(out), cnt.nonconv_ptr, _ptr(ws), wb, _stream()))
-    _count(2)
     if check_convergence:
         cnt.raise_if_set()
     return out
@@ -296,7 +286,6 @@ def fidelity_stats_blocks(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin
     check(lib().rc_fidelity_stats_blocks(_ptr(ctrl), Cn, nspin, inspin, outspin, _ptr(sigmas), S, B, model, int(bool(zz)),
                                          C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, world, rank, float(dkw_eps),
                                          _ptr(out), cnt.nonconv_ptr, _ptr(ws), wb, _stream()))
-    _count(2)
     if counters is None:
         cnt.raise_if_set()
     return out
@@ -312,7 +301,6 @@ def stats_from_blocks(blocks: torch.Tensor, B: int, dkw_eps: float = 0.0) -> tor
     nseg = blocks.shape[1]
     out = torch.empty((NUM_STATS, nseg), dtype=torch.float64, device=dev)
     check(lib().rc_stats_from_blocks(_ptr(blocks), nseg, B, float(dkw_eps), _ptr(out), _stream()))
-    _count(1)
     return out
 
 
@@ -329,7 +317,6 @@ def ranks(values) -> torch.Tensor:
         raise ValueError("ranking problem too large")
     ws = torch.empty(wb, dtype=torch.uint8, device=dev)
     check(lib().rc_ranks(_ptr(v2), R, n, _ptr(out), _ptr(ws), wb, _stream()))
-    _count(2 if n <= 4096 else 3)
     return out.reshape(v.shape)
 
 
@@ -345,7 +332,6 @@ def clustered_ranks(values, alpha: float | None = 0.05, r: float | None = None) 
     ws = torch.empty(wb, dtype=torch.uint8, device=dev)
     a, rf = (-1.0, float(r)) if r is not None else (float(alpha), 0.0)
     check(lib().rc_clustered_ranks(_ptr(v2), R, n, a, rf, _ptr(out), _ptr(ws), wb, _stream()))
-    _count(2 if n <= 4096 else 3)
     return out.reshape(v.shape)
 
 
@@ -365,7 +351,6 @@ def kendall_tau_b(x, y) -> torch.Tensor:
     tau = torch.empty((Rx, Ry), dtype=torch.float64, device=dev)
     counts = torch.empty((Rx, Ry, 4), dtype=torch.int64, device=dev)
     check(lib().rc_kendall_tau_b(_ptr(x2), Rx, _ptr(y2), Ry, n, _ptr(tau), _ptr(counts), _stream()))
-    _count(2)
     return tau
 
 
@@ -392,7 +377,6 @@ def kendall_tau_b_batched(x: torch.Tensor, y: torch.Tensor, force_large: bool = 
         check(lib().rc_kendall_tau_b_large(_ptr(x), _ptr(y), G, Rx, Ry, n, _ptr(tau), _ptr(counts), _ptr(ws), wb, _stream()))
         return tau
     check(lib().rc_kendall_tau_b_batched(_ptr(x), _ptr(y), G, Rx, Ry, n, _ptr(tau), _ptr(counts), _stream()))
-    _count(2)
     return tau
 
 
@@ -418,7 +402,6 @@ def grouped_rank_consistency(W: torch.Tensor, groups: int, topk: int = 100, alph
     ws = torch.empty(wb, dtype=torch.uint8, device=dev)
     check(lib().rc_rank_consistency(_ptr(W), S, groups, Cg, topk, float(alpha), _ptr(tau), _ptr(sel), _ptr(Wsel),
                                     _ptr(ws), wb, _stream()))
-    _count(9)   # 2 argsort, mark, compact, gather, clustered walk, scatter, Kendall count + finalize
     return tau, sel, Wsel
 
 
@@ -451,7 +434,6 @@ def mc_sweep_host(ctrl: np.ndarray, sigmas: np.ndarray, B: int, nspin: int, insp
     check(lib().rc_mc_sweep_host(vp(ctrl), Cn, nspin, inspin, outspin, vp(sigmas), S, B, model, int(bool(zz)),
                                  C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, vp(replay), float(dkw_eps),
                                  int(bool(fused)), vp(fids_out), vp(stats_out), _stream()))
-    _count(2)
     return stats_out, fids_out
 
 
@@ -494,7 +476,6 @@ def robustness_sweep_host(ctrl: np.ndarray, sigmas: np.ndarray, B: int, nspin: i
                                          C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset, float(dkw_eps),
                                          int(bool(fused)), groups, topk, float(alpha_cluster), vp(st), vp(tau), vp(sel),
                                          int(nboot), vp(ar), vp(ars), _stream()))
-    _count(12)  # evolution + (finalize when fused | sort-free statistics otherwise) + 9 ranking kernels + ARIM bootstrap (per sigma chunk: +2)
     return st, tau, sel, ar, ars
 
 
@@ -524,7 +505,6 @@ def objective_host(x, rows, nspin: int, inspin: int, outspin: int, *, model: int
                                   float(dkw_eps), C.c_void_p(out.ctypes.data if want_fids else 0),
                                   C.c_void_p(st.ctypes.data if want_stats else 0),
                                   C.c_void_p(amps.ctypes.data if want_amps else 0), _stream()))
-    _count(2 if want_stats else 1)
     res = (out, st) if want_stats else (out,)
     if want_amps:
         res = res + (amps,)
@@ -563,7 +543,6 @@ class ObjectiveEvaluator:
         code = self._fn(*args)
         if code:
             check(code)
-        _count(1)
         return self
 
 
@@ -619,7 +598,6 @@ class RobustnessSweepPlan:
                                         _ptr(self.arim_std), self.counters.nonconv_ptr, _ptr(self.ws), self.wb,
                                         C.c_void_p(evolution_events[0].cuda_event if evolution_events else 0),
                                         C.c_void_p(evolution_events[1].cuda_event if evolution_events else 0), _stream()))
-        _count(12)  # evolution + (finalize when fused | sort-free statistics otherwise) + 9 ranking kernels + ARIM bootstrap
         return stats, self.tau
 
 
@@ -633,7 +611,6 @@ def arim_bootstrap_device(rims, nboot: int = 100, seed: int = 0):
     a = torch.empty(R, dtype=torch.float64, device=dev)
     s = torch.empty(R, dtype=torch.float64, device=dev)
     check(lib().rc_arim_bootstrap(_ptr(r2), R, k, int(nboot), C.c_uint64(seed & (2**64 - 1)), _ptr(a), _ptr(s), _stream()))
-    _count(1)
     return a.reshape(r.shape[:-1]), s.reshape(r.shape[:-1])
 
 
@@ -651,7 +628,6 @@ def expm_batch(A) -> torch.Tensor:
         raise ValueError("square matrices expected")
     out = torch.empty_like(A)
     check(lib().rc_expm_batch(_ptr(A), batch, M, _ptr(out), _stream()))
-    _count(1)
     return out
 
 
@@ -684,7 +660,6 @@ def fidelity_grad(X, nspin: int, inspin: int, outspin: int, *, rows=None, zz: bo
     err, grad = np.empty(Cn), np.empty((Cn, nspin + 1))
     check(lib().rc_fidelity_grad_host(C.c_void_p(X.ctypes.data), Cn, nspin, inspin, outspin, rp, int(bool(zz)),
                                       C.c_void_p(err.ctypes.data), C.c_void_p(grad.ctypes.data), _stream()))
-    _count(1)
     return err, grad
 
 

@@ -304,3 +304,21 @@ def test_lbfgs_objective_host_logic_matches_reference(monkeypatch):
     np.random.seed(13)
     ad = np.array([env.fidelity_ss(x, noisy=True, ham_noisy=False) for x in X])
     assert np.abs(ad - g["obj_adaptive"]).max() < 1e-12
+
+
+def test_oracle_port_equals_the_staged_unmodified_reference():
+    """The oracle's per-sample port (bench.py's fallback CPU arm) against the UNMODIFIED reference staged by build()
+    in oracle/_ref (the default CPU arm): same numpy seed, same controller -> the same fidelities, draw for draw."""
+    from oracle import ref_runner
+    if not ref_runner.available():
+        pytest.skip("reference not staged (no /root/reference at build time)")
+    ref_nm, _, _ = ref_runner._import_reference()
+    for n, i, o in [(4, 0, 2), (7, 0, 6)]:
+        x = orc.synthetic_controllers(3, n, seed=n)
+        np.random.seed(5)
+        ref = ref_nm.structured_perturbation(Nspin=n, inspin=i, outspin=o, noise=0.05)
+        want = [ref.evaluate_noisy_fidelity(x[k % 3], True) for k in range(12)]
+        np.random.seed(5)
+        port = orc.ReferencePathPort(n, i, o, 0.05)
+        got = [port.evaluate_noisy_fidelity(x[k % 3], True) for k in range(12)]
+        assert np.abs(np.array(got) - np.array(want)).max() < 1e-13
