@@ -103,6 +103,8 @@ int fused_reg_threads(int n, bool replay, long long B) {
 // multiple of 32 when fewer than 256 lanes fit (N >= 29: warp count matters more than balance).
 // RC_SMEM_THREADS (environment) overrides for tuning.
 constexpr size_t SMEM_BYTES_MAX = 227 * 1024;
+constexpr size_t ZIG_TABLE_BYTES = sizeof(ZigEntry) * ZIG_LAYERS;
+constexpr size_t WARP_STATIC_SMEM = (SMEM_MAX_THREADS / 32) * WACC_DOUBLES * sizeof(double);   // fidelity_stats_smem_warp_kernel
 constexpr size_t FUSED_STATIC_SMEM = (SMEM_FUSED_MAX_THREADS / 32) * PART_DOUBLES * sizeof(double);   // merge scratch
 static int smem_threads_bytes(size_t lane_bytes, int cap = SMEM_MAX_THREADS, size_t static_bytes = 0) {
     static int env = -1;
@@ -133,6 +135,12 @@ static int smem_algo(int n) {
         v = !s ? -1 : ((s[0] == 'v' || s[0] == '0') ? ALGO_VECTORS : ALGO_SPECTRAL);
     }
     return v >= 0 ? v : (n >= SPEC_MIN_N ? ALGO_SPECTRAL : ALGO_VECTORS);
+}
+// RC_SPEC_ZIGS=0 (environment) keeps the ziggurat table in global memory (A/B measurements)
+static bool spec_zigs_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* s = getenv("RC_SPEC_ZIGS"); v = (s && s[0] == '0') ? 0 : 1; }
+    return v != 0;
 }
 // bytes of shared memory per lane for a launch
 static size_t lane_bytes_for(int algo, int n, int in, int out) {
@@ -183,14 +191,20 @@ static cudaError_t launch_smem(const FidArgs& a0, int sm_count, cudaStream_t st)
         a.respec = respec_counter_device();
         // the CTA sizes the launcher picks (768 lanes for N <= 18, 640 to N = 22, 512 to N = 28, 384 above) have the stride
         // compiled in (Philox mode): shared-memory offsets become immediates
-        if (!REPLAY && !AMPS && threads == 768)
-            return launch_persistent(fidelity_smem_kernel<MODEL, false, false, ALGO_SPECTRAL, SMEM_MAX_THREADS, 768>, threads, smem, nblk, sm_count, st, &a);
-        if (!REPLAY && !AMPS && threads == 640)
-            return launch_persistent(fidelity_smem_kernel<MODEL, false, false, ALGO_SPECTRAL, SMEM_MAX_THREADS, 640>, threads, smem, nblk, sm_count, st, &a);
-        if (!REPLAY && !AMPS && threads == 512)
-            return launch_persistent(fidelity_smem_kernel<MODEL, false, false, ALGO_SPECTRAL, SMEM_WIDE_THREADS, 512>, threads, smem, nblk, sm_count, st, &a);
-        if (!REPLAY && !AMPS && threads == 384)
-            return launch_persistent(fidelity_smem_kernel<MODEL, false, false, ALGO_SPECTRAL, SMEM_WIDE_THREADS, 384>, threads, smem, nblk, sm_count, st, &a);
+        // ... and keep the ziggurat fast-path table behind the columns when the CTA has 16 KB to spare
+        const bool zigs = spec_zigs_enabled() && smem + ZIG_TABLE_BYTES <= SMEM_BYTES_MAX;
+        const size_t smz = smem + (zigs ? ZIG_TABLE_BYTES : 0);
+#define RC_SPEC_LAUNCH(T, MAXT)                                                                                          \
+        if (!REPLAY && !AMPS && threads == T)                                                                            \
+            return zigs ? launch_persistent(fidelity_smem_kernel<MODEL, false, false, ALGO_SPECTRAL, MAXT, T, true>,     \
+                                            threads, smz, nblk, sm_count, st, &a)                                        \
+                        : launch_persistent(fidelity_smem_kernel<MODEL, false, false, ALGO_SPECTRAL, MAXT, T, false>,    \
+                                            threads, smz, nblk, sm_count, st, &a);
+        RC_SPEC_LAUNCH(768, SMEM_MAX_THREADS)
+        RC_SPEC_LAUNCH(640, SMEM_MAX_THREADS)
+        RC_SPEC_LAUNCH(512, SMEM_WIDE_THREADS)
+        RC_SPEC_LAUNCH(384, SMEM_WIDE_THREADS)
+#undef RC_SPEC_LAUNCH
         if (threads <= SMEM_WIDE_THREADS)
             return launch_persistent(fidelity_smem_kernel<MODEL, REPLAY, AMPS, ALGO_SPECTRAL, SMEM_WIDE_THREADS>, threads, smem, nblk, sm_count, st, &a);
         return launch_persistent(fidelity_smem_kernel<MODEL, REPLAY, AMPS, ALGO_SPECTRAL>, threads, smem, nblk, sm_count, st, &a);
@@ -230,21 +244,26 @@ static cudaError_t launch_fused_smem_warp(const FusedArgs& g0, int sm_count, cud
     FusedArgs g = g0;
     const int algo = smem_algo(g.f.N);
     const size_t lane = lane_bytes_for(algo, g.f.N, g.f.in, g.f.out);
-    const int threads = smem_threads_bytes(lane, SMEM_MAX_THREADS, (SMEM_MAX_THREADS / 32) * WACC_DOUBLES * sizeof(double));
+    const int threads = smem_threads_bytes(lane, SMEM_MAX_THREADS, WARP_STATIC_SMEM);
     const size_t smem = lane * threads;
     const long long wpc = threads / 32;
     const long long nitems = (long long)g.f.S * g.f.C * g.nchunks;
     const long long need = (nitems + wpc - 1) / wpc;
     if (algo == ALGO_SPECTRAL) {
         g.f.respec = respec_counter_device();
-        if (threads == 768)
-            return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL, SMEM_MAX_THREADS, 768>, threads, smem, need, sm_count, st, &g);
-        if (threads == 640)
-            return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL, SMEM_MAX_THREADS, 640>, threads, smem, need, sm_count, st, &g);
-        if (threads == 512)
-            return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL, SMEM_WIDE_THREADS, 512>, threads, smem, need, sm_count, st, &g);
-        if (threads == 384)
-            return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL, SMEM_WIDE_THREADS, 384>, threads, smem, need, sm_count, st, &g);
+        const bool zigs = spec_zigs_enabled() && smem + WARP_STATIC_SMEM + ZIG_TABLE_BYTES <= SMEM_BYTES_MAX;
+        const size_t smz = smem + (zigs ? ZIG_TABLE_BYTES : 0);
+#define RC_SPEC_LAUNCH(T, MAXT)                                                                                          \
+        if (threads == T)                                                                                                \
+            return zigs ? launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL, MAXT, T, true>,        \
+                                            threads, smz, need, sm_count, st, &g)                                        \
+                        : launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL, MAXT, T, false>,       \
+                                            threads, smz, need, sm_count, st, &g);
+        RC_SPEC_LAUNCH(768, SMEM_MAX_THREADS)
+        RC_SPEC_LAUNCH(640, SMEM_MAX_THREADS)
+        RC_SPEC_LAUNCH(512, SMEM_WIDE_THREADS)
+        RC_SPEC_LAUNCH(384, SMEM_WIDE_THREADS)
+#undef RC_SPEC_LAUNCH
         if (threads <= SMEM_WIDE_THREADS)
             return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL, SMEM_WIDE_THREADS>, threads, smem, need, sm_count, st, &g);
         return launch_persistent(fidelity_stats_smem_warp_kernel<MODEL, ALGO_SPECTRAL>, threads, smem, need, sm_count, st, &g);

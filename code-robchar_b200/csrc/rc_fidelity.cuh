@@ -542,11 +542,23 @@ __host__ __device__ inline int spec_lane_doubles(int n, int in, int out) { retur
 // rounding order as build_tridiagonal / eval_smem).  Philox mode, complex model: three draws per site but two
 // columns — the imaginary coupling draw nn2_i is parked in the spare slot e[n-1] and folded into
 // e[i-1] = |1 + sigma nn_i + i sigma nn2_i| as soon as its Philox block is complete (a block holds at most one).
-template <int MODEL, bool REPLAY, int LD = 0>
+// ZIGS: the CTA keeps a copy of the 16 KB ziggurat fast-path table behind the lanes' columns in dynamic shared
+// memory (spec_zig_table; staged by the kernel) — at N = 16 a third of the noise generation's stall samples were
+// waits on the L1 / L2 path of the table look-ups (profiles/r02_ncu_fidelity_smem_spectral_final_summary.txt).
+template <int LD>
+__device__ __forceinline__ ZigEntry* spec_zig_table(const FidArgs& a) {
+    extern __shared__ double rc_spec_dyn_smem[];
+    return reinterpret_cast<ZigEntry*>(rc_spec_dyn_smem + (size_t)spec_lane_doubles(a.N, a.in, a.out) * LD);
+}
+
+template <int MODEL, bool REPLAY, int LD = 0, bool ZIGS = false>
 __device__ __noinline__ void build_spec(const FidArgs& a, long long s, long long c, long long b, const double* row,
                                         double* d, double* e, int ld_rt) {
+    static_assert(!ZIGS || (LD > 0 && !REPLAY), "the shared table copy exists in the LD-templated Philox kernels only");
     const int n = a.N, ld = LD ? LD : ld_rt;
     constexpr int P = draws_per_site(MODEL);
+    ZigTables zt = a.zig;
+    if (ZIGS) zt.kw = spec_zig_table<LD ? LD : 1>(a);
     const double* x = a.ctrl + c * (n + 1);
     const double sigma = __ldg(a.sigma + s);
     if (REPLAY) {
@@ -563,7 +575,7 @@ __device__ __noinline__ void build_spec(const FidArgs& a, long long s, long long
             }
         }
     } else if (MODEL == MODEL_REAL2) {
-        normals_fill(noise_key(a, s, c, b), P * n - (P - 1), a.zig, [&](int jc) -> double& {
+        normals_fill(noise_key(a, s, c, b), P * n - (P - 1), zt, [&](int jc) -> double& {
             const int site = jc == 0 ? 0 : 1 + (jc - 1) / P, kind = jc == 0 ? 0 : (jc - 1) % P;
             return *(kind == 0 ? d + (size_t)site * ld : e + (size_t)(site - 1) * ld);
         });
@@ -582,10 +594,10 @@ __device__ __noinline__ void build_spec(const FidArgs& a, long long s, long long
             const Philox4 r = philox_block(key, (uint32_t)p);
             const int j0 = 2 * p;
             bool miss;
-            *slot(j0) = zig_try(r.x, r.y, a.zig.kw, &miss);
+            *slot(j0) = zig_try(r.x, r.y, zt.kw, &miss);
             if (miss) pend = (pend << 8) | (uint32_t)(j0 + 1);
             if (j0 + 1 < nc) {
-                *slot(j0 + 1) = zig_try(r.z, r.w, a.zig.kw, &miss);
+                *slot(j0 + 1) = zig_try(r.z, r.w, zt.kw, &miss);
                 if (miss) pend = (pend << 8) | (uint32_t)(j0 + 2);
             }
             // the block's imaginary coupling draw, if any (jc = 3 i, i >= 1): uniform over the warp
@@ -596,7 +608,7 @@ __device__ __noinline__ void build_spec(const FidArgs& a, long long s, long long
                     const uint32_t jc = (pend & 0xFFu) - 1u;
                     pend >>= 8;
                     double* q = slot((int)jc);
-                    *q = zig_complete(key, jc, *q, a.zig);
+                    *q = zig_complete(key, jc, *q, zt);
                 }
             }
             if (fold) {
@@ -647,7 +659,7 @@ __device__ __noinline__ double2 spec_recompute(const FidArgs& a, bool mine, long
 
 // One evaluation per lane; ALL 32 lanes of the warp must call it converged (`valid` = this lane has work): the
 // rare evaluations whose spectral error estimate is rejected are recomputed inside the call (spec_recompute).
-template <int MODEL, bool REPLAY, bool AMPS = false, int LD = 0>
+template <int MODEL, bool REPLAY, bool AMPS = false, int LD = 0, bool ZIGS = false>
 __device__ __forceinline__ double eval_spec(const FidArgs& a, bool valid, long long s, long long c, long long b,
                                             const double* row /* global replay row */, double* sm) {
     const int n = a.N, ld = LD ? LD : (int)blockDim.x;   // LD: compile-time CTA size (immediate shared-memory offsets)
@@ -661,7 +673,7 @@ __device__ __forceinline__ double eval_spec(const FidArgs& a, bool valid, long l
     bool ok = true;
     if (valid) {
         T = fabs(__ldg(a.ctrl + c * (n + 1) + n));
-        build_spec<MODEL, REPLAY, LD>(a, s, c, b, row, d, e, ld);
+        build_spec<MODEL, REPLAY, LD, ZIGS>(a, s, c, b, row, d, e, ld);
         SpecBlocks xb;
         xb.xd = xd; xb.xe = xe; xb.na = lo; xb.nb = n - 1 - hi;
         for (int j = 0; j < lo; ++j) { xd[(size_t)j * ld] = d[(size_t)j * ld]; xe[(size_t)j * ld] = e[(size_t)j * ld]; }
@@ -686,9 +698,11 @@ __device__ __forceinline__ double eval_spec(const FidArgs& a, bool valid, long l
     return fma(re, re, im * im);
 }
 
-template <int MODEL, bool REPLAY, bool AMPS = false, int ALGO = ALGO_VECTORS, int MAXT = SMEM_MAX_THREADS, int LD = 0>
+template <int MODEL, bool REPLAY, bool AMPS = false, int ALGO = ALGO_VECTORS, int MAXT = SMEM_MAX_THREADS, int LD = 0,
+          bool ZIGS = false>
 __global__ void __launch_bounds__(MAXT, 1) fidelity_smem_kernel(FidArgs a) {
     extern __shared__ double sm[];
+    if (ZIGS) load_zig_table(a.zig.kw, spec_zig_table<LD ? LD : 1>(a));
     const long long K = (long long)draws_per_site(MODEL) * a.N;
     const long long total = (long long)a.S * a.C * a.B;
     // CTA-uniform trip count: the spectral evaluator is a warp-collective call
@@ -698,7 +712,7 @@ __global__ void __launch_bounds__(MAXT, 1) fidelity_smem_kernel(FidArgs a) {
         EvalIndex ix = decode_eval(valid ? ev : 0, a.C, a.B);
         const double* row = REPLAY ? a.replay + (valid ? ev : 0) * K : nullptr;
         if (ALGO == ALGO_SPECTRAL) {
-            const double f = eval_spec<MODEL, REPLAY, AMPS, LD>(a, valid, ix.s, ix.c, ix.b, row, sm);
+            const double f = eval_spec<MODEL, REPLAY, AMPS, LD, ZIGS>(a, valid, ix.s, ix.c, ix.b, row, sm);
             if (valid) a.fids[ev] = f;
         } else if (valid) {
             a.fids[ev] = eval_smem<MODEL, REPLAY, AMPS>(a, ix.s, ix.c, ix.b, row, sm);
@@ -707,9 +721,10 @@ __global__ void __launch_bounds__(MAXT, 1) fidelity_smem_kernel(FidArgs a) {
 }
 
 // Warp-autonomous fused variant of the shared-memory kernel (Philox mode): see fidelity_stats_reg_warp_kernel.
-template <int MODEL, int ALGO = ALGO_VECTORS, int MAXT = SMEM_MAX_THREADS, int LD = 0>
+template <int MODEL, int ALGO = ALGO_VECTORS, int MAXT = SMEM_MAX_THREADS, int LD = 0, bool ZIGS = false>
 __global__ void __launch_bounds__(MAXT, 1) fidelity_stats_smem_warp_kernel(FusedArgs g) {
     extern __shared__ double sm[];
+    if (ZIGS) load_zig_table(g.f.zig.kw, spec_zig_table<LD ? LD : 1>(g.f));
     __shared__ double wacc_all[(SMEM_MAX_THREADS / 32) * WACC_DOUBLES];
     double* wacc = wacc_all + (threadIdx.x >> 5) * WACC_DOUBLES;
     const FidArgs& a = g.f;
@@ -725,7 +740,7 @@ __global__ void __launch_bounds__(MAXT, 1) fidelity_stats_smem_warp_kernel(Fused
             const long long b = bt + lane;
             const bool valid = b < b1;
             double f = 0.0;
-            if (ALGO == ALGO_SPECTRAL) f = eval_spec<MODEL, false, false, LD>(a, valid, s, c, b, nullptr, sm);
+            if (ALGO == ALGO_SPECTRAL) f = eval_spec<MODEL, false, false, LD, ZIGS>(a, valid, s, c, b, nullptr, sm);
             else if (valid) f = eval_smem<MODEL, false>(a, s, c, b, nullptr, sm);
             warp_acc_pass(wacc, bt == b0, valid, f, g.eps);
         }
