@@ -46,6 +46,18 @@ RC_HD double rc_rsqrt(double h) {
 #endif
 }
 
+// Same value to within rounding, one level less on the dependent chain: (y e) (1/2 + 3 e / 8) + y.
+RC_HD double rc_rsqrt_short(double h) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(h));
+    const double e = fma(-(h * y), y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+#else
+    return 1.0 / sqrt(h);
+#endif
+}
+
 // sqrt(x) for x >= 0 (x = 0 gives 0): x * rsqrt(x) plus one Heron correction (<= 1 ulp).
 RC_HD double rc_sqrt(double x) {
 #if defined(__CUDA_ARCH__)

@@ -64,17 +64,23 @@ RC_HD int ql_eigenvalues_strided(double* d, double* e, int ld_rt, int n, int tol
                 const double ein = *(pe - ld), din = *(pd - ld);   // operands of rotation i-1 (pad row when i = 0)
                 const double f = s * ei, b = c * ei;
                 const double h = fma(f, f, fma(g, g, tiny));
-                const double rinv = rc_rsqrt(h);
+                // Two levels off the dependent chain at the same operation count: 2b is ready before c, and the
+                // cubic correction of 1/sqrt(h) multiplies y e and (1/2 + 3e/8) side by side (rc_rsqrt_short).
+                // Measured on B200 (profiles/README.md, r02x): +0.4 % at N = 16 (six warps per scheduler hide the
+                // chain), +2.4 % at N = 28 / 32 (three).  Taking (di - g') f + 2 g b out of the chain as well costs
+                // one more multiplication: +2.9 % at N = 32 but -0.7 % at N = 16 — not taken.
+                const double b2 = b + b;
+                const double gp = d_up - p, dg = di - gp;
+                const double rinv = rc_rsqrt_short(h);
                 r = h * rinv;
                 pe[ld] = r;
                 rmin = hi_word(r) < rmin ? hi_word(r) : rmin;
                 s = f * rinv;
                 c = g * rinv;
-                g = d_up - p;
-                r = fma(di - g, s, (2.0 * c) * b);
+                r = fma(dg, s, c * b2);
                 p = s * r;
-                pd[ld] = g + p;
-                g = c * r - b;
+                pd[ld] = gp + p;
+                g = fma(c, r, -b);
                 d_up = di;
                 ei = ein; di = din;
                 pe -= ld; pd -= ld;
