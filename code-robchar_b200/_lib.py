@@ -82,6 +82,7 @@ _SIGNATURES = {
     "rc_mc_sweep_host": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64, _vp, _f64,
                                    _i32, _vp, _vp, _vp]),
     "rc_objective_host": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp]),
+    "rc_objective_release": (C.c_int, []),
     "rc_fidelity_grad": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "rc_fidelity_grad_host": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
     "rc_dense_fidelity_mc_workspace_bytes": (_sz, [_i32, _i64]),

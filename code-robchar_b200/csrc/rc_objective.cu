@@ -34,17 +34,27 @@ __device__ __forceinline__ double ld_sys(const double* p) {
     return v;
 }
 
+// One request: stage the inputs, one matrix per lane, the 15 statistics, results + flag through the mapping.
+// Called by every thread of the CTA.
 template <int MODEL>
-__global__ void __launch_bounds__(256) objective_kernel(ObjParams q) {
-    extern __shared__ double sm[];
+__device__ __forceinline__ void objective_body(const ObjParams& q, double* sm) {
     const int n = q.N, ld = blockDim.x, lane = threadIdx.x;
     double* inp = sm + (size_t)4 * n * ld;                               // [x (n+1)] [sigma] [rows m*K]
     double* fs = inp + (n + 2) + (q.has_rows ? (size_t)q.m * q.K : 0);   // fidelities of the m evaluations
     const int nin = n + 2 + (q.has_rows ? q.m * q.K : 0);
-    for (int k = lane; k < nin; k += ld) inp[k] = ld_sys(q.in + k);
+    // reads through the mapping cost a PCIe round trip each: four in flight per lane before the first one is used
+    for (int k0 = lane; k0 < nin; k0 += 4 * ld) {
+        double r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] = (k0 + u * ld < nin) ? ld_sys(q.in + k0 + u * ld) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (k0 + u * ld < nin) inp[k0 + u * ld] = r[u];
+    }
     __shared__ unsigned nonconv;
     if (lane == 0) nonconv = 0;
     __syncthreads();
+    // one fidelity and nothing else wanted: it travels WITH the sequence flag in one 16-byte store (no fence)
+    const bool fast_publish = q.m == 1 && !q.want_stats && !q.want_amps;
     constexpr int P = draws_per_site(MODEL);
     if (lane < q.m) {
         double* d = sm + lane;
@@ -75,7 +85,7 @@ __global__ void __launch_bounds__(256) objective_kernel(ObjParams q) {
         if (fail) atomicAdd(&nonconv, 1u);
         const double f = fma(re, re, im * im);
         fs[lane] = f;
-        q.out[lane] = f;
+        if (!fast_publish) q.out[lane] = f;
         if (q.want_amps) {
             q.out[q.m + RC_NUM_STATS + 2 * lane] = re;
             q.out[q.m + RC_NUM_STATS + 2 * lane + 1] = im;
@@ -131,9 +141,125 @@ __global__ void __launch_bounds__(256) objective_kernel(ObjParams q) {
     }
     __syncthreads();
     if (lane == 0) {
-        q.flag[1] = nonconv;
+        // flag words: [0] sequence, [1] the fidelity of a fast publish, [3] non-convergence count (written only when
+        // non-zero; the host clears it after reading)
+        if (nonconv) { *(volatile unsigned long long*)(q.flag + 3) = nonconv; __threadfence_system(); }
+        if (fast_publish) {
+            asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(q.flag), "l"(q.seq),
+                         "l"((unsigned long long)__double_as_longlong(fs[0]))
+                         : "memory");
+        } else {
+            __threadfence_system();
+            *(volatile unsigned long long*)q.flag = q.seq;
+        }
+    }
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(256) objective_kernel(ObjParams q) {
+    extern __shared__ double sm[];
+    objective_body<MODEL>(q, sm);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Resident server: an optimiser loop calls the objective every few tens of microseconds, and ~10 us of each
+// one-shot call are the kernel launch.  The server is ONE CTA that stays on the device between calls: lane 0 polls
+// a request sequence number in the pinned mailbox, the CTA then reads the request through the mapping, evaluates
+// it with the same code as the one-shot kernel and publishes results + flag.  It leaves by itself after
+// `idle_ns` without a request (so device-wide synchronisations wait at most that long), announcing it in the
+// mailbox: state = EXITING, one last look at the request word (a request posted in that window is still served),
+// state = EXITED.  The host relaunches it when it finds it gone.
+// Mailbox words (8 bytes each): device -> host [0] done sequence, [1] the fidelity of a one-value answer, [2] state,
+// [3] non-convergence count; host -> device [16] request sequence, [17] m | flags << 32 (flag bits: 1 statistics,
+// 2 amplitudes, 4 rows present, 8 leave), [18] dkw eps — one 32-byte sector, read by one coalesced load;
+// [SRV_IN..) inputs [x (N+1)] [sigma] [rows m*K], then (next 128-byte line) outputs [fids m] [stats 15] [amps 2m].
+// Measured on B200 (tools/server_probe.py): every extra warp that read the three header words itself added 2.4-3.5 us
+// to a call, ten dependent 256-byte input reads 11 us — reads through the mapping are issued as few, as wide and as
+// early as possible.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SRV_REQ = 16, SRV_HDR = 17, SRV_EPS = 18, SRV_IN = 32;
+// outputs start on their own 128-byte line behind the inputs
+__host__ __device__ inline size_t srv_out_offset(int n, long long m_rows, int K) {
+    return ((size_t)(n + 2) + (size_t)m_rows * K + 15) / 16 * 16;
+}
+constexpr unsigned long long SRV_RUNNING = 1, SRV_EXITING = 2, SRV_EXITED = 3;   // state = generation * 4 + one of these
+
+struct SrvParams {
+    unsigned long long* ctl;      // mapped mailbox
+    unsigned long long start_seq; // last request already answered
+    unsigned long long idle_ns, gen;
+    int N, in_site, out_site, K, zz;
+};
+
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(256) objective_server_kernel(SrvParams p) {
+    extern __shared__ double sm[];
+    __shared__ unsigned long long s_seq, s_hdr, s_eps;
+    __shared__ int s_last;
+    const int lane = threadIdx.x;
+    unsigned long long done = p.start_seq;
+    volatile unsigned long long* ctl = p.ctl;
+    if (lane == 0) ctl[2] = p.gen * 4 + SRV_RUNNING;
+    bool last = false;
+    while (!last) {
+        if (lane < 32) {
+            // warp 0 polls: lanes 0..2 read {request sequence, header, eps} — one 32-byte sector, one PCIe read.
+            // (Reads through the mapping are expensive and those of one line do not overlap: nobody else reads it.)
+            unsigned long long w = 0, v, t0 = global_ns();
+            int leaving = 0;
+            for (;;) {
+                if (lane < 3) w = ld_sys_u64(p.ctl + SRV_REQ + lane);
+                v = __shfl_sync(0xffffffffu, w, 0);
+                if (v != done) break;
+                if (leaving) { v = 0; break; }
+                if (global_ns() - t0 > p.idle_ns) {          // idle: announce, then look once more
+                    if (lane == 0) { ctl[2] = p.gen * 4 + SRV_EXITING; __threadfence_system(); }
+                    leaving = 1;
+                }
+                leaving = __shfl_sync(0xffffffffu, leaving, 0);
+            }
+            const unsigned long long hdr = __shfl_sync(0xffffffffu, w, 1), eps = __shfl_sync(0xffffffffu, w, 2);
+            if (lane == 0) { s_seq = v; s_hdr = hdr; s_eps = eps; s_last = leaving; }
+        }
+        __syncthreads();
+        const unsigned long long v = s_seq;
+        last = s_last != 0;
+        if (v != 0 && v != done) {
+            const unsigned long long hdr = s_hdr;
+            ObjParams q;
+            q.m = (int)(hdr & 0xffffffffull);
+            const unsigned flags = (unsigned)(hdr >> 32);
+            q.want_stats = flags & 1; q.want_amps = (flags >> 1) & 1; q.has_rows = (flags >> 2) & 1;
+            q.eps = __longlong_as_double((long long)s_eps);
+            q.N = p.N; q.in_site = p.in_site; q.out_site = p.out_site; q.K = p.K; q.zz = p.zz;
+            q.in = reinterpret_cast<const double*>(p.ctl + SRV_IN);
+            q.out = reinterpret_cast<double*>(p.ctl + SRV_IN) + srv_out_offset(p.N, q.has_rows ? q.m : 0, p.K);
+            q.flag = p.ctl;
+            q.seq = v;
+            if (flags & 8u) {                                 // leave
+                last = true;
+                if (lane == 0) { __threadfence_system(); ctl[0] = v; }
+            } else if (q.m >= 1 && q.m <= (int)blockDim.x) {
+                objective_body<MODEL>(q, sm);
+            }
+            done = v;
+        }
+        __syncthreads();
+    }
+    if (lane == 0) {
         __threadfence_system();
-        *(volatile unsigned long long*)q.flag = q.seq;
+        ctl[2] = p.gen * 4 + SRV_EXITED;
     }
 }
 
@@ -263,15 +389,15 @@ static int objective_host_fast(const double* x_host, int nspin, int inspin, int 
     const size_t n_in = (size_t)(nspin + 2) + (rows_host ? (size_t)m * K : 0);
     const size_t n_out = (size_t)m + RC_NUM_STATS + 2 * (size_t)m;
     Mailbox* mb = nullptr;
-    RC_CUDA_TRY(mailbox((2 + n_in + n_out) * 8, &mb));
+    RC_CUDA_TRY(mailbox((16 + n_in + n_out) * 8, &mb));
     double* hp = (double*)mb->host;
     volatile unsigned long long* hflag = (volatile unsigned long long*)mb->host;
-    memcpy(hp + 2, x_host, (size_t)(nspin + 1) * 8);
-    hp[2 + nspin + 1] = rows_host ? 1.0 : 0.0;              // rows are explicit perturbations (sigma 1); none: sigma 0
-    if (rows_host) memcpy(hp + 2 + nspin + 2, rows_host, (size_t)m * K * 8);
+    memcpy(hp + 16, x_host, (size_t)(nspin + 1) * 8);
+    hp[16 + nspin + 1] = rows_host ? 1.0 : 0.0;             // rows are explicit perturbations (sigma 1); none: sigma 0
+    if (rows_host) memcpy(hp + 16 + nspin + 2, rows_host, (size_t)m * K * 8);
     ObjParams q;
-    q.in = (const double*)mb->dev + 2;
-    q.out = (double*)mb->dev + 2 + n_in;
+    q.in = (const double*)mb->dev + 16;
+    q.out = (double*)mb->dev + 16 + n_in;
     q.flag = (unsigned long long*)mb->dev;
     q.seq = ++mb->seq;
     q.N = nspin; q.in_site = inspin; q.out_site = outspin; q.m = (int)m; q.K = K; q.zz = zz;
@@ -297,12 +423,190 @@ static int objective_host_fast(const double* x_host, int nspin, int inspin, int 
         }
     }
     __sync_synchronize();
-    const double* op = hp + 2 + n_in;
-    const unsigned long long nonconv = hflag[1];
+    const double* op = hp + 16 + n_in;
+    const unsigned long long nonconv = hflag[3];
+    if (nonconv) hflag[3] = 0;
+    if (m == 1 && !stats_host && !amps_host) op = hp + 1;   // the one-value answer came with the flag
     if (fids_host) memcpy(fids_host, op, (size_t)m * 8);
     if (stats_host) memcpy(stats_host, op + m, (size_t)RC_NUM_STATS * 8);
     if (amps_host) memcpy(amps_host, op + m + RC_NUM_STATS, 2 * (size_t)m * 8);
     if (nonconv) return set_error(RC_ERR_NONCONV, "eigensolver did not converge for %llu evaluations (NaN written)", nonconv);
+    return RC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side of the resident server (one per host thread and device).
+// ---------------------------------------------------------------------------------------------------------------
+namespace rc {
+struct Server {
+    char* host = nullptr;
+    char* dev = nullptr;
+    size_t bytes = 0;
+    cudaStream_t st = nullptr;
+    unsigned long long seq = 0, gen = 0;
+    bool launched = false, broken = false;
+    int model = -1, N = 0, in = 0, out = 0, zz = 0, threads = 0;
+    int smem_set[2] = {0, 0};
+};
+static Server* server_slot() {
+    static thread_local Server cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    return &cache[dev];
+}
+// RC_OBJECTIVE_SERVER=0 keeps the one-shot launches; RC_OBJECTIVE_IDLE_US = idle time after which the server leaves
+static bool server_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* s = getenv("RC_OBJECTIVE_SERVER"); v = (s && s[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+static unsigned long long server_idle_ns() {
+    static long long v = -1;
+    if (v < 0) { const char* s = getenv("RC_OBJECTIVE_IDLE_US"); v = s ? atoll(s) : 1000; if (v < 1) v = 1; if (v > 1000000) v = 1000000; }
+    return (unsigned long long)v * 1000ull;
+}
+static bool server_alive(const Server& sv) {
+    return sv.launched && ((volatile unsigned long long*)sv.host)[2] != sv.gen * 4 + SRV_EXITED;
+}
+// waits until the server has answered request `seq` or is gone; 0 = answered, 1 = gone without answering, 2 = timeout
+static int server_wait(const Server& sv, unsigned long long seq, double timeout_s) {
+    volatile unsigned long long* c = (volatile unsigned long long*)sv.host;
+    const double t0 = now_s();
+    unsigned spins = 0;
+    for (;;) {
+        if (c[0] == seq) return 0;
+        if (c[2] == sv.gen * 4 + SRV_EXITED) return c[0] == seq ? 0 : 1;
+        if ((++spins & 0xFFFu) == 0 && now_s() - t0 > timeout_s) return 2;
+    }
+}
+static cudaError_t server_launch(Server& sv, int model, int N, int in, int out, int zz, int threads, int K) {
+    const size_t smem = ((size_t)4 * N * threads + (size_t)(N + 2) + (size_t)threads * K + (size_t)threads) * 8;
+    const int mi = model == RC_MODEL_COMPLEX3 ? 0 : 1;
+    cudaError_t e;
+    if (smem > 40 * 1024 && sv.smem_set[mi] < (int)OBJ_SMEM_MAX) {
+        e = mi == 0 ? cudaFuncSetAttribute(objective_server_kernel<MODEL_COMPLEX3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OBJ_SMEM_MAX)
+                    : cudaFuncSetAttribute(objective_server_kernel<MODEL_REAL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OBJ_SMEM_MAX);
+        if (e != cudaSuccess) return e;
+        sv.smem_set[mi] = (int)OBJ_SMEM_MAX;
+    }
+    SrvParams p;
+    p.ctl = (unsigned long long*)sv.dev;
+    p.start_seq = sv.seq;
+    p.idle_ns = server_idle_ns();
+    p.gen = ++sv.gen;
+    p.N = N; p.in_site = in; p.out_site = out; p.K = K; p.zz = zz;
+    volatile unsigned long long* c = (volatile unsigned long long*)sv.host;
+    c[2] = sv.gen * 4 + SRV_RUNNING;
+    c[SRV_REQ] = sv.seq;
+    __sync_synchronize();
+    if (mi == 0) objective_server_kernel<MODEL_COMPLEX3><<<1, threads, smem, sv.st>>>(p);
+    else objective_server_kernel<MODEL_REAL2><<<1, threads, smem, sv.st>>>(p);
+    rc::note_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    sv.launched = true;
+    sv.model = model; sv.N = N; sv.in = in; sv.out = out; sv.zz = zz; sv.threads = threads;
+    return cudaSuccess;
+}
+// asks a live server to leave and waits for the stream to drain
+static void server_quit(Server& sv) {
+    if (!sv.launched) return;
+    if (server_alive(sv)) {
+        volatile unsigned long long* c = (volatile unsigned long long*)sv.host;
+        c[SRV_HDR] = 8ull << 32;
+        __sync_synchronize();
+        c[SRV_REQ] = ++sv.seq;
+    }
+    cudaStreamSynchronize(sv.st);
+    sv.launched = false;
+}
+}  // namespace rc
+
+// 0 = served; -1 = not applicable / server unusable (the caller takes the one-shot path); > 0 = error code
+static int objective_host_server(const double* x_host, int nspin, int inspin, int outspin, const double* rows_host, int64_t m,
+                                 int model, int zz, double dkw_eps, double* fids_host, double* stats_host, double* amps_host,
+                                 int K) {
+    Server* svp = server_slot();
+    if (!svp || svp->broken) return -1;
+    Server& sv = *svp;
+    int need_threads = (int)((m + 31) / 32 * 32);
+    {   // RC_OBJECTIVE_MIN_THREADS (environment): CTA size floor of the resident evaluator (tuning)
+        static int floor_t = -1;
+        if (floor_t < 0) { const char* e = getenv("RC_OBJECTIVE_MIN_THREADS"); floor_t = e ? atoi(e) : 0; if (floor_t < 0 || floor_t > OBJ_MAX_LANES) floor_t = 0; floor_t = floor_t / 32 * 32; }
+        if (need_threads < floor_t) need_threads = floor_t;
+    }
+    const bool same = sv.launched && sv.model == model && sv.N == nspin && sv.in == inspin && sv.out == outspin && sv.zz == zz;
+    int threads = same && sv.threads >= need_threads ? sv.threads : need_threads;
+    if (same && sv.threads > threads) threads = sv.threads;
+    const size_t smem = ((size_t)4 * nspin * threads + (size_t)(nspin + 2) + (size_t)threads * K + (size_t)threads) * 8;
+    if (smem > OBJ_SMEM_MAX) return -1;
+    const size_t words = SRV_IN + srv_out_offset(nspin, threads, K) + (size_t)threads + RC_NUM_STATS + 2 * (size_t)threads;
+    if (!sv.st && cudaStreamCreateWithFlags(&sv.st, cudaStreamNonBlocking) != cudaSuccess) { sv.broken = true; return -1; }
+    if (sv.bytes < words * 8) {
+        server_quit(sv);
+        if (sv.host) cudaFreeHost(sv.host);
+        sv.host = sv.dev = nullptr; sv.bytes = 0;
+        size_t cap = 1 << 16;
+        while (cap < words * 8) cap *= 2;
+        if (cudaHostAlloc((void**)&sv.host, cap, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void**)&sv.dev, sv.host, 0) != cudaSuccess) { sv.broken = true; cudaGetLastError(); return -1; }
+        memset(sv.host, 0, cap);
+        sv.bytes = cap;
+        sv.seq = 0;
+    }
+    if (sv.launched && !(same && sv.threads == threads)) server_quit(sv);
+    volatile unsigned long long* c = (volatile unsigned long long*)sv.host;
+    if (!server_alive(sv)) {
+        if (sv.launched) { cudaStreamSynchronize(sv.st); sv.launched = false; }   // gone: idle timeout
+        if (server_launch(sv, model, nspin, inspin, outspin, zz, threads, K) != cudaSuccess) { sv.broken = true; cudaGetLastError(); return -1; }
+    }
+    // the request: header, inputs, then the sequence number (x86 keeps the store order; the device reads the
+    // inputs only after it has seen the new sequence number)
+    double* hp = (double*)sv.host;
+    memcpy(hp + SRV_IN, x_host, (size_t)(nspin + 1) * 8);
+    hp[SRV_IN + nspin + 1] = rows_host ? 1.0 : 0.0;
+    if (rows_host) memcpy(hp + SRV_IN + nspin + 2, rows_host, (size_t)m * K * 8);
+    const unsigned flags = (stats_host ? 1u : 0u) | (amps_host ? 2u : 0u) | (rows_host ? 4u : 0u);
+    c[SRV_HDR] = (unsigned long long)(unsigned)m | ((unsigned long long)flags << 32);
+    hp[SRV_EPS] = dkw_eps;
+    __sync_synchronize();
+    const unsigned long long seq = ++sv.seq;
+    c[SRV_REQ] = seq;
+    int w = server_wait(sv, seq, 2.0);
+    if (w == 1) {
+        // the server left (idle timeout) just before the request arrived: start a new one, which finds it pending
+        cudaStreamSynchronize(sv.st);
+        sv.seq = seq - 1;
+        if (server_launch(sv, model, nspin, inspin, outspin, zz, threads, K) != cudaSuccess) { sv.broken = true; cudaGetLastError(); return -1; }
+        sv.seq = seq;
+        c[SRV_REQ] = seq;
+        w = server_wait(sv, seq, 2.0);
+    }
+    if (w != 0) {
+        // never expected: give the one-shot path the call and stop using the server in this thread
+        sv.broken = true;
+        c[SRV_HDR] = 8ull << 32; __sync_synchronize(); c[SRV_REQ] = ++sv.seq;
+        cudaError_t e = cudaStreamSynchronize(sv.st);
+        if (e != cudaSuccess) return set_error(RC_ERR_CUDA, "rc_objective_host: resident evaluator: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    __sync_synchronize();
+    const double* op = hp + SRV_IN + srv_out_offset(nspin, rows_host ? m : 0, K);
+    const unsigned long long nonconv = c[3];
+    if (nonconv) c[3] = 0;
+    if (m == 1 && !stats_host && !amps_host) op = hp + 1;   // the one-value answer came with the flag
+    if (fids_host) memcpy(fids_host, op, (size_t)m * 8);
+    if (stats_host) memcpy(stats_host, op + m, (size_t)RC_NUM_STATS * 8);
+    if (amps_host) memcpy(amps_host, op + m + RC_NUM_STATS, 2 * (size_t)m * 8);
+    if (nonconv) return set_error(RC_ERR_NONCONV, "eigensolver did not converge for %llu evaluations (NaN written)", nonconv);
+    return RC_OK;
+}
+
+// Asks the calling thread's resident evaluator (if any) on the current device to leave now instead of after its idle
+// time, and waits for it: for callers about to time device work, and before a device reset.
+extern "C" int rc_objective_release(void) {
+    Server* sv = server_slot();
+    if (sv && sv->launched) server_quit(*sv);
     return RC_OK;
 }
 
@@ -323,6 +627,11 @@ extern "C" int rc_objective_host(const double* x_host, int nspin, int inspin, in
     if (m <= OBJ_MAX_LANES && !objective_force_general()) {
         const int threads = (int)((m + 31) / 32 * 32);
         const size_t smem = ((size_t)4 * nspin * threads + (size_t)(nspin + 2) + (rows_host ? (size_t)m * K : 0) + (size_t)m) * 8;
+        if (smem <= OBJ_SMEM_MAX && server_enabled()) {
+            const int r = objective_host_server(x_host, nspin, inspin, outspin, rows_host, m, model, zz, dkw_eps, fids_host,
+                                                stats_host, amps_host, K);
+            if (r >= 0) return r;
+        }
         if (smem <= OBJ_SMEM_MAX)
             return objective_host_fast(x_host, nspin, inspin, outspin, rows_host, m, model, zz, dkw_eps, fids_host, stats_host,
                                        amps_host, (cudaStream_t)stream, K, threads, smem);

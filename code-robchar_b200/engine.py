@@ -546,6 +546,12 @@ class ObjectiveEvaluator:
         return self
 
 
+def objective_release() -> None:
+    """Ask the calling thread's resident objective evaluator (rc_objective_host keeps one CTA on the device between
+    calls, see include/robchar_b200.h) to leave now rather than after its idle time; waits for it."""
+    check(lib().rc_objective_release())
+
+
 class RobustnessSweepPlan:
     """Device buffers + workspace of rc_robustness_sweep for one problem shape, allocated once; run() issues the
     whole fig-4/5 sweep (evolution, statistics, top-k, Kendall matrices, ARIM bootstrap) from ONE C call with no

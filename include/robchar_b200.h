@@ -282,6 +282,16 @@ int rc_objective_host(const double* x_host, int nspin, int inspin, int outspin, 
                       int model, int zz, double dkw_eps, double* fids_host, double* stats_host, double* amps_host,
                       void* stream);
 
+/* m <= 256 evaluations are served by a RESIDENT evaluator: one CTA that stays on the device between calls, polls the
+ * calling thread's pinned mailbox for the next request and leaves by itself after RC_OBJECTIVE_IDLE_US (environment,
+ * default 1000) microseconds without one — an optimiser loop (scipy.optimize.fmin_l_bfgs_b around LBFGS.fidelity_ss,
+ * qnewton.py:497,513) then pays no kernel launch per call.  It runs on a private non-blocking stream (`stream` orders
+ * only the one-shot and large-m paths); a device-wide synchronisation issued while it is idle waits for it at most
+ * the idle time.  rc_objective_release() asks the calling thread's evaluator on the current device to leave now and
+ * waits for it (before timing other device work, or before tearing the context down).  RC_OBJECTIVE_SERVER=0
+ * (environment) disables the resident evaluator: every call launches one kernel. */
+int rc_objective_release(void);
+
 /* Infidelity 1 - |U[out,in]|^2 and its analytic gradient w.r.t. the N biases and the evolution time for C controllers
  * x [C][N+1]: LBFGS.eval_static_fidelity_gradient (qnewton.py:162-212), the L-BFGS inner call (qnewton.py:497,513).
  * Upstream evaluates N + 1 dense matrix exponentials (N of them on 2N x 2N block matrices); here the derivatives come

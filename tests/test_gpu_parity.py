@@ -1011,6 +1011,66 @@ def test_objective_fast_path_equals_copy_path_and_sweep(rb, monkeypatch):
     assert np.abs(amps - U).max() < FID_TOL
 
 
+_RESIDENT_CASES = [(5, 1, 1, False), (5, 1, 30, True), (7, 0, 7, True), (7, 1, 100, True), (12, 0, 1, False), (5, 1, 1, False)]
+
+
+def _resident_case_results(rb):
+    """The shapes an optimiser alternates between (nominal value, wass_cost rows, fixed Hamiltonian sets), in an order
+    that makes the resident evaluator grow and change its signature."""
+    out = []
+    rs = np.random.RandomState(11)
+    for n, model, m, with_rows in _RESIDENT_CASES:
+        K = (3 if model == 0 else 2) * n
+        x = orc.synthetic_controllers(1, n, seed=100 + n)[0]
+        if with_rows:
+            rows = 0.05 * rs.standard_normal((m, K))
+            f, st = rb.engine.objective_host(x, rows, n, 0, n - 1, model=model, want_stats=True, dkw_eps=0.02)
+            out += [f, st]
+            if model == 1:
+                out.append(rb.engine.objective_host(x, rows, n, 0, n - 1, model=1, want_amps=True)[1].view(np.float64))
+        else:
+            out.append(rb.engine.objective_host(x, None, n, 0, n - 1, model=model))
+    return out
+
+
+def test_resident_objective_evaluator_equals_one_shot_launches(rb, tmp_path):
+    """rc_objective_host serves m <= 256 from a CTA that stays on the device between calls (csrc/rc_objective.cu):
+    bit-identical to the one-kernel-per-call path (RC_OBJECTIVE_SERVER=0, run in a child process), across idle exits,
+    explicit release, growing m and changing chains."""
+    import subprocess, sys, time
+    from conftest import ROOT as _ROOT
+    got = _resident_case_results(rb)
+    script = tmp_path / "one_shot.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {_ROOT!r}); sys.path.insert(0, {os.path.join(_ROOT, 'tests')!r})\n"
+        "import robchar_b200 as rb, test_gpu_parity as t\n"
+        f"np.savez({str(tmp_path / 'one_shot.npz')!r}, *t._resident_case_results(rb))\n")
+    env = dict(os.environ, RC_OBJECTIVE_SERVER="0")
+    subprocess.run([sys.executable, str(script)], check=True, env=env, timeout=300)
+    ref = np.load(tmp_path / "one_shot.npz")
+    assert len(ref.files) == len(got)
+    for k, g in enumerate(got):
+        assert np.array_equal(np.asarray(g), ref[f"arr_{k}"], equal_nan=True), k
+    # the evaluator leaves after its idle time (1 ms) and on request; the next call starts a new one
+    n = 6
+    x = orc.synthetic_controllers(1, n, seed=5)[0]
+    want = orc.evaluate_fidelity(x, n, 0, 5)
+    ev = rb.engine.ObjectiveEvaluator(n, 0, 5, 0, model=1)
+    launches0 = rb.engine.launch_count()
+    for _ in range(200):
+        assert abs(ev(x).fids[0] - want) < FID_TOL
+    assert rb.engine.launch_count() - launches0 <= 20         # resident: no launch per call (idle exits aside)
+    for pause in (0.0, 0.0005, 0.003, 0.02):
+        time.sleep(pause)
+        assert abs(ev(x).fids[0] - want) < FID_TOL
+        torch.cuda.synchronize()                              # a device-wide wait returns within the idle time
+    rb.engine.objective_release()
+    rb.engine.objective_release()
+    assert abs(ev(x).fids[0] - want) < FID_TOL
+    rb.engine.objective_release()
+
+
 def test_user_hamiltonians_outside_the_tridiagonal_form_take_the_dense_path(rb):
     """fidelity_ss(use_fixed_ham=True, rH=...) with complex / ring / non-symmetric rH must evaluate the full matrix
     like upstream's expm (qnewton.py:395-397), not silently drop entries."""
