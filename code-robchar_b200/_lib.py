@@ -31,6 +31,14 @@ class EigensolverNonConvergence(RobcharLibraryError):
 
 _i64, _i32, _u64, _f64, _vp, _sz = C.c_int64, C.c_int, C.c_uint64, C.c_double, C.c_void_p, C.c_size_t
 
+class ObjectiveFrame(C.Structure):
+    """rc_objective_frame (include/robchar_b200.h)."""
+    _fields_ = [("x_host", C.c_void_p), ("rows_host", C.c_void_p), ("fids_host", C.c_void_p), ("stats_host", C.c_void_p),
+                ("amps_host", C.c_void_p), ("stream", C.c_void_p), ("m", C.c_int64), ("dkw_eps", C.c_double),
+                ("nspin", C.c_int32), ("inspin", C.c_int32), ("outspin", C.c_int32), ("model", C.c_int32),
+                ("zz", C.c_int32), ("reserved", C.c_int32)]
+
+
 _SIGNATURES = {
     "rc_version": (C.c_int, []),
     "rc_last_error": (C.c_char_p, []),
@@ -83,6 +91,7 @@ _SIGNATURES = {
                                    _i32, _vp, _vp, _vp]),
     "rc_objective_host": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp]),
     "rc_objective_release": (C.c_int, []),
+    "rc_objective_call": (C.c_int, [_vp]),
     "rc_fidelity_grad": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "rc_fidelity_grad_host": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
     "rc_dense_fidelity_mc_workspace_bytes": (_sz, [_i32, _i64]),

@@ -25,6 +25,7 @@ struct ObjParams {
     unsigned long long* flag;   // mapped: [0] sequence flag, [1] non-convergence count
     unsigned long long seq;
     int N, in_site, out_site, m, K, zz, want_stats, want_amps, has_rows;
+    int reg_ql;                 // chains of N <= 8: eigensolve in registers (fidelity_reg_compact) instead of shared memory
     double eps;
 };
 
@@ -32,6 +33,33 @@ __device__ __forceinline__ double ld_sys(const double* p) {
     double v;
     asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
+}
+
+// One evaluation with the register-resident QL of the short-chain sweep kernels (same build arithmetic as the strided
+// path below; the eigensolver differs in rounding only).  scratch: 2N doubles at stride ld.
+template <int MODEL, int N>
+__device__ __noinline__ double objective_eval_reg(const ObjParams& q, const double* inp, const double* row, double* scratch,
+                                                  int ld, int* fail, double* amp) {
+    constexpr int P = draws_per_site(MODEL);
+    double d[N], e[N];
+    const double sigma = inp[N + 1];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double base = q.zz ? zz_diag(i, N) : 0.0;
+        const double z = q.has_rows ? row[P * i] : 0.0;
+        d[i] = __dadd_rn(__dadd_rn(base, __dmul_rn(sigma, z)), inp[i]);
+        if (i >= 1) {
+            const double aa = __dadd_rn(1.0, __dmul_rn(sigma, q.has_rows ? row[P * i + 1] : 0.0));
+            if (MODEL == MODEL_COMPLEX3) {
+                const double bb = __dmul_rn(sigma, q.has_rows ? row[P * i + 2] : 0.0);
+                e[i - 1] = rc_sqrt(fma(aa, aa, bb * bb));
+            } else {
+                e[i - 1] = aa;
+            }
+        }
+    }
+    e[N - 1] = 0.0;
+    return fidelity_reg_compact<N, true>(d, e, q.in_site, q.out_site, fabs(inp[N]), scratch, ld, fail, amp);
 }
 
 // One request: stage the inputs, one matrix per lane, the 15 statistics, results + flag through the mapping.
@@ -56,7 +84,27 @@ __device__ __forceinline__ void objective_body(const ObjParams& q, double* sm) {
     // one fidelity and nothing else wanted: it travels WITH the sequence flag in one 16-byte store (no fence)
     const bool fast_publish = q.m == 1 && !q.want_stats && !q.want_amps;
     constexpr int P = draws_per_site(MODEL);
-    if (lane < q.m) {
+    if (lane < q.m && q.reg_ql && n <= 8) {
+        const double* row = inp + n + 2 + (size_t)lane * q.K;
+        int fail = 0;
+        double amp[2], f;
+        switch (n) {
+            case 2: f = objective_eval_reg<MODEL, 2>(q, inp, row, sm + lane, ld, &fail, amp); break;
+            case 3: f = objective_eval_reg<MODEL, 3>(q, inp, row, sm + lane, ld, &fail, amp); break;
+            case 4: f = objective_eval_reg<MODEL, 4>(q, inp, row, sm + lane, ld, &fail, amp); break;
+            case 5: f = objective_eval_reg<MODEL, 5>(q, inp, row, sm + lane, ld, &fail, amp); break;
+            case 6: f = objective_eval_reg<MODEL, 6>(q, inp, row, sm + lane, ld, &fail, amp); break;
+            case 7: f = objective_eval_reg<MODEL, 7>(q, inp, row, sm + lane, ld, &fail, amp); break;
+            default: f = objective_eval_reg<MODEL, 8>(q, inp, row, sm + lane, ld, &fail, amp); break;
+        }
+        if (fail) atomicAdd(&nonconv, 1u);
+        fs[lane] = f;
+        if (!fast_publish) q.out[lane] = f;
+        if (q.want_amps) {
+            q.out[q.m + RC_NUM_STATS + 2 * lane] = amp[0];
+            q.out[q.m + RC_NUM_STATS + 2 * lane + 1] = amp[1];
+        }
+    } else if (lane < q.m) {
         double* d = sm + lane;
         double* e = d + (size_t)n * ld;
         double* zi = e + (size_t)n * ld;
@@ -188,7 +236,7 @@ struct SrvParams {
     unsigned long long* ctl;      // mapped mailbox
     unsigned long long start_seq; // last request already answered
     unsigned long long idle_ns, gen;
-    int N, in_site, out_site, K, zz;
+    int N, in_site, out_site, K, zz, reg_ql;
 };
 
 __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
@@ -218,12 +266,13 @@ __global__ void __launch_bounds__(256) objective_server_kernel(SrvParams p) {
             // (Reads through the mapping are expensive and those of one line do not overlap: nobody else reads it.)
             unsigned long long w = 0, v, t0 = global_ns();
             int leaving = 0;
+            unsigned polls = 0;
             for (;;) {
                 if (lane < 3) w = ld_sys_u64(p.ctl + SRV_REQ + lane);
                 v = __shfl_sync(0xffffffffu, w, 0);
                 if (v != done) break;
                 if (leaving) { v = 0; break; }
-                if (global_ns() - t0 > p.idle_ns) {          // idle: announce, then look once more
+                if ((++polls & 15u) == 0 && global_ns() - t0 > p.idle_ns) {   // idle: announce, then look once more
                     if (lane == 0) { ctl[2] = p.gen * 4 + SRV_EXITING; __threadfence_system(); }
                     leaving = 1;
                 }
@@ -242,7 +291,7 @@ __global__ void __launch_bounds__(256) objective_server_kernel(SrvParams p) {
             const unsigned flags = (unsigned)(hdr >> 32);
             q.want_stats = flags & 1; q.want_amps = (flags >> 1) & 1; q.has_rows = (flags >> 2) & 1;
             q.eps = __longlong_as_double((long long)s_eps);
-            q.N = p.N; q.in_site = p.in_site; q.out_site = p.out_site; q.K = p.K; q.zz = p.zz;
+            q.N = p.N; q.in_site = p.in_site; q.out_site = p.out_site; q.K = p.K; q.zz = p.zz; q.reg_ql = p.reg_ql;
             q.in = reinterpret_cast<const double*>(p.ctl + SRV_IN);
             q.out = reinterpret_cast<double*>(p.ctl + SRV_IN) + srv_out_offset(p.N, q.has_rows ? q.m : 0, p.K);
             q.flag = p.ctl;
@@ -304,6 +353,12 @@ static double now_s() {
 constexpr size_t OBJ_SMEM_MAX = 200 * 1024;
 constexpr int OBJ_MAX_LANES = 256;
 
+// RC_OBJECTIVE_REGQL=0: chains of N <= 8 use the shared-memory eigensolver like the longer ones (A/B measurements)
+static int objective_reg_ql() {
+    static int v = -1;
+    if (v < 0) { const char* s = getenv("RC_OBJECTIVE_REGQL"); v = (s && s[0] == '0') ? 0 : 1; }
+    return v;
+}
 // 1 when RC_OBJECTIVE_PATH=general forces the copy-based path (A/B measurements)
 static bool objective_force_general() {
     static int v = -1;
@@ -403,6 +458,7 @@ static int objective_host_fast(const double* x_host, int nspin, int inspin, int 
     q.N = nspin; q.in_site = inspin; q.out_site = outspin; q.m = (int)m; q.K = K; q.zz = zz;
     q.want_stats = stats_host != nullptr; q.want_amps = amps_host != nullptr; q.has_rows = rows_host != nullptr;
     q.eps = dkw_eps;
+    q.reg_ql = objective_reg_ql();
     const int mi = model == RC_MODEL_COMPLEX3 ? 0 : 1;
     if (smem > 40 * 1024 && mb->smem_set[mi] < (int)smem) {
         RC_CUDA_TRY(mi == 0 ? cudaFuncSetAttribute(objective_kernel<MODEL_COMPLEX3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OBJ_SMEM_MAX)
@@ -494,7 +550,7 @@ static cudaError_t server_launch(Server& sv, int model, int N, int in, int out, 
     p.start_seq = sv.seq;
     p.idle_ns = server_idle_ns();
     p.gen = ++sv.gen;
-    p.N = N; p.in_site = in; p.out_site = out; p.K = K; p.zz = zz;
+    p.N = N; p.in_site = in; p.out_site = out; p.K = K; p.zz = zz; p.reg_ql = objective_reg_ql();
     volatile unsigned long long* c = (volatile unsigned long long*)sv.host;
     c[2] = sv.gen * 4 + SRV_RUNNING;
     c[SRV_REQ] = sv.seq;
@@ -529,17 +585,15 @@ static int objective_host_server(const double* x_host, int nspin, int inspin, in
     Server* svp = server_slot();
     if (!svp || svp->broken) return -1;
     Server& sv = *svp;
-    int need_threads = (int)((m + 31) / 32 * 32);
-    {   // RC_OBJECTIVE_MIN_THREADS (environment): CTA size floor of the resident evaluator (tuning)
-        static int floor_t = -1;
-        if (floor_t < 0) { const char* e = getenv("RC_OBJECTIVE_MIN_THREADS"); floor_t = e ? atoi(e) : 0; if (floor_t < 0 || floor_t > OBJ_MAX_LANES) floor_t = 0; floor_t = floor_t / 32 * 32; }
-        if (need_threads < floor_t) need_threads = floor_t;
-    }
+    // CTA size: at least 128 lanes (more lanes = more reads of the rows in flight through the mapping: 30 rows 20.4 ->
+    // 17.9 us at N = 5; the nominal call does not care), never smaller than a live evaluator of the same chain
+    const int need_threads = (int)((m + 31) / 32 * 32);
     const bool same = sv.launched && sv.model == model && sv.N == nspin && sv.in == inspin && sv.out == outspin && sv.zz == zz;
-    int threads = same && sv.threads >= need_threads ? sv.threads : need_threads;
+    auto smem_for = [&](int t) { return ((size_t)4 * nspin * t + (size_t)(nspin + 2) + (size_t)t * K + (size_t)t) * 8; };
+    int threads = need_threads < 128 ? 128 : need_threads;
     if (same && sv.threads > threads) threads = sv.threads;
-    const size_t smem = ((size_t)4 * nspin * threads + (size_t)(nspin + 2) + (size_t)threads * K + (size_t)threads) * 8;
-    if (smem > OBJ_SMEM_MAX) return -1;
+    if (smem_for(threads) > OBJ_SMEM_MAX) threads = need_threads;
+    if (smem_for(threads) > OBJ_SMEM_MAX) return -1;
     const size_t words = SRV_IN + srv_out_offset(nspin, threads, K) + (size_t)threads + RC_NUM_STATS + 2 * (size_t)threads;
     if (!sv.st && cudaStreamCreateWithFlags(&sv.st, cudaStreamNonBlocking) != cudaSuccess) { sv.broken = true; return -1; }
     if (sv.bytes < words * 8) {
@@ -638,4 +692,12 @@ extern "C" int rc_objective_host(const double* x_host, int nspin, int inspin, in
     }
     return objective_host_general(x_host, nspin, inspin, outspin, rows_host, m, model, zz, dkw_eps, fids_host, stats_host,
                                   amps_host, stream);
+}
+
+// The same call through a caller-built frame: one pointer argument instead of thirteen (what a foreign-function layer
+// such as ctypes spends per call is proportional to the argument count: ~2 us of a 13 us call).
+extern "C" int rc_objective_call(const rc_objective_frame* f) {
+    if (!f) return set_error(RC_ERR_NULL, "rc_objective_call: null frame");
+    return rc_objective_host(f->x_host, f->nspin, f->inspin, f->outspin, f->rows_host, f->m, f->model, f->zz, f->dkw_eps,
+                             f->fids_host, f->stats_host, f->amps_host, f->stream);
 }

@@ -210,15 +210,18 @@ RC_HD double fidelity_reg(double (&d)[N], double (&e)[N], int in, int out, doubl
 // sequence of sweeps, and a warp iterates max-over-lanes(total sweeps) times.
 // scratch: 2N doubles per lane, element k at scratch[k * sstride].
 // ---------------------------------------------------------------------------------------------
-template <int N>
+// AMP: also stores the transfer amplitude <out| exp(-iHT) |in> as amp[0] + i amp[1] (NaN where the fidelity is NaN).
+template <int N, bool AMP = false>
 RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int out, double T, double* scratch,
                                   int sstride, int* fail
 #ifdef RC_QL_STATS
                                   , QlStats* st
 #endif
+                                  , double* amp = nullptr
 ) {
     double zi[N], zo[N];
     double anorm = 0.0, chk = T;
+    if (AMP) { amp[0] = NAN; amp[1] = NAN; }
     e[N - 1] = 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -322,6 +325,7 @@ RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int ou
         re = fma(w, cs, re);
         im = fma(-w, sn, im);
     }
+    if (AMP) { amp[0] = re; amp[1] = im; }
     return fma(re, re, im * im);
 }
 

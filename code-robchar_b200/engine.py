@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import MODEL_COMPLEX3, MODEL_REAL2, NUM_STATS, check, lib
+from ._lib import MODEL_COMPLEX3, MODEL_REAL2, NUM_STATS, ObjectiveFrame, check, lib
 
 # keys of the reference's metric registry, in .mcm order (mcsim.py:178-183, 496-498)
 METRIC_W = r'$W(.,\delta(x-1))$'
@@ -527,20 +527,19 @@ class ObjectiveEvaluator:
         self.fids = np.empty(self.m) if want_fids else None
         self.stats = np.empty(NUM_STATS) if want_stats else None
         self.amps = np.empty(self.m, dtype=np.complex128) if want_amps else None
-        vp = lambda a: C.c_void_p(a.ctypes.data if a is not None else 0)
-        self._fn = lib().rc_objective_host
-        self._args = (vp(self.x), nspin, inspin, outspin, vp(self.rows), self.m, model, int(bool(zz)), float(dkw_eps),
-                      vp(self.fids), vp(self.stats), vp(self.amps), C.c_void_p(0))
-        self._stream_slot = len(self._args) - 1
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        # one pointer argument per call instead of thirteen; stream 0: host buffers in and out, the call is synchronous
+        self._frame = ObjectiveFrame(ptr(self.x), ptr(self.rows), ptr(self.fids), ptr(self.stats), ptr(self.amps), None,
+                                     self.m, float(dkw_eps), nspin, inspin, outspin, model, int(bool(zz)), 0)
+        self._fn = lib().rc_objective_call
+        self._arg = C.byref(self._frame)
 
     def __call__(self, x, rows=None):
         """Evaluate; results are in self.fids / self.stats / self.amps (overwritten by the next call)."""
         self.x[:] = x
         if self.rows is not None:
             self.rows[:] = rows
-        stream = torch.cuda.current_stream().cuda_stream
-        args = self._args if stream == 0 else self._args[:self._stream_slot] + (C.c_void_p(stream),)
-        code = self._fn(*args)
+        code = self._fn(self._arg)
         if code:
             check(code)
         return self

@@ -292,6 +292,22 @@ int rc_objective_host(const double* x_host, int nspin, int inspin, int outspin, 
  * (environment) disables the resident evaluator: every call launches one kernel. */
 int rc_objective_release(void);
 
+/* rc_objective_host through a frame the caller fills once per shape and reuses: an optimiser calls its objective
+ * thousands of times with the same buffers (the preallocated arrays of engine.ObjectiveEvaluator), and a foreign-function
+ * layer pays per argument.  Field meaning = the parameters of rc_objective_host. */
+typedef struct rc_objective_frame {
+    const double* x_host;
+    const double* rows_host;
+    double* fids_host;
+    double* stats_host;
+    double* amps_host;
+    void* stream;
+    int64_t m;
+    double dkw_eps;
+    int32_t nspin, inspin, outspin, model, zz, reserved;
+} rc_objective_frame;
+int rc_objective_call(const rc_objective_frame* frame);
+
 /* Infidelity 1 - |U[out,in]|^2 and its analytic gradient w.r.t. the N biases and the evolution time for C controllers
  * x [C][N+1]: LBFGS.eval_static_fidelity_gradient (qnewton.py:162-212), the L-BFGS inner call (qnewton.py:497,513).
  * Upstream evaluates N + 1 dense matrix exponentials (N of them on 2N x 2N block matrices); here the derivatives come
