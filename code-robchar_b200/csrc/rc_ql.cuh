@@ -35,7 +35,7 @@ namespace rc {
 constexpr int QL_MAX_SWEEPS = 40;  // per eigenvalue (EISPACK uses 30)
 
 #ifdef RC_QL_STATS
-struct QlStats { int sweeps_per_l[64]; int total_sweeps; int rotations; };
+struct QlStats { int sweeps_per_l[64]; int total_sweeps; int rotations; int irregular; };
 #define RC_STAT(x) x
 #else
 #define RC_STAT(x)
@@ -62,6 +62,10 @@ RC_HD double wilkinson_g(double dl, double dl1, double el, double dm) {
     const double t = delta + copysign(q * rc_rsqrt(q), delta);
     return (dm - dl) + e2 * rc_rcp_approx(t);
 }
+
+// Strided-memory solver (defined below); tolhi_given != 0: continue a started solve under its threshold.
+RC_HD void amplitude_strided(double* d, double* e, double* zi, double* zo, int ld, int n, double T, int* fail,
+                             double& re_out, double& im_out, int tolhi_given = 0);
 
 // One implicit QL sweep on the unreduced block [L, m] (m found by the caller), L compile time.
 // e[i] couples sites i and i+1; e[N-1] is a scratch slot.
@@ -210,6 +214,193 @@ RC_HD double fidelity_reg(double (&d)[N], double (&e)[N], int in, int out, doubl
 // sequence of sweeps, and a warp iterates max-over-lanes(total sweeps) times.
 // scratch: 2N doubles per lane, element k at scratch[k * sstride].
 // ---------------------------------------------------------------------------------------------
+#ifndef RC_QL_PINNED_END
+#define RC_QL_PINNED_END 1
+#endif
+#if RC_QL_PINNED_END
+// ---------------------------------------------------------------------------------------------
+// Pinned-end form (round 2, what the kernels use).  The block-at-index-0 form below pays for its
+// static shift end with data movement: every deflation shifts the four register arrays down by one
+// (48 moves at N=7), the chase starts at a dynamic position (a select chain for d[m], a predicate per
+// rotation slot that skips the slots above m) and finished eigenpairs are stored through a dynamic
+// index.  Here nothing moves: the active block is [L, N-1] with the END pinned at N-1, so the chase
+// always starts with the static slot N-2 (s = c = 1, p = 0 folded in: two multiplications and the
+// dead store of the first r less per sweep) and LEAVES after the slot that rotates (L, L+1).  The chase
+// value g travels in e[i] and the pending "- p" in d[i] (each slot stores d[i] - p, which is what the next
+// slot would compute first and is the final diagonal element if there is no next slot), so a slot has
+// no epilogue that depends on being the last one.  The slot that was the last one (static index again)
+// hands the three numbers of the next Wilkinson shift — of block L, or of block L+1 when e[L] has just
+// become negligible — to the common tail; deflated eigenpairs simply stay where they are.
+// Every arithmetic operation and its order equal the form below: results are bit-identical.
+//
+// The price is generality: a sweep cannot stop short of N-1.  A negligible INTERIOR coupling (seen as
+// in the other form by `rmin`, the smallest coupling the sweep wrote) would need exactly that, so such
+// evaluations (measured: a few in 1e5 at the paper's noise levels, plus exactly decoupled chains) leave
+// for ql_irregular: the state goes to a lane-private local-memory array and the strided solver finishes it
+// from where the sweeps stand, out of line.
+// ---------------------------------------------------------------------------------------------
+struct QlTail { double dl, dl1, el; bool defl; };
+
+template <int N, int I>
+RC_HD void ql_rows(double (&zi)[N], double (&zo)[N], double s, double c) {
+    double t = zi[I + 1];
+    zi[I + 1] = fma(s, zi[I], c * t);
+    zi[I] = fma(c, zi[I], -(s * t));
+    t = zo[I + 1];
+    zo[I + 1] = fma(s, zo[I], c * t);
+    zo[I] = fma(c, zo[I], -(s * t));
+}
+
+// operands of the next shift after slot I was the last of the sweep
+template <int N, int I>
+RC_HD void ql_tail(const double (&d)[N], const double (&e)[N], int tolhi, QlTail& t) {
+    const bool ng = negligible_hi(e[I], tolhi);
+    t.defl = ng;
+    if constexpr (I + 2 <= N - 1) {
+        t.dl = ng ? d[I + 1] : d[I];
+        t.dl1 = ng ? d[I + 2] : d[I + 1];
+        t.el = ng ? e[I + 1] : e[I];
+    } else {   // block (N-2, N-1): deflation ends the solve, the shift is not used
+        t.dl = d[I]; t.dl1 = d[I + 1]; t.el = e[I];
+    }
+}
+
+template <int N, int I>
+struct QlChain {
+    static RC_HD void run(double (&d)[N], double (&e)[N], double (&zi)[N], double (&zo)[N], double s, double c,
+                          int L, double tiny, int tolhi, int& rmin, QlTail& t) {
+        const double g = e[I + 1];
+        const double f = s * e[I];
+        const double b = c * e[I];
+        const double h = fma(f, f, fma(g, g, tiny));
+        const double rinv = rc_rsqrt(h);
+        const double r = h * rinv;
+        e[I + 1] = r;
+        rmin = hi_word(r) < rmin ? hi_word(r) : rmin;   // smallest interior coupling of this sweep (r >= 0)
+        s = f * rinv;
+        c = g * rinv;
+        const double gg = d[I + 1];                      // already d - p of the slot before
+        const double r2 = fma(d[I] - gg, s, (2.0 * c) * b);
+        const double p = s * r2;
+        d[I + 1] = gg + p;
+        e[I] = c * r2 - b;
+        d[I] = d[I] - p;
+        ql_rows<N, I>(zi, zo, s, c);
+        if constexpr (I == 0) {
+            ql_tail<N, 0>(d, e, tolhi, t);
+        } else {
+            if (L == I) ql_tail<N, I>(d, e, tolhi, t);
+            else QlChain<N, I - 1>::run(d, e, zi, zo, s, c, L, tiny, tolhi, rmin, t);
+        }
+    }
+};
+
+// Out-of-line continuation of an evaluation the pinned-end sweeps cannot finish (negligible interior
+// coupling).  st = d[N], e[N], zi[N], zo[N] of the lane; the strided solver skips the deflated head
+// (its couplings are negligible under the same threshold) and goes on exactly as the block-at-0 form would.
+template <int N>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+void ql_irregular(double* st, double T, int tolhi, int* fail, double* reim) {
+    double re, im;
+    amplitude_strided(st, st + N, st + 2 * N, st + 3 * N, 1, N, T, fail, re, im, tolhi);
+    reim[0] = re; reim[1] = im;
+}
+
+template <int N, bool AMP = false>
+RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int out, double T, double* scratch,
+                                  int sstride, int* fail
+#ifdef RC_QL_STATS
+                                  , QlStats* st
+#endif
+                                  , double* amp = nullptr
+) {
+    double zi[N], zo[N];
+    double anorm = 0.0, chk = T;
+    if (AMP) { amp[0] = NAN; amp[1] = NAN; }
+    e[N - 1] = 0.0;
+    int emin = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        zi[k] = (k == in) ? 1.0 : 0.0;
+        zo[k] = (k == out) ? 1.0 : 0.0;
+        anorm = fmax(anorm, fabs(d[k]) + fabs(e[k]));
+        chk += d[k] + e[k];
+        if (k < N - 1) { const int h = hi_word(e[k]) & 0x7fffffff; emin = h < emin ? h : emin; }
+    }
+    *fail = 0;
+    if (!(fabs(chk) <= DBL_MAX)) return NAN;  // NaN / Inf controller or draw (mcsim.py:369-374)
+    const double tol = DBL_EPSILON * anorm;
+    const int tolhi = threshold_hi(tol);
+    const double tiny = fmin(tol, 1e-280);  // == 1e-280, kept in a register instead of re-materialised per rotation
+    double re = 0.0, im = 0.0;
+    // L = first site of the active block; N = "left for ql_irregular".  Non-convergence (more than
+    // QL_MAX_SWEEPS sweeps on one eigenvalue) leaves the loop through its condition with L < N - 1.
+    int L = emin < tolhi ? N : 0, it = 0;
+    if constexpr (N >= 2) {
+        double g = wilkinson_g(d[0], d[1], e[0], d[N - 1]);
+        while (L < N - 1 && it <= QL_MAX_SWEEPS) {
+            ++it;
+            int rmin = 0x7fffffff;
+            QlTail t;
+            {   // slot N-2: first rotation of every sweep, s = c = 1 and p = 0 folded in, its r is not stored
+                constexpr int I = N - 2;
+                const double b = e[I];
+                const double h = fma(b, b, fma(g, g, tiny));
+                const double rinv = rc_rsqrt(h);
+                const double s = b * rinv;
+                const double c = g * rinv;
+                const double gg = d[I + 1];
+                const double r2 = fma(d[I] - gg, s, (2.0 * c) * b);
+                const double p = s * r2;
+                d[I + 1] = gg + p;
+                e[I] = c * r2 - b;
+                d[I] = d[I] - p;
+                ql_rows<N, I>(zi, zo, s, c);
+                if constexpr (I == 0) {
+                    ql_tail<N, 0>(d, e, tolhi, t);
+                } else {
+                    if (L == I) ql_tail<N, I>(d, e, tolhi, t);
+                    else QlChain<N, I - 1>::run(d, e, zi, zo, s, c, L, tiny, tolhi, rmin, t);
+                }
+            }
+            RC_STAT(st->total_sweeps++; st->rotations += N - 1 - L;)
+            if (t.defl) { ++L; it = 0; }
+            if (rmin < tolhi) L = N;     // negligible interior coupling: ql_irregular takes over
+            g = wilkinson_g(t.dl, t.dl1, t.el, d[N - 1]);
+        }
+    }
+    if (L == N) {
+        RC_STAT(st->irregular++;)
+        double buf[4 * N], reim[2];
+#pragma unroll
+        for (int k = 0; k < N; ++k) { buf[k] = d[k]; buf[N + k] = e[k]; buf[2 * N + k] = zi[k]; buf[3 * N + k] = zo[k]; }
+        ql_irregular<N>(buf, T, tolhi, fail, reim);
+        re = reim[0]; im = reim[1];
+        if (*fail) return NAN;
+    } else {
+        if (L < N - 1) { *fail = 1; return NAN; }
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            scratch[(size_t)k * sstride] = d[k];
+            scratch[(size_t)(N + k) * sstride] = zi[k] * zo[k];
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int k = 0; k < N; ++k) {
+            double sn, cs;
+            rc_sincos_tab(scratch[(size_t)k * sstride] * T, &sn, &cs);
+            const double w = scratch[(size_t)(N + k) * sstride];
+            re = fma(w, cs, re);
+            im = fma(-w, sn, im);
+        }
+    }
+    if (AMP) { amp[0] = re; amp[1] = im; }
+    return fma(re, re, im * im);
+}
+#else
 // AMP: also stores the transfer amplitude <out| exp(-iHT) |in> as amp[0] + i amp[1] (NaN where the fidelity is NaN).
 template <int N, bool AMP = false>
 RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int out, double T, double* scratch,
@@ -329,13 +520,15 @@ RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int ou
     return fma(re, re, im * im);
 }
 
+#endif  // RC_QL_PINNED_END
+
 // ---------------------------------------------------------------------------------------------
 // Strided-memory variant for large N: arrays live in shared (or any) memory with element stride
 // `ld` between consecutive matrix positions (column = this lane), dynamic loop bounds.
 // Holds the "i+1" elements in registers while chasing upwards to halve the memory traffic.
 // ---------------------------------------------------------------------------------------------
 RC_HD void amplitude_strided(double* d, double* e, double* zi, double* zo, int ld, int n, double T, int* fail,
-                             double& re_out, double& im_out) {
+                             double& re_out, double& im_out, int tolhi_given) {
 #define AT(a, i) a[(size_t)(i) * ld]
     double anorm = 0.0, chk = T;
     AT(e, n - 1) = 0.0;
@@ -346,7 +539,7 @@ RC_HD void amplitude_strided(double* d, double* e, double* zi, double* zo, int l
     re_out = NAN; im_out = NAN;
     if (!(fabs(chk) <= DBL_MAX)) { *fail = 0; return; }
     const double tol = DBL_EPSILON * anorm;
-    const int tolhi = threshold_hi(tol);
+    const int tolhi = tolhi_given ? tolhi_given : threshold_hi(tol);   // given: continuation of a started solve (ql_irregular)
     const double tiny = fmin(tol, 1e-280);
     int bad = 0;
     // rmin: smallest high word among the couplings the last sweep wrote (see fidelity_reg_compact) — the

@@ -11,7 +11,7 @@
 template <int N>
 void run(FILE* fi, FILE* fo, int in, int out, int count, int strided) {
     std::vector<double> buf(2 * N);
-    long hist[64] = {0}; long totsweeps = 0, totrot = 0; int maxsweeps = 0; long perl[64] = {0};
+    long hist[64] = {0}; long totsweeps = 0, totrot = 0, irregular = 0; int maxsweeps = 0; long perl[64] = {0};
     for (int k = 0; k < count; ++k) {
         if (fread(buf.data(), sizeof(double), 2 * N, fi) != (size_t)(2 * N)) { fprintf(stderr, "short read\n"); exit(1); }
         double d[N], e[N], T = buf[2 * N - 1];
@@ -28,7 +28,7 @@ void run(FILE* fi, FILE* fo, int in, int out, int count, int strided) {
             rc::QlStats st; memset(&st, 0, sizeof st);
             if (strided == 2) { double scr[2 * N]; f = rc::fidelity_reg_compact<N>(d, e, in, out, T, scr, 1, &fail, &st); }
             else f = rc::fidelity_reg<N>(d, e, in, out, T, &fail, &st);
-            totsweeps += st.total_sweeps; totrot += st.rotations;
+            totsweeps += st.total_sweeps; totrot += st.rotations; irregular += st.irregular;
             if (st.total_sweeps > maxsweeps) maxsweeps = st.total_sweeps;
             hist[st.total_sweeps < 63 ? st.total_sweeps : 63]++;
             for (int l = 0; l < N; ++l) perl[l] += st.sweeps_per_l[l];
@@ -37,7 +37,7 @@ void run(FILE* fi, FILE* fo, int in, int out, int count, int strided) {
         fwrite(&f, sizeof(double), 1, fo);
     }
     if (strided != 1) {
-        fprintf(stderr, "N=%d mean sweeps %.3f max %d mean rotations %.2f\n per-l mean:", N, (double)totsweeps / count, maxsweeps, (double)totrot / count);
+        fprintf(stderr, "N=%d mean sweeps %.3f max %d mean rotations %.2f irregular %ld of %d\n per-l mean:", N, (double)totsweeps / count, maxsweeps, (double)totrot / count, irregular, count);
         for (int l = 0; l < N; ++l) fprintf(stderr, " %.2f", (double)perl[l] / count);
         fprintf(stderr, "\n");
     }
