@@ -16,7 +16,7 @@ namespace rc {
 constexpr int MODEL_COMPLEX3 = 0;  // noise_model.py:122-147: (z_ii, nn_i, nn2_i) per site
 constexpr int MODEL_REAL2 = 1;     // qnewton.py:366-379:     (z_ii, nn_i) per site
 constexpr int REG_MAX_N = 16;      // register-resident eigensolver compiled up to here
-constexpr int REG_DEFAULT_N = 8;   // measured crossover on B200: registers win for N <= 8, shared memory above
+constexpr int REG_DEFAULT_N = 12;  // measured crossover on B200 (round 2, pinned-end QL): registers win for N <= 12, shared memory above
 constexpr int MAX_N = 32;
 
 struct FidArgs {
@@ -177,10 +177,11 @@ __device__ __forceinline__ double eval_reg(const FidArgs& a, long long s, long l
 #define RC_TILE_SYNC 0
 #endif
 __host__ __device__ constexpr int reg_cta_threads(int n, bool replay) {
-    return RC_REG_THREADS ? RC_REG_THREADS : (n > 8 ? 128 : (replay ? 256 : (n <= 4 ? 1024 : (n == 5 ? 896 : 768))));
+    return RC_REG_THREADS ? RC_REG_THREADS
+                          : (n > REG_DEFAULT_N ? 128 : (n > 8 ? (replay ? 256 : 512) : (replay ? 256 : (n <= 4 ? 1024 : (n == 5 ? 896 : 768)))));
 }
 __host__ __device__ constexpr int reg_cta_min_blocks(int n, bool replay) {
-    return RC_REG_MIN_BLOCKS ? RC_REG_MIN_BLOCKS : (n > 8 ? 1 : (replay ? 3 : 1));
+    return RC_REG_MIN_BLOCKS ? RC_REG_MIN_BLOCKS : (n > REG_DEFAULT_N ? 1 : (n > 8 ? (replay ? 2 : 1) : (replay ? 3 : 1)));
 }
 constexpr int MAX_CTA_WARPS = 32;
 constexpr int SMEM_MAX_THREADS = 768;         // launch bound of the shared-memory evolution kernel

@@ -167,9 +167,10 @@ def _mirror_controllers(C, n, seed, scale=10.0):
     return ctrl
 
 
-@pytest.mark.parametrize("n", [11, 12, 16, 24, 32])
+@pytest.mark.parametrize("n", [11, 12, 13, 16, 24, 32])
 def test_spectral_weights_path_and_its_fallback(rb, n):
-    """N >= 11 evaluates from eigenvalues alone (csrc/rc_spectral.cuh).  Mirror-symmetric and double-well
+    """N >= 13 evaluates from eigenvalues alone (csrc/rc_spectral.cuh; N = 11, 12 did until the pinned-end register
+    solver took them over — they stay in the list as degenerate-spectrum cases of that solver).  Mirror-symmetric and double-well
     chains have near-coincident eigenvalue pairs with O(1) weights: the error estimate must reject those
     evaluations and the in-kernel recomputation with eigenvector rows must give the oracle's value; regular
     sweeps must (almost) never take the fallback.  End-to-end and interior in/out, replay and Philox mode."""
@@ -188,7 +189,9 @@ def test_spectral_weights_path_and_its_fallback(rb, n):
         assert np.abs(f - ref).max() < FID_TOL, (n, i, o, np.abs(f - ref).max())
         assert ref.max() > 1e-3                          # the set contains evaluations with real transfer
     nfb = rb.engine.spectral_fallbacks(reset=True)
-    assert nfb > 0                                       # the degenerate rows did exercise the fallback
+    spectral = "spectral" in rb.engine.evolution_kernel_name(n, replay=True)
+    assert spectral == (n >= 13)
+    assert (nfb > 0) if spectral else (nfb == 0)         # the degenerate rows did exercise the fallback
     # Philox mode == replay of its own normals, bit for bit, through the fallback as well
     kw = dict(seed=5, c_offset=2, b_offset=1)
     z = rb.engine.philox_normals(C, n, 3, B, **kw)
@@ -854,10 +857,12 @@ def test_get_rims_mean_only_statistic(rb, tmp_path, monkeypatch):
     assert rb_all.shape == (4, 3) and np.array_equal(rb_all[0], sim.get_rims(ctrl[0], seed=9))   # same Philox counters (c = 0)
 
 
-@pytest.mark.parametrize("n", [4, 7, 12, 20])
+@pytest.mark.parametrize("n", [2, 3, 4, 7, 8, 9, 12, 13, 20])
 def test_split_matrices_zero_and_tiny_couplings(rb, n):
     """Interior off-diagonals that are exactly zero / below the deflation threshold (the chain splits):
-    the lazy split detection of the compact eigensolver must still converge to the right answer."""
+    the lazy split detection of the eigensolvers must still converge to the right answer.  The register solver
+    (N <= 12) pins the end of its active block and hands such evaluations to the strided solver out of line
+    (ql_irregular, csrc/rc_ql.cuh); Philox mode and the fused statistics go through the same code."""
     rs = np.random.RandomState(n)
     C, B = 6, 40
     ctrl = orc.synthetic_controllers(C, n, seed=5)
@@ -873,6 +878,8 @@ def test_split_matrices_zero_and_tiny_couplings(rb, n):
     f2 = rb.engine.fidelity_mc(ctrl, [sigma], B, n, i, o, model=rb._lib.MODEL_REAL2, replay=nrm).cpu().numpy()
     ref2 = orc.fidelity_mc_replay(ctrl, [sigma], nrm, n, i, o, model=orc.MODEL_REAL2)
     assert np.abs(f2 - ref2).max() < FID_TOL
+    st = rb.engine.fidelity_stats(ctrl, [sigma], B, n, 0, n - 1, dkw_eps=0.0, model=rb._lib.MODEL_REAL2, replay=nrm).cpu().numpy()
+    assert np.abs(st[0, 0] - (1.0 - ref[0].mean(axis=1))).max() < 1e-10      # row 0 = W = 1 - mean fidelity
 
 
 def test_dense_expm_generality_path(rb):
