@@ -3,11 +3,11 @@
 set -e
 cd "$(dirname "$0")"
 JOBS=${1:-8}
-OUT=../librobchar_b200.so
-OBJ=_obj
+OUT=${RC_OUT:-../librobchar_b200.so}   # RC_OUT / RC_OBJ / RC_EXTRA_FLAGS: tuning builds next to the shipped one
+OBJ=${RC_OBJ:-_obj}
 mkdir -p $OBJ
 NVCC=${NVCC:-nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --extended-lambda -Xcompiler -fPIC -diag-suppress 550,20091"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --extended-lambda -Xcompiler -fPIC -diag-suppress 550,20091 ${RC_EXTRA_FLAGS:-}"
 cmds=()
 for n in $(seq 2 16); do
   cmds+=("$NVCC $FLAGS -DRC_NSPIN=$n -c rc_fidelity_n.cu -o $OBJ/rc_fidelity_$n.o")

@@ -40,13 +40,15 @@ struct FidArgs {
 
 __host__ __device__ constexpr int draws_per_site(int model) { return model == MODEL_COMPLEX3 ? 3 : 2; }
 
-// Algorithm of the register-resident family (N <= 8): 0 = QL accumulating the in / out eigenvector rows (default),
-// 1 = eigenvalues + spectral weights (rc_spectral.cuh, amplitude_reg_spectral) with the former as in-line
-// recomputation.  Measured on B200 (round 2, kernel only, 2.0e7 evaluations): the spectral variant LOSES at every
-// short chain — N=4 10.2e9 vs 11.0e9, N=5 7.14 vs 7.54, N=6 5.37 vs 5.70, N=7 4.18 vs 4.29, N=8 3.40 vs 3.41
-// evals/s: below N ~ 10 the N(N-1) weight products and the per-eigenvalue reciprocal / error estimate (kept as
-// loops to protect the instruction cache) cost more than the 8 FP64 per rotation they save, and the footprint
-// argument of the shared-memory family does not apply to registers.  Kept for tuning builds only.
+// Algorithm of the register-resident family: 0 = QL accumulating the in / out eigenvector rows (default),
+// 1 = eigenvalues + spectral weights (rc_spectral.cuh, amplitude_reg_spectral) with the former as out-of-line
+// recomputation.  Measured on B200 twice (kernel only, 2.0e7 evaluations), and the spectral variant LOSES at every
+// short chain both times.  Block-at-0 solvers (first half of round 2): N=4 10.2e9 vs 11.0e9, N=5 7.14 vs 7.54,
+// N=6 5.37 vs 5.70, N=7 4.18 vs 4.29, N=8 3.40 vs 3.41 evals/s.  Pinned-end solvers (second half): N=4 10.8e9 vs
+// 11.9e9, N=5 7.67 vs 8.49, N=6 5.96 vs 6.56, N=7 4.67 vs 5.09, N=8 3.85 vs 4.06, N=9 3.04 vs 3.15, N=10 2.62 vs
+// 2.67: the N(N-1) weight products and the per-eigenvalue reciprocal / error estimate (kept as loops to protect the
+// instruction cache) cost more than the 8 FP64 per rotation they save, and above N = 12 the 3N-double shared-memory
+// row caps the CTA at 512 lanes, where the eigenvector form fits as well.  Kept for tuning builds only.
 #ifndef RC_REG_SPECTRAL
 #define RC_REG_SPECTRAL 0
 #endif

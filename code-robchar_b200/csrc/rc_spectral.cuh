@@ -301,6 +301,38 @@ struct QlSweepValues {
     }
 };
 
+#if RC_QL_PINNED_END
+// QlChain of rc_ql.cuh without the eigenvector rows (21 FP64 per slot)
+template <int N, int I>
+struct QlChainValues {
+    static RC_HD void run(double (&d)[N], double (&e)[N], double s, double c, int L, double tiny, int tolhi, int& rmin,
+                          QlTail& t) {
+        const double g = e[I + 1];
+        const double f = s * e[I];
+        const double b = c * e[I];
+        const double h = fma(f, f, fma(g, g, tiny));
+        const double rinv = rc_rsqrt(h);
+        const double r = h * rinv;
+        e[I + 1] = r;
+        rmin = hi_word(r) < rmin ? hi_word(r) : rmin;
+        s = f * rinv;
+        c = g * rinv;
+        const double gg = d[I + 1];
+        const double r2 = fma(d[I] - gg, s, (2.0 * c) * b);
+        const double p = s * r2;
+        d[I + 1] = gg + p;
+        e[I] = c * r2 - b;
+        d[I] = d[I] - p;
+        if constexpr (I == 0) {
+            ql_tail<N, 0>(d, e, tolhi, t);
+        } else {
+            if (L == I) ql_tail<N, I>(d, e, tolhi, t);
+            else QlChainValues<N, I - 1>::run(d, e, s, c, L, tiny, tolhi, rmin, t);
+        }
+    }
+};
+#endif
+
 template <int N>
 RC_HD bool amplitude_reg_spectral(double (&d)[N], double (&e)[N], int in, int out, double T, double* scratch, int sstride,
                                   double& re_out, double& im_out) {
@@ -324,6 +356,49 @@ RC_HD bool amplitude_reg_spectral(double (&d)[N], double (&e)[N], int in, int ou
     const double tol = DBL_EPSILON * anorm;
     const int tolhi = threshold_hi(tol);
     const double tiny = fmin(tol, 1e-280);
+#if RC_QL_PINNED_END
+    // eigenvalues by the pinned-end chase of rc_ql.cuh (active block [L, N-1], nothing moves on deflation),
+    // without the eigenvector rows; an evaluation with a negligible interior coupling is left to the caller's
+    // recomputation (fidelity_reg_compact handles it), like a rejected estimate
+    {
+        int emin = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < N - 1; ++k) { const int h = hi_word(e[k]) & 0x7fffffff; emin = h < emin ? h : emin; }
+        int L = emin < tolhi ? N : 0, it = 0;
+        double g = wilkinson_g(d[0], d[1], e[0], d[N - 1]);
+        while (L < N - 1 && it <= QL_MAX_SWEEPS) {
+            ++it;
+            int rmin = 0x7fffffff;
+            QlTail t;
+            {
+                constexpr int I = N - 2;
+                const double b = e[I];
+                const double h = fma(b, b, fma(g, g, tiny));
+                const double rinv = rc_rsqrt(h);
+                const double s = b * rinv;
+                const double c = g * rinv;
+                const double gg = d[I + 1];
+                const double r2 = fma(d[I] - gg, s, (2.0 * c) * b);
+                const double p = s * r2;
+                d[I + 1] = gg + p;
+                e[I] = c * r2 - b;
+                d[I] = d[I] - p;
+                if constexpr (I == 0) {
+                    ql_tail<N, 0>(d, e, tolhi, t);
+                } else {
+                    if (L == I) ql_tail<N, I>(d, e, tolhi, t);
+                    else QlChainValues<N, I - 1>::run(d, e, s, c, L, tiny, tolhi, rmin, t);
+                }
+            }
+            if (t.defl) { ++L; it = 0; }
+            if (rmin < tolhi) L = N;
+            g = wilkinson_g(t.dl, t.dl1, t.el, d[N - 1]);
+        }
+        if (L != N - 1) return false;
+#pragma unroll
+        for (int k = 0; k < N; ++k) RC_S(k) = d[k];
+    }
+#else
     int nact = N, ndone = 0, it = 0, rmin = 0;
     while (nact > 1 && it <= QL_MAX_SWEEPS) {
         if (negligible_hi(e[0], tolhi)) {
@@ -353,6 +428,7 @@ RC_HD bool amplitude_reg_spectral(double (&d)[N], double (&e)[N], int in, int ou
     }
     if (nact > 1) return false;
     RC_S(ndone) = d[0];
+#endif
     // weights: loops, not unrolled (the hot code of the register kernels has to stay inside the instruction cache)
     const double cgap = (double)(N - 1) * 4.0 * DBL_EPSILON * anorm;
     const int na = a, nb = N - 1 - b;
@@ -416,21 +492,30 @@ RC_HD bool amplitude_reg_spectral(double (&d)[N], double (&e)[N], int in, int ou
 #undef RC_S
 }
 
-// Fidelity with the in-line recomputation: d / e are restored from the scratch row and handed to the
-// eigenvector-accumulating solver when the spectral result is rejected.
+// Recomputation of a rejected evaluation with the eigenvector-accumulating solver, OUT OF LINE (its 4N live doubles
+// must not set the register allocation of the spectral path): d / e are restored from the scratch row.
+template <int N>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+double fidelity_reg_recompute(double* scratch, int sstride, int in, int out, double T, int* fail) {
+    double d[N], e[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        d[k] = scratch[(size_t)(N + k) * sstride];
+        e[k] = k < N - 1 ? scratch[(size_t)(2 * N + k) * sstride] : 0.0;
+    }
+    return fidelity_reg_compact<N>(d, e, in, out, T, scratch, sstride, fail);
+}
+
 template <int N>
 RC_HD double fidelity_reg_spectral(double (&d)[N], double (&e)[N], int in, int out, double T, double* scratch, int sstride,
                                    int* fail, int* recomputed) {
     double re, im;
     *fail = 0;
     if (amplitude_reg_spectral<N>(d, e, in, out, T, scratch, sstride, re, im)) return fma(re, re, im * im);
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        d[k] = scratch[(size_t)(N + k) * sstride];
-        e[k] = k < N - 1 ? scratch[(size_t)(2 * N + k) * sstride] : 0.0;
-    }
     *recomputed = 1;
-    return fidelity_reg_compact<N>(d, e, in, out, T, scratch, sstride, fail);
+    return fidelity_reg_recompute<N>(scratch, sstride, in, out, T, fail);
 }
 
 }  // namespace rc

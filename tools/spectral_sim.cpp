@@ -44,7 +44,12 @@ int main(int argc, char** argv) {
             case 6: run_reg<6>(fi, in, out, count); break;
             case 7: run_reg<7>(fi, in, out, count); break;
             case 8: run_reg<8>(fi, in, out, count); break;
-            default: fprintf(stderr, "reg variant: N = 4..8\n"); return 2;
+            case 9: run_reg<9>(fi, in, out, count); break;
+            case 10: run_reg<10>(fi, in, out, count); break;
+            case 12: run_reg<12>(fi, in, out, count); break;
+            case 13: run_reg<13>(fi, in, out, count); break;
+            case 16: run_reg<16>(fi, in, out, count); break;
+            default: fprintf(stderr, "reg variant: N = 4..10, 12, 13, 16\n"); return 2;
         }
         return 0;
     }
