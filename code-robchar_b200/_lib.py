@@ -97,6 +97,8 @@ _SIGNATURES = {
     "rc_dense_fidelity_mc_workspace_bytes": (_sz, [_i32, _i64]),
     "rc_dense_fidelity_mc": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _i32, _u64, _i64, _i64, _vp, _vp,
                                        _vp, _sz, _vp]),
+    "rc_directional_fidelity_mc": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _i32, _u64, _i64, _i64, _vp, _vp,
+                                             _vp, _vp, _sz, _vp]),
     "rc_expm_batch": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "rc_fp64_peak_tflops": (C.c_int, [_vp, _vp]),
 }

@@ -137,6 +137,37 @@ def dense_fidelity_mc(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: in
     return out
 
 
+def directional_fidelity_mc(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, *, zz: bool = False,
+                            ring: bool = False, seed: int = 0, c_offset: int = 0, b_offset: int = 0, replay=None, out=None,
+                            return_draws: bool = False, tile: int = 1 << 17):
+    """Fidelity tensor [S][C][B] of a sweep under directional_perturbation (noise_model.py:150-201) through
+    rc_directional_fidelity_mc.  replay: [S][C][B][3] = (direction index, n0, n1) with standard normals — what
+    np.random.randint(0, 3N) and rng(size=2) / sigma give upstream — or None (in-kernel Philox draws;
+    return_draws=True also returns the [S][C][B][3] draws that were used)."""
+    dev = require_cuda()
+    ctrl = _f64(ctrl, dev)
+    sigmas = _f64(sigmas, dev).reshape(-1)
+    if ctrl.dim() != 2 or ctrl.shape[1] != nspin + 1:
+        raise ValueError(f"ctrl must be [C][{nspin + 1}], got {tuple(ctrl.shape)}")
+    Cn, S = ctrl.shape[0], sigmas.shape[0]
+    if replay is not None:
+        replay = _f64(replay, dev)
+        if replay.numel() != S * Cn * B * 3:
+            raise ValueError("replay must hold S*C*B*3 values: (direction index, n0, n1) per evaluation")
+    if out is None:
+        out = torch.empty((S, Cn, B), dtype=torch.float64, device=dev)
+    draws = torch.empty((S, Cn, B, 3), dtype=torch.float64, device=dev) if (return_draws and replay is None) else None
+    total = S * Cn * B
+    wb = lib().rc_dense_fidelity_mc_workspace_bytes(nspin, max(1, min(tile, total)))
+    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+    check(lib().rc_directional_fidelity_mc(_ptr(ctrl), Cn, nspin, inspin, outspin, _ptr(sigmas), S, B, int(bool(zz)),
+                                           int(bool(ring)), C.c_uint64(seed & (2**64 - 1)), c_offset, b_offset,
+                                           _ptr(replay), _ptr(out), _ptr(draws), _ptr(ws), wb, _stream()))
+    if return_draws:
+        return out, (replay.reshape(S, Cn, B, 3) if replay is not None else draws)
+    return out
+
+
 def fidelity_mc_stats(ctrl, sigmas, B: int, nspin: int, inspin: int, outspin: int, *, dkw_eps: float = 0.0,
                       model: int = MODEL_COMPLEX3, zz: bool = False, seed: int = 0, c_offset: int = 0, b_offset: int = 0,
                       replay=None, out=None, counters: Counters | None = None, check: bool = True):

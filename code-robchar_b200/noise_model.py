@@ -158,3 +158,17 @@ class directional_perturbation(noise_model_base):
         z[pert_index] = nval[0] + 1j * nval[1]
         z[pert_index2] = nval[0] - 1j * nval[1]
         return z
+
+    def evaluate_noisy_fidelity_batch(self, X, draws: int = 1, ham_noisy: bool = True, noises=None, seed: int = 0,
+                                      as_numpy: bool = True, replay=None):
+        """All (noise level, controller, draw) fidelities of a directional-perturbation sweep in one call
+        (rc_directional_fidelity_mc): upstream evaluates them one at a time (noise_model.py:98-109 with :165-201).
+        replay: optional [S][C][draws][3] = (direction index, n0, n1), the values np.random.randint(0, 3N) and
+        rng(size=2) / sigma return upstream; default: in-kernel Philox draws.  Returns [S][C][draws]."""
+        if noises is None:
+            noises = [self.rng.args.get("scale", self.noise) if ham_noisy else 0.0]
+        sig = np.asarray(noises, dtype=np.float64) if ham_noisy else np.zeros(len(noises))
+        out = engine.directional_fidelity_mc(np.asarray(X, dtype=np.float64).reshape(-1, self.Nspin + 1), sig, draws,
+                                             self.Nspin, self.inspin, self.outspin, zz=self.zz, ring=self.topo == "ring",
+                                             seed=seed, replay=replay)
+        return out.cpu().numpy() if as_numpy else out

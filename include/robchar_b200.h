@@ -341,6 +341,21 @@ int rc_dense_fidelity_mc(const double* ctrl_dev, int64_t C, int nspin, int inspi
                          const double* replay_dev, double* fids_dev, void* workspace_dev, size_t workspace_bytes,
                          void* stream);
 
+/* Batched Monte-Carlo sweep under directional_perturbation (noise_model.py:150-201): per evaluation ONE of the 3N
+ * `directions` (noise_model.py:155-163, same order) is drawn and the pair z[i][j] = v, z[j][i] = conj(v),
+ * v = sigma (n0 + i n1), is added to H (noise_model.py:191-199; on a diagonal direction H[i][i] becomes complex, so the
+ * evaluation goes through the dense exponential like rc_dense_fidelity_mc).  The reference evaluates these one call at
+ * a time (noise_model.py:98-109).  replay_dev: [S][C][B][3] = (direction index as a double, n0, n1) with n0, n1 STANDARD
+ * normals — exactly what np.random.randint(0, 3N) and rng(size=2) / sigma return upstream — or NULL: the index comes from
+ * Philox block sub-stream 127 of the evaluation's (seed, sigma, controller, draw) counter ((word * 3N) >> 32) and the
+ * normals are its primary-stream draws 0 and 1; draws_out_dev (optional, Philox mode) receives the [S][C][B][3] draws
+ * that were used, so that a Philox sweep can be replayed through the reference / the oracle.  An index outside
+ * [0, 3N) gives a NaN fidelity.  fids [S][C][B]; workspace as for rc_dense_fidelity_mc. */
+int rc_directional_fidelity_mc(const double* ctrl_dev, int64_t C, int nspin, int inspin, int outspin,
+                               const double* sigma_dev, int S, int64_t B, int zz, int ring, uint64_t seed, int64_t c_offset,
+                               int64_t b_offset, const double* replay_dev, double* fids_dev, double* draws_out_dev,
+                               void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* FP64 FMA throughput micro-benchmark of the current device (TFLOP/s, 2 flops per DFMA); used as
  * the roofline denominator of the evolution kernel. */
 int rc_fp64_peak_tflops(double* tflops, void* stream);

@@ -882,6 +882,61 @@ def test_split_matrices_zero_and_tiny_couplings(rb, n):
     assert np.abs(st[0, 0] - (1.0 - ref[0].mean(axis=1))).max() < 1e-10      # row 0 = W = 1 - mean fidelity
 
 
+def test_directional_perturbation_batched_sweep(rb):
+    """rc_directional_fidelity_mc: the batched form of directional_perturbation.evaluate_noisy_fidelity
+    (noise_model.py:98-109 with :150-201).  (1) the reference's own seeded run, replayed; (2) oracle on random draws
+    covering every direction, several chain lengths, ring and Z term; (3) Philox mode == replay of the draws it
+    reports, direction index uniform over the 3N directions, normals standard."""
+    g = load_golden("dense_path.npz")
+    n, sigma = 5, 0.1
+    np.random.seed(42)                                   # noise_model.py:189-193 consumes randint(0, 3N), then normal(size=2)
+    d = np.empty((40, 3))
+    for k in range(40):
+        d[k, 0] = np.random.randint(low=0, high=3 * n)
+        d[k, 1:] = np.random.normal(scale=sigma, size=2) / sigma
+    dp = rb.directional_perturbation(Nspin=n, inspin=0, outspin=4, noise=sigma)
+    got = dp.evaluate_noisy_fidelity_batch(g["dir_x"], draws=40, replay=d[None, None])[0, 0]
+    assert np.abs(got - g["dir_noisy"]).max() < FID_TOL
+    rs = np.random.RandomState(3)
+    for (nn, i, o, ring, zz) in [(2, 0, 1, False, False), (3, 0, 2, False, False), (7, 0, 6, False, False), (6, 1, 4, True, False),
+                                 (9, 0, 8, False, True), (16, 0, 15, False, False)]:
+        C, B = 4, 3 * nn + 5
+        ctrl = orc.synthetic_controllers(C, nn, seed=nn)
+        sig = np.array([0.0, 0.05, 0.3])
+        dr = np.empty((3, C, B, 3))
+        dr[..., 0] = np.arange(B) % (3 * nn)            # every direction
+        dr[..., 1:] = rs.standard_normal((3, C, B, 2))
+        f = rb.engine.directional_fidelity_mc(ctrl, sig, B, nn, i, o, ring=ring, zz=zz, replay=dr).cpu().numpy()
+        ref = orc.directional_fidelity_mc_replay(ctrl, sig, dr, nn, i, o, zz=zz, topo="ring" if ring else "chain")
+        # a complex diagonal entry makes the evolution non-unitary: "fidelities" reach 1e4 at sigma = 0.3, T = 30
+        assert (np.abs(f - ref) / np.maximum(1.0, np.abs(ref))).max() < FID_TOL, (nn, ring, zz, np.abs(f - ref).max())
+    bad = np.array([[[[-1.0, 0, 0], [15.0, 0, 0], [2.5, 0, 0], [np.nan, 0, 0], [3.0, 0.1, 0.2]]]])
+    fb = rb.engine.directional_fidelity_mc(g["dir_x"][None], [sigma], 5, n, 0, 4, replay=bad).cpu().numpy()[0, 0]
+    assert np.isnan(fb[:4]).all() and np.isfinite(fb[4])
+    # Philox mode
+    C, B = 50, 400
+    ctrl = orc.synthetic_controllers(C, n, seed=8)
+    kw = dict(seed=77, c_offset=3, b_offset=9)
+    fa, dz = rb.engine.directional_fidelity_mc(ctrl, [0.05, 0.1], B, n, 0, 4, return_draws=True, **kw)
+    fr = rb.engine.directional_fidelity_mc(ctrl, [0.05, 0.1], B, n, 0, 4, replay=dz)
+    assert torch.equal(fa, fr)
+    dz = dz.cpu().numpy()
+    sub = (slice(None), slice(0, 3), slice(0, 20))
+    ref = orc.directional_fidelity_mc_replay(ctrl[:3], np.array([0.05, 0.1]), dz[sub], n, 0, 4)
+    assert np.abs(fa.cpu().numpy()[sub] - ref).max() < FID_TOL
+    k = dz[..., 0].reshape(-1)
+    assert np.array_equal(k, np.floor(k)) and k.min() == 0 and k.max() == 3 * n - 1
+    cnt = np.bincount(k.astype(int), minlength=3 * n)
+    chi2 = ((cnt - k.size / (3 * n)) ** 2 / (k.size / (3 * n))).sum()
+    assert chi2 < 45.0                                   # 14 degrees of freedom: P(chi2 > 45) ~ 4e-5
+    z = dz[..., 1:].reshape(-1)
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.02
+    # sharding: the draws depend on the global (sigma, controller, draw) indices only
+    fs = rb.engine.directional_fidelity_mc(ctrl[10:20], [0.05, 0.1], 100, n, 0, 4, seed=77, c_offset=13, b_offset=59)
+    assert torch.equal(fs, fa[:, 10:20, 50:150])
+    assert rb.engine.directional_fidelity_mc(ctrl[:0], [0.05], 4, n, 0, 4).shape == (1, 0, 4)
+
+
 def test_dense_expm_generality_path(rb):
     """rc_expm_batch vs scipy.linalg.expm; ring topology, directional perturbation (incl. its non-Hermitian
     complex-diagonal draws) and the analytic gradient vs the unmodified reference."""

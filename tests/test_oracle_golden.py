@@ -159,3 +159,27 @@ def test_arim_golden():
     g = load_golden("objective_arim.npz")
     for j in range(g["arim_rims"].shape[0]):
         assert abs(orc.arim(g["arim_rims"][j]) - g["arim_centre"][j]) < 1e-15
+
+
+def _directional_draws_of_reference_run(seed, n, sigma, count):
+    """The draws directional_perturbation.perturbation (noise_model.py:165-201) consumes per evaluation under
+    np.random.seed(seed): np.random.randint(0, 3N), then rng(size=2) = np.random.normal(scale=sigma, size=2)."""
+    np.random.seed(seed)
+    d = np.empty((count, 3))
+    for k in range(count):
+        d[k, 0] = np.random.randint(low=0, high=3 * n)
+        d[k, 1:] = np.random.normal(scale=sigma, size=2) / sigma
+    return d
+
+
+def test_directional_oracle_against_reference_run():
+    """The oracle's directional-perturbation sweep on the replayed numpy stream == the unmodified reference's
+    directional_perturbation.evaluate_noisy_fidelity under the same seed (tests/golden/make_golden.py:make_dense_path)."""
+    g = load_golden("dense_path.npz")
+    n, sigma = 5, 0.1
+    ref = g["dir_noisy"]
+    d = _directional_draws_of_reference_run(42, n, sigma, len(ref))
+    got = orc.directional_fidelity_mc_replay(g["dir_x"][None, :], np.array([sigma]), d[None, None], n, 0, 4)[0, 0]
+    assert np.abs(got - ref).max() < 1e-12
+    assert set(d[:, 0].astype(int)) & {0, 1, 3, 6, 9}            # the run contains complex-diagonal (non-Hermitian) draws
+    assert orc.directional_directions(5)[:5] == [(0, 0), (4, 4), (1, 0), (1, 1), (1, 2)] and len(orc.directional_directions(2)) == 6
