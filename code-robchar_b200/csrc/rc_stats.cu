@@ -355,6 +355,112 @@ __global__ void __launch_bounds__(256, E <= 4 ? RC_STATS_MINB : (E <= 8 ? 3 : 2)
     }
 }
 
+// Short segments (B <= 128), round 2: G = 4 lanes per segment instead of a whole warp.  The warp-per-segment kernel
+// above spends ~1100 warp-instructions per 100-sample segment (four samples per lane, then seven 5-step shuffle
+// reductions, three divisions and a square root executed for ONE segment per warp): 0.29 ms for the 2.1e5 segments of
+// the paper sweep, 9 % of the HBM rate.  Here a warp works on 8 segments at once: lane q of a group owns samples
+// q, q+4, ... (consecutive lanes read consecutive doubles: every 32-byte sector is used in full), accumulates them in
+// ONE pass — sums of y = v - shift and y^2 about the segment's first sample (the fused kernels' form; m2 = syy - sy^2/n),
+// the six threshold counts in 8-bit fields of two integers, minimum, NaN / illegal flags — and the group reduces with
+// two xor-shuffle steps; lanes 0..2 of the group finish one variant (centre, upper, lower) each.  ~170
+// warp-instructions per segment.  EXACT: (E-1)*G < B, only the last element of a lane can be out of range.
+template <int G, int E, bool EXACT>
+__global__ void __launch_bounds__(256, 2) stats_unsorted_group_kernel(const double* __restrict__ fids, long long nseg, int B,
+                                                                   double eps, long long stat_stride,
+                                                                   double* __restrict__ stats, unsigned long long* illegal) {
+    constexpr int SPW = 32 / G;
+    const int lane = threadIdx.x & 31, q = lane & (G - 1), grp = lane / G;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const double nB = (double)B;
+    for (long long seg0 = warp0 * SPW; seg0 < nseg; seg0 += nwarps * SPW) {
+        const long long seg = seg0 + grp;
+        const bool live = seg < nseg;
+        const double* src = fids + (live ? seg : seg0) * (long long)B;
+        double f[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int idx = j * G + q;
+            f[j] = ((EXACT && j < E - 1) || idx < B) ? __ldcs(src + idx) : 1.0;
+        }
+        // shift = the segment's first sample (lane 0 of the group), per variant.  NaN samples are flagged and the segment's
+        // W / std / worst case become NaN at the end; they stay out of the threshold counts as in numpy (a NaN compares false)
+        const double s0 = __shfl_sync(0xffffffffu, f[0], grp * G);
+        // clip to [0, 1] on the bit pattern (6 integer instructions; the compiler turns compare + select on doubles
+        // back into its 7-instruction fmin / fmax sequence): negative -> +0, high word >= that of 1.0 -> exactly 1.0
+        // (a positive NaN becomes 1, a negative one 0: NaN segments are replaced by NaN at the end anyway)
+        auto clip = [](double t) {
+            int hi = __double2hiint(t), lo = __double2loint(t);
+            const int keep = ~(hi >> 31);
+            hi &= keep; lo &= keep;
+            const bool ge1 = hi >= 0x3FF00000;
+            return __hiloint2double(ge1 ? 0x3FF00000 : hi, ge1 ? 0 : lo);
+        };
+        const double sh[3] = {s0, clip(s0 - eps), clip(s0 + eps)};
+        double sy[3] = {0.0, 0.0, 0.0}, syy[3] = {0.0, 0.0, 0.0};
+        unsigned c95 = 0, c98 = 0;       // 8-bit fields (B <= 128): centre, upper, lower
+        double mn = INFINITY;
+        unsigned flags = 0;              // low half: illegal samples, high half: NaN samples
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            if ((EXACT && j < E - 1) || j * G + q < B) {
+                const double x = f[j], xm = x - eps, xp = x + eps;
+                const double v[3] = {x, clip(xm), clip(xp)};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double y = v[k] - sh[k];
+                    sy[k] += y;
+                    syy[k] = fma(y, y, syy[k]);
+                }
+                // clip to [0, 1] does not change a comparison with a threshold inside (0, 1)
+                if (x >= 0.95) c95 += 1u;
+                if (xm >= 0.95) c95 += 0x100u;
+                if (xp >= 0.95) c95 += 0x10000u;
+                if (x >= 0.98) c98 += 1u;
+                if (xm >= 0.98) c98 += 0x100u;
+                if (xp >= 0.98) c98 += 0x10000u;
+                mn = fmin(mn, x);
+                if (x != x) flags += 0x10000u;
+                if (fabs(x - 1e-8) > 1.0) flags += 1u;   // check_fidtype (wd_sortof_fast_implementation.py:23)
+            }
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                sy[k] += __shfl_xor_sync(0xffffffffu, sy[k], o);
+                syy[k] += __shfl_xor_sync(0xffffffffu, syy[k], o);
+            }
+            c95 += __shfl_xor_sync(0xffffffffu, c95, o);
+            c98 += __shfl_xor_sync(0xffffffffu, c98, o);
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            flags += __shfl_xor_sync(0xffffffffu, flags, o);
+        }
+        const unsigned bad = (live && q == 0) ? (flags & 0xffffu) : 0u;
+        const unsigned badw = __reduce_add_sync(0xffffffffu, bad);
+        if (badw && illegal && lane == 0) atomicAdd(illegal, (unsigned long long)badw);
+        if (live && q < 3) {
+            const int k = q;
+            const bool anynan = (flags >> 16) != 0 || s0 != s0;
+            const double syk = k == 0 ? sy[0] : (k == 1 ? sy[1] : sy[2]);
+            const double syyk = k == 0 ? syy[0] : (k == 1 ? syy[1] : syy[2]);
+            const double shk = k == 0 ? sh[0] : (k == 1 ? sh[1] : sh[2]);
+            const double a95 = (double)((c95 >> (8 * k)) & 0xffu);
+            const double a98 = (double)((c98 >> (8 * k)) & 0xffu);
+            const double mk = k == 0 ? mn : clip(mn + (k == 1 ? -eps : eps));
+            const double svk = fma(nB, shk, syk);                        // sum of the samples
+            const double m2 = fmax(syyk - syk * syk / nB, 0.0);
+            double* out = stats + seg;
+            // W = mean(1 - v) = (B - sum v) / B
+            out[(ST_W + k) * stat_stride] = anynan ? NAN : (nB - svk) / nB;
+            out[(ST_Q95 + k) * stat_stride] = -1.0 * (a95 / nB);
+            out[(ST_Q98 + k) * stat_stride] = -1.0 * (a98 / nB);
+            out[(ST_STD + k) * stat_stride] = anynan ? NAN : sqrt(m2 / nB);
+            out[(ST_WC + k) * stat_stride] = anynan ? NAN : -mk;
+        }
+    }
+}
+
 // One CTA per (long) segment.
 __global__ void __launch_bounds__(256) stats_unsorted_block_kernel(const double* __restrict__ fids, long long nseg, long long B,
                                                                    double eps, long long stat_stride,
@@ -437,6 +543,32 @@ static cudaError_t launch_stats_unsorted_warp(const double* fids, long long nseg
     return cudaGetLastError();
 }
 
+template <int G, int E, bool EXACT>
+static cudaError_t launch_stats_unsorted_group(const double* fids, long long nseg, int B, double eps, long long stride,
+                                               double* stats, unsigned long long* illegal, int sm, cudaStream_t st) {
+    int occ = 0;
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stats_unsorted_group_kernel<G, E, EXACT>, 256, 0);
+    if (err != cudaSuccess) return err;
+    if (occ < 1) occ = 1;
+    long long grid = (long long)sm * occ;
+    const long long need = (nseg + 8 * (32 / G) - 1) / (8 * (32 / G));
+    if (grid > need) grid = need;
+    stats_unsorted_group_kernel<G, E, EXACT><<<(unsigned)grid, 256, 0, st>>>(fids, nseg, B, eps, stride, stats, illegal); rc::note_launch();
+    return cudaGetLastError();
+}
+template <int E>
+static cudaError_t launch_stats_unsorted_quad(const double* fids, long long nseg, int B, double eps, long long stride,
+                                              double* stats, unsigned long long* illegal, int sm, cudaStream_t st) {
+    return (E - 1) * 4 < B ? launch_stats_unsorted_group<4, E, true>(fids, nseg, B, eps, stride, stats, illegal, sm, st)
+                           : launch_stats_unsorted_group<4, E, false>(fids, nseg, B, eps, stride, stats, illegal, sm, st);
+}
+
+static bool stats_warp_per_segment() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RC_STATS_WARP"); v = (e && atoi(e)) ? 1 : 0; }
+    return v == 1;
+}
+
 int stats_unsorted_impl(const double* fids_dev, int64_t nseg, int64_t B, double dkw_eps, double* stats_dev,
                         int64_t stat_stride, unsigned long long* illegal_dev, cudaStream_t st) {
     if (nseg < 0 || B < 1) return set_error(RC_ERR_BAD_ARG, "rc_stats_unsorted: nseg=%lld B=%lld", (long long)nseg, (long long)B);
@@ -449,6 +581,12 @@ int stats_unsorted_impl(const double* fids_dev, int64_t nseg, int64_t B, double 
         long long grid = nseg < (long long)sm * 8 ? nseg : (long long)sm * 8;
         stats_unsorted_block_kernel<<<(unsigned)grid, 256, 0, st>>>(fids_dev, nseg, B, dkw_eps, stat_stride, stats_dev, illegal_dev); rc::note_launch();
         err = cudaGetLastError();
+    } else if (b <= 128 && !stats_warp_per_segment()) {
+        // four lanes per segment (RC_STATS_WARP=1 in the environment keeps the warp-per-segment kernels: A/B)
+        if (b <= 32) err = launch_stats_unsorted_quad<8>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);
+        else if (b <= 64) err = launch_stats_unsorted_quad<16>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);
+        else if (b <= 100) err = launch_stats_unsorted_quad<25>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);
+        else err = launch_stats_unsorted_quad<32>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);
     } else if (b <= 32) err = launch_stats_unsorted_warp<1>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);
     else if (b <= 64) err = launch_stats_unsorted_warp<2>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);
     else if (b <= 128) err = launch_stats_unsorted_warp<4>(fids_dev, nseg, b, dkw_eps, stat_stride, stats_dev, illegal_dev, sm, st);

@@ -762,7 +762,10 @@ def test_objective_host_entry_point(rb, n, model, zz):
         f2, st = rb.engine.objective_host(x, rows, n, 0, n - 1, model=model, zz=zz, want_stats=True, dkw_eps=0.02)
         assert np.array_equal(f2, f)
         ref = rb.engine.stats_unsorted(torch.as_tensor(f).cuda().reshape(1, -1), 0.02).cpu().numpy().reshape(-1)
-        assert np.array_equal(st, ref)
+        # the objective kernel reduces its m values like the warp-per-segment statistics kernel, rc_stats_unsorted uses
+        # four lanes per segment for m <= 128: same values up to summation order; counts and the minimum exactly
+        assert np.array_equal(st[3:9], ref[3:9]) and np.array_equal(st[12:], ref[12:])
+        assert np.abs(st - ref).max() < 1e-13
         assert abs((1.0 - st[0]) - f.mean()) < 1e-14 and abs(st[0] - orc.wd_from_ideal(f.copy())) < 1e-13
     f0 = rb.engine.objective_host(x, None, n, 0, n - 1, model=model, zz=zz)
     assert f0.shape == (1,) and abs(f0[0] - orc.evaluate_fidelity(x, n, 0, n - 1, zz=zz)) < FID_TOL
