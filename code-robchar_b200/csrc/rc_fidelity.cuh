@@ -391,6 +391,110 @@ __device__ __forceinline__ void warp_acc_finish(const double* __restrict__ wacc,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-lane accumulation (round 2): warp_acc_pass reduces the 32 fidelities of EVERY pass across the warp (six 5-step
+// double sums, a 5-step minimum, eight ballots, lane 0's read-modify-write of the warp accumulator: ~270 warp
+// instructions per pass, 5-6 % of an N=7 evaluation).  Where the shared memory of the CTA has room for eleven more
+// doubles per lane, every lane keeps its own partial sums there for the whole item — ~70 instructions per pass, no
+// cross-lane traffic — and the warp reduces once per item (lane_acc_reduce).  The grouping of the draws into the
+// partial sums depends on B only (lane = draw mod 32 within an item), so the statistics stay independent of the
+// controller sharding.
+// lane slots: sy[3] syy[3] | c95[3] c98[3] as six u32 | mn | n, nan as two u32.  While an item accumulates, the warp's
+// slots WA_C95.. hold the three shifts.
+// ---------------------------------------------------------------------------------------------
+#ifndef RC_FUSED_LANE_ACC
+#define RC_FUSED_LANE_ACC 1
+#endif
+constexpr int LACC_DOUBLES = 11;
+__host__ __device__ constexpr bool fused_lane_acc(int model, int n) {
+    return RC_FUSED_LANE_ACC != 0 &&
+           (long long)reg_cta_threads(n, false) * (reg_row_doubles(model, n) + LACC_DOUBLES) * 8 + 16384 + 6144 <= 232448;
+}
+
+// clip to [0, 1] on the bit pattern (6 integer instructions instead of the 14 of fmin(fmax())): negative -> +0, high
+// word >= that of 1.0 -> exactly 1.0 (NaN: flagged by the caller, the item's statistics become NaN)
+__device__ __forceinline__ double clip01_bits(double t) {
+    int hi = __double2hiint(t), lo = __double2loint(t);
+    const int keep = ~(hi >> 31);
+    hi &= keep; lo &= keep;
+    const bool ge1 = hi >= 0x3FF00000;
+    return __hiloint2double(ge1 ? 0x3FF00000 : hi, ge1 ? 0 : lo);
+}
+
+// All 32 lanes call, converged; `valid` lanes hold a fidelity.  `first`: first pass of the item (lane 0 is valid).
+__device__ __forceinline__ void lane_acc_pass(double* __restrict__ lacc, double* __restrict__ wacc, bool first, bool valid,
+                                              double f, double eps) {
+    if (first) {
+        const int lane = threadIdx.x & 31;
+        __syncwarp();
+        const double f0 = __shfl_sync(0xffffffffu, f, 0);
+        if (lane == 0) {
+            wacc[WA_SHIFT] = f0;
+            wacc[WA_C95] = f0; wacc[WA_C95 + 1] = clip01_bits(f0 - eps); wacc[WA_C95 + 2] = clip01_bits(f0 + eps);
+        }
+#pragma unroll
+        for (int j = 0; j < LACC_DOUBLES; ++j) lacc[j] = 0.0;
+        lacc[9] = INFINITY;
+        __syncwarp();
+    }
+    if (valid) {
+        const double xm = f - eps, xp = f + eps;
+        const double v[3] = {f, clip01_bits(xm), clip01_bits(xp)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double y = v[k] - wacc[WA_C95 + k];
+            lacc[k] += y;
+            lacc[3 + k] = fma(y, y, lacc[3 + k]);
+        }
+        uint2* cnt = reinterpret_cast<uint2*>(lacc + 6);
+        uint2 c0 = cnt[0], c1 = cnt[1], c2 = cnt[2];
+        // clip to [0, 1] does not change a comparison with a threshold inside (0, 1); a NaN compares false
+        if (f >= 0.95) c0.x += 1u;
+        if (xm >= 0.95) c0.y += 1u;
+        if (xp >= 0.95) c1.x += 1u;
+        if (f >= 0.98) c1.y += 1u;
+        if (xm >= 0.98) c2.x += 1u;
+        if (xp >= 0.98) c2.y += 1u;
+        cnt[0] = c0; cnt[1] = c1; cnt[2] = c2;
+        lacc[9] = fmin(lacc[9], f);
+        uint2 nn = *reinterpret_cast<uint2*>(lacc + 10);
+        nn.x += 1u;
+        if (f != f) nn.y += 1u;
+        *reinterpret_cast<uint2*>(lacc + 10) = nn;
+    }
+}
+
+// End of an item, all 32 lanes converged: the lanes' partial sums -> the warp accumulator (fixed shuffle trees).
+__device__ __forceinline__ void lane_acc_reduce(const double* __restrict__ lacc, double* __restrict__ wacc) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    double tot[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) tot[k] = warp_sum_f64(lacc[k]);
+    const uint2* cnt = reinterpret_cast<const uint2*>(lacc + 6);
+    const uint2 c0 = cnt[0], c1 = cnt[1], c2 = cnt[2], nn = cnt[4];
+    const unsigned c[6] = {__reduce_add_sync(0xffffffffu, c0.x), __reduce_add_sync(0xffffffffu, c0.y),
+                           __reduce_add_sync(0xffffffffu, c1.x), __reduce_add_sync(0xffffffffu, c1.y),
+                           __reduce_add_sync(0xffffffffu, c2.x), __reduce_add_sync(0xffffffffu, c2.y)};
+    const unsigned n = __reduce_add_sync(0xffffffffu, nn.x), nnan = __reduce_add_sync(0xffffffffu, nn.y);
+    double mn = lacc[9];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            wacc[WA_SY + k] = tot[k];
+            wacc[WA_SYY + k] = tot[3 + k];
+            wacc[WA_C95 + k] = (double)c[k];
+            wacc[WA_C98 + k] = (double)c[3 + k];
+        }
+        wacc[WA_MN] = mn;
+        wacc[WA_N] = (double)n;
+        wacc[WA_NAN] = (double)nnan;
+    }
+    __syncwarp();
+}
+
 template <int N, int MODEL>
 __global__ void __launch_bounds__(reg_cta_threads(N, false), reg_cta_min_blocks(N, false)) fidelity_stats_reg_warp_kernel(FusedArgs g) {
     constexpr int K = draws_per_site(MODEL) * N;
@@ -403,6 +507,8 @@ __global__ void __launch_bounds__(reg_cta_threads(N, false), reg_cta_min_blocks(
     __shared__ double wacc_all[MAX_CTA_WARPS * WACC_DOUBLES];
     double* wacc = wacc_all + (threadIdx.x >> 5) * WACC_DOUBLES;
     const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    constexpr bool LACC = fused_lane_acc(MODEL, N);
+    double* lacc = smem_raw + 2 * ZIG_LAYERS + (size_t)blockDim.x * KP + (size_t)threadIdx.x * LACC_DOUBLES;   // LACC only
     const long long nitems = (long long)a.S * a.C * g.nchunks;
     const long long stride = (long long)gridDim.x * wpc;
     for (long long item = (long long)blockIdx.x * wpc + (threadIdx.x >> 5); item < nitems; item += stride) {
@@ -415,8 +521,10 @@ __global__ void __launch_bounds__(reg_cta_threads(N, false), reg_cta_min_blocks(
             const bool valid = b < b1;
             double f = 0.0;
             if (valid) f = eval_reg<N, MODEL, false>(a, s, c, b, row, kw);
-            warp_acc_pass(wacc, bt == b0, valid, f, g.eps);
+            if (LACC) lane_acc_pass(lacc, wacc, bt == b0, valid, f, g.eps);
+            else warp_acc_pass(wacc, bt == b0, valid, f, g.eps);
         }
+        if (LACC) lane_acc_reduce(lacc, wacc);
         __syncwarp();
         if (lane == 0) {
             Moments m;

@@ -42,7 +42,8 @@ template <int MODEL>
 static cudaError_t launch_fused_reg_warp(const FusedArgs& g, int sm_count, cudaStream_t st) {
     constexpr int N = RC_NSPIN;
     const int threads = reg_threads_runtime(N, false);
-    size_t smem = (size_t)threads * reg_row_doubles(MODEL, N) * sizeof(double) + sizeof(ZigEntry) * ZIG_LAYERS;
+    size_t smem = (size_t)threads * (reg_row_doubles(MODEL, N) + (fused_lane_acc(MODEL, N) ? LACC_DOUBLES : 0)) * sizeof(double) +
+                  sizeof(ZigEntry) * ZIG_LAYERS;
     auto kern = fidelity_stats_reg_warp_kernel<N, MODEL>;
     cudaError_t err;
     if (smem > 40 * 1024) {
