@@ -217,6 +217,9 @@ RC_HD double fidelity_reg(double (&d)[N], double (&e)[N], int in, int out, doubl
 #ifndef RC_QL_PINNED_END
 #define RC_QL_PINNED_END 1
 #endif
+#ifndef RC_QL_SHIFT_AT_TOP
+#define RC_QL_SHIFT_AT_TOP 1
+#endif
 #if RC_QL_PINNED_END
 // ---------------------------------------------------------------------------------------------
 // Pinned-end form (round 2, what the kernels use).  The block-at-index-0 form below pays for its
@@ -339,11 +342,20 @@ RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int ou
     // QL_MAX_SWEEPS sweeps on one eigenvalue) leaves the loop through its condition with L < N - 1.
     int L = emin < tolhi ? N : 0, it = 0;
     if constexpr (N >= 2) {
+#if RC_QL_SHIFT_AT_TOP
+        QlTail t;
+        t.dl = d[0]; t.dl1 = d[1]; t.el = e[0]; t.defl = false;
+        while (L < N - 1 && it <= QL_MAX_SWEEPS) {
+            // the shift of this sweep from the three numbers the previous sweep's last slot handed over (computed here
+            // rather than at the end of the trip: the trip that deflates the last pair does not pay for a shift nobody uses)
+            const double g = wilkinson_g(t.dl, t.dl1, t.el, d[N - 1]);
+#else
         double g = wilkinson_g(d[0], d[1], e[0], d[N - 1]);
         while (L < N - 1 && it <= QL_MAX_SWEEPS) {
+            QlTail t;
+#endif
             ++it;
             int rmin = 0x7fffffff;
-            QlTail t;
             {   // slot N-2: first rotation of every sweep, s = c = 1 and p = 0 folded in, its r is not stored
                 constexpr int I = N - 2;
                 const double b = e[I];
@@ -368,7 +380,9 @@ RC_HD double fidelity_reg_compact(double (&d)[N], double (&e)[N], int in, int ou
             RC_STAT(st->total_sweeps++; st->rotations += N - 1 - L;)
             if (t.defl) { ++L; it = 0; }
             if (rmin < tolhi) L = N;     // negligible interior coupling: ql_irregular takes over
+#if !RC_QL_SHIFT_AT_TOP
             g = wilkinson_g(t.dl, t.dl1, t.el, d[N - 1]);
+#endif
         }
     }
     if (L == N) {
