@@ -257,8 +257,8 @@ RC_HD bool amplitude_spectral_strided(double* d, double* e, int ld_rt, int n, do
 #undef RC_AT
 
 // ---------------------------------------------------------------------------------------------
-// Register-resident variant for the short chains (N <= 8): same single-body compact QL as
-// fidelity_reg_compact (active block pinned at index 0, deflation = register shift), without the two
+// Register-resident variant for the short chains (tuning builds, RC_REG_SPECTRAL): the solver of
+// fidelity_reg_compact (pinned-end chase by default, block-at-0 form with RC_QL_PINNED_END=0), without the two
 // eigenvector rows — 21 instead of 29 FP64 per rotation slot, half the shift moves, 2N fewer live
 // registers — then the spectral weights from the eigenvalues parked in the lane's scratch row.
 // scratch: >= 3N doubles per lane, element k at scratch[k * sstride]:

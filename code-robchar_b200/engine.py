@@ -222,7 +222,7 @@ def evolution_kernel_name(nspin: int, replay: bool = False, fused: bool = False)
 
 
 def spectral_fallbacks(reset: bool = False) -> int:
-    """Evaluations of the N >= 11 kernels that were recomputed with accumulated eigenvector rows because the
+    """Evaluations of the N >= 13 kernels that were recomputed with accumulated eigenvector rows because the
     spectral-weights error estimate rejected them (rc_spectral_fallbacks), since the last reset."""
     require_cuda()
     v = C.c_ulonglong(0)

@@ -75,11 +75,11 @@ int rc_fidelity_mc_stats(const double* ctrl_dev, int64_t C, int nspin, int inspi
                          double* fids_dev, double* stats_dev, unsigned long long* nonconv_dev,
                          unsigned long long* illegal_dev, void* stream);
 
-/* Name of the evolution kernel the launcher picks for this chain length / mode (register family N <= 8,
+/* Name of the evolution kernel the launcher picks for this chain length / mode (register family N <= 12,
  * shared-memory family above, eigenvector rows or spectral weights): what a benchmark labels its roofline with. */
 int rc_evolution_kernel_name(int nspin, int replay, int fused, char* buf, size_t buf_bytes);
 
-/* Chain lengths above the register-resident range (N >= 11) evaluate <out|exp(-iHT)|in> from the eigenvalues
+/* Chain lengths above the register-resident range (N >= 13) evaluate <out|exp(-iHT)|in> from the eigenvalues
  * alone (characteristic-polynomial weights, csrc/rc_spectral.cuh) and recompute an evaluation with accumulated
  * eigenvector rows when its a-posteriori error estimate exceeds 1e-11 (near-coincident eigenvalues with large
  * weights).  This diagnostic returns how many evaluations took that fallback on the current device since the

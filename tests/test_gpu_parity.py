@@ -284,7 +284,7 @@ def test_philox_ziggurat_tails_and_bins(rb):
 @pytest.mark.parametrize("n,B", [(4, 100), (7, 1000), (8, 5000), (9, 300), (12, 700), (16, 5000), (24, 129), (29, 64), (32, 257)])
 def test_fused_statistics_every_kernel_family(rb, n, B):
     """Streaming (fused) statistics == statistics of the materialised fidelities, in Philox mode, for every
-    kernel family / CTA shape (register kernels N <= 8, shared-memory kernels above, ragged B)."""
+    kernel family / CTA shape (register kernels N <= 12, shared-memory kernels above, ragged B)."""
     ctrl = orc.synthetic_controllers(5, n, seed=n)
     sig = np.array([0.0, 0.04, 0.1])
     eps = float(orc.compute_dkw_error(0.05, B))
